@@ -1,0 +1,78 @@
+/* pai_b200 -- C-ABI of the B200-native Pix2Pix / PatchGAN / SSIM-PSNR hot path.
+ *
+ * The reference (cristianpjensen/thesis-pai-reconstruction) is pure Python/PyTorch and has no
+ * FFI of its own; every entry point below names the reference call site whose arithmetic it
+ * replaces.  The host side (thesis-pai-reconstruction_b200/pai_b200/lib.py) binds these with
+ * ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch); the library allocates
+ *     nothing persistent and never synchronises the stream
+ *   - activations / gradients: NHWC bf16, `ld` = elements between consecutive pixels (>= channels,
+ *     so a tensor may be a channel slice of a wider concat buffer)
+ *   - `stream` is a cudaStream_t passed as void*
+ *   - return 0 on success, negative on error; pai_last_error() describes the last failure of the
+ *     calling thread.  There is no CPU fallback anywhere.
+ */
+#ifndef PAI_B200_H
+#define PAI_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAI_ACT_NONE 0
+#define PAI_ACT_LEAKY 1 /* LeakyReLU(slope) */
+#define PAI_ACT_RELU 2
+#define PAI_ACT_TANH 3
+
+#define PAI_DTYPE_F32 0
+#define PAI_DTYPE_BF16 1
+
+const char* pai_last_error(void);
+int pai_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * 4x4 convolutions as tcgen05 implicit GEMM.
+ *
+ * pai_conv4x4_fprop: nn.Conv2d(cin, cout, kernel_size=4, stride=stride, padding=1)
+ *   (models/pix2pix.py:63-69,141-147 stride 2; models/wrapper.py:196-203,229-233 stride 2 and 1)
+ *     y[n,oh,ow,co] = act(bias[co] + sum_{ky,kx,ci} x[n, stride*oh-1+ky, stride*ow-1+kx, ci] * W[co,ci,ky,kx])
+ *   x: [n,h,w,cin] bf16, cin % 64 == 0; stride 2 needs x_ld == cin and even h, w.
+ *   w_packed: bf16 [cout_pad][16*cin], w_packed[co][(ky*4+kx)*cin + ci] = W[co,ci,ky,kx];
+ *             rows cout..cout_pad-1 zero, cout_pad % n_tile == 0.
+ *   y: [n,ho,wo,*] (ho = h/2 | h-1), bf16 or fp32 (y_f32), pixel stride y_ld.
+ *   The same routine is the data-gradient of ConvTranspose2d(4,2,1) (models/pix2pix.py:99-105) when
+ *   fed dL/dy and the ConvT weight [Cin_T,Cout_T,4,4] read as a Conv weight [out=Cin_T, in=Cout_T].
+ */
+int pai_conv4x4_fprop(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
+                      int cout_pad, int stride, const float* bias, int act, float slope, void* y, int y_ld,
+                      int y_f32, int n_tile, void* stream);
+
+/* pai_convT4x4s2_fprop: nn.ConvTranspose2d(cin, cout, kernel_size=4, stride=2, padding=1)
+ *   (models/pix2pix.py:99-105,186-192), run as 4 sub-pixel phases:
+ *     y[n,2a+py,2b+px,co] = act(bias[co] + sum_ci sum_{(ky,dy) in T[py]} sum_{(kx,dx) in T[px]}
+ *                               x[n,a+dy,b+dx,ci] * W[ci,co,ky,kx]),  T[0]={(1,0),(3,-1)}, T[1]={(0,+1),(2,0)}
+ *   w_packed: bf16 [4][cout_pad][4*cin]: w_packed[py*2+px][co][(ty*2+tx)*cin+ci] = W[ci,co,T[py][ty].k,T[px][tx].k]
+ *   Also the data-gradient of Conv2d(4,2,1) when fed dL/dy and the Conv weight [Cout,Cin,4,4]
+ *   read as a ConvT weight [in=Cout, out=Cin].
+ */
+int pai_convT4x4s2_fprop(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
+                         int cout_pad, const float* bias, int act, float slope, void* y, int y_ld, int y_f32,
+                         int n_tile, void* stream);
+
+/* Weight gradients (autograd of the two modules above).
+ * pai_conv4x4_wgrad:   dw[ky*4+kx][co][ci] += sum_{n,oh,ow} gy[n,oh,ow,co] * x[n,stride*oh-1+ky,stride*ow-1+kx,ci]
+ * pai_convT4x4s2_wgrad: dw[ky*4+kx][ci][co] += sum_{n,a,b} x[n,a,b,ci] * gy[n,2a-1+ky,2b-1+kx,co]
+ *   dw is fp32 and is ACCUMULATED into (zero it first); channel counts: the first (row) one % 128 == 0,
+ *   the second % 64 == 0.  x: [n,h,w,cin]; gy: the module's output gradient.
+ */
+int pai_conv4x4_wgrad(const void* x, int n, int h, int w, int cin, int x_ld, const void* gy, int cout, int gy_ld,
+                      int stride, float* dw, int splitk, void* stream);
+int pai_convT4x4s2_wgrad(const void* x, int n, int h, int w, int cin, int x_ld, const void* gy, int cout, int gy_ld,
+                         float* dw, int splitk, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAI_B200_H */

@@ -1,0 +1,272 @@
+// C-ABI entry points (include/pai_b200.h): argument validation, TMA tensor-map construction and
+// tap tables for the implicit-GEMM kernels in igemm.cu.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <cudaTypedefs.h>
+
+#include "pai_common.cuh"
+#include "pai_kernels.h"
+
+namespace pai {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return -1;
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    }
+    return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box) {
+    auto fn = get_encode();
+    PAI_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled driver entry point unavailable");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                    reinterpret_cast<const cuuint64_t*>(dims), reinterpret_cast<const cuuint64_t*>(strides_bytes),
+                    reinterpret_cast<const cuuint32_t*>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]",
+                  (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                  (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                  (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0,
+                  rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0);
+        return -3;
+    }
+    return 0;
+}
+
+static int pow2_ge(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+struct PixBox {
+    int bw, bh, bn, tiles_w, tiles_h, tiles_n;
+};
+// Splits `m` (128 or 64) GEMM rows over a (w, h, n) box of the pixel grid.
+static PixBox pick_box(int gw, int gh, int gn, int m) {
+    PixBox b;
+    b.bw = pow2_ge(gw) < m ? pow2_ge(gw) : m;
+    int rest = m / b.bw;
+    b.bh = pow2_ge(gh) < rest ? pow2_ge(gh) : rest;
+    b.bn = rest / b.bh;
+    b.tiles_w = (gw + b.bw - 1) / b.bw;
+    b.tiles_h = (gh + b.bh - 1) / b.bh;
+    b.tiles_n = (gn + b.bn - 1) / b.bn;
+    return b;
+}
+
+// 5-D views of an NHWC bf16 tensor: (C', W', P, H', N).
+static int map_unit(CUtensorMap* m, const void* base, int n, int h, int w, int c, int ld, const PixBox& b) {
+    uint64_t dims[5] = {(uint64_t)c, (uint64_t)w, 1, (uint64_t)h, (uint64_t)n};
+    uint64_t str[4] = {(uint64_t)ld * 2, (uint64_t)w * ld * 2, (uint64_t)w * ld * 2, (uint64_t)h * w * ld * 2};
+    uint32_t box[5] = {64, (uint32_t)b.bw, 1, (uint32_t)b.bh, (uint32_t)b.bn};
+    return encode_tmap_bf16(m, base, 5, dims, str, box);
+}
+// parity-split view for "input = 2*o - 1 + k" access: column 2*wq+px -> (c + px*C, wq), row 2*hq+py -> (py, hq)
+static int map_split(CUtensorMap* m, const void* base, int n, int h, int w, int c, const PixBox& b) {
+    uint64_t dims[5] = {(uint64_t)2 * c, (uint64_t)w / 2, 2, (uint64_t)h / 2, (uint64_t)n};
+    uint64_t str[4] = {(uint64_t)2 * c * 2, (uint64_t)w * c * 2, (uint64_t)2 * w * c * 2, (uint64_t)h * w * c * 2};
+    uint32_t box[5] = {64, (uint32_t)b.bw, 1, (uint32_t)b.bh, (uint32_t)b.bn};
+    return encode_tmap_bf16(m, base, 5, dims, str, box);
+}
+// k in 0..3 of a stride-2, pad-1 access -> (quotient offset, parity)
+static void s2_tap(int k, int* q, int* par) {
+    static const int Q[4] = {-1, 0, 0, 1}, P[4] = {1, 0, 1, 0};
+    *q = Q[k];
+    *par = P[k];
+}
+// ConvTranspose2d(4,2,1) sub-pixel phases: T[parity][t] = (k, d)
+static const int kTd[2][2] = {{0, -1}, {1, 0}};
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace pai
+
+using namespace pai;
+
+extern "C" {
+
+const char* pai_last_error(void) { return g_err; }
+int pai_version(void) { return 100; }
+
+int pai_conv4x4_fprop(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
+                      int cout_pad, int stride, const float* bias, int act, float slope, void* y, int y_ld,
+                      int y_f32, int n_tile, void* stream) {
+    PAI_REQUIRE(x && w_packed && y, "pai_conv4x4_fprop: null pointer");
+    PAI_REQUIRE(stride == 1 || stride == 2, "pai_conv4x4_fprop: stride must be 1 or 2 (got %d)", stride);
+    PAI_REQUIRE(cin > 0 && cin % 64 == 0, "pai_conv4x4_fprop: cin must be a multiple of 64 (got %d)", cin);
+    PAI_REQUIRE(n_tile >= 16 && n_tile <= 256 && n_tile % 16 == 0 && cout_pad % n_tile == 0 && cout <= cout_pad,
+                "pai_conv4x4_fprop: bad n_tile %d / cout %d / cout_pad %d", n_tile, cout, cout_pad);
+    PAI_REQUIRE(aligned16(x) && aligned16(w_packed) && x_ld % 8 == 0, "pai_conv4x4_fprop: x / w must be 16 B aligned");
+    int ho, wo;
+    if (stride == 2) {
+        PAI_REQUIRE(h % 2 == 0 && w % 2 == 0 && x_ld == cin, "pai_conv4x4_fprop: stride 2 needs even h,w and dense x");
+        ho = h / 2;
+        wo = w / 2;
+    } else {
+        PAI_REQUIRE(h >= 2 && w >= 2, "pai_conv4x4_fprop: stride 1 needs h,w >= 2");
+        ho = h - 1;
+        wo = w - 1;
+    }
+    PixBox b = pick_box(wo, ho, n, 128);
+    CUtensorMap tm_a, tm_b;
+    int rc = stride == 2 ? map_split(&tm_a, x, n, h, w, cin, b) : map_unit(&tm_a, x, n, h, w, cin, x_ld, b);
+    if (rc) return rc;
+    uint64_t bd[2] = {(uint64_t)16 * cin, (uint64_t)cout_pad};
+    uint64_t bs[1] = {(uint64_t)16 * cin * 2};
+    uint32_t bb[2] = {64, (uint32_t)n_tile};
+    rc = encode_tmap_bf16(&tm_b, w_packed, 2, bd, bs, bb);
+    if (rc) return rc;
+
+    IgemmFpropParams p;
+    memset(&p, 0, sizeof(p));
+    p.bw = b.bw, p.bh = b.bh, p.bn = b.bn, p.tiles_w = b.tiles_w, p.tiles_h = b.tiles_h;
+    p.gw = wo, p.gh = ho, p.gn = n;
+    p.n_tile = n_tile, p.cout = cout, p.kc_per_tap = cin / 64, p.ntaps = 16;
+    for (int ky = 0; ky < 4; ++ky)
+        for (int kx = 0; kx < 4; ++kx) {
+            int t = ky * 4 + kx;
+            if (stride == 2) {
+                int qx, px, qy, py;
+                s2_tap(kx, &qx, &px);
+                s2_tap(ky, &qy, &py);
+                p.tap_c[t] = px * cin, p.tap_w[t] = qx, p.tap_p[t] = py, p.tap_h[t] = qy;
+            } else {
+                p.tap_c[t] = 0, p.tap_w[t] = kx - 1, p.tap_p[t] = 0, p.tap_h[t] = ky - 1;
+            }
+        }
+    p.b_rows_per_phase = cout_pad;
+    p.out_sn = (long long)ho * wo * y_ld, p.out_sh = (long long)wo * y_ld, p.out_sw = y_ld;
+    p.bias = bias, p.act = act, p.slope = slope, p.out_f32 = y_f32, p.out = y;
+    return launch_igemm_fprop(tm_a, tm_b, p, b.tiles_w * b.tiles_h * b.tiles_n, cout_pad / n_tile, 1,
+                              (cudaStream_t)stream);
+}
+
+int pai_convT4x4s2_fprop(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
+                         int cout_pad, const float* bias, int act, float slope, void* y, int y_ld, int y_f32,
+                         int n_tile, void* stream) {
+    PAI_REQUIRE(x && w_packed && y, "pai_convT4x4s2_fprop: null pointer");
+    PAI_REQUIRE(cin > 0 && cin % 64 == 0, "pai_convT4x4s2_fprop: cin must be a multiple of 64 (got %d)", cin);
+    PAI_REQUIRE(n_tile >= 16 && n_tile <= 256 && n_tile % 16 == 0 && cout_pad % n_tile == 0 && cout <= cout_pad,
+                "pai_convT4x4s2_fprop: bad n_tile %d / cout %d / cout_pad %d", n_tile, cout, cout_pad);
+    PAI_REQUIRE(aligned16(x) && aligned16(w_packed) && x_ld % 8 == 0 && x_ld >= cin,
+                "pai_convT4x4s2_fprop: x / w must be 16 B aligned");
+    PixBox b = pick_box(w, h, n, 128);
+    CUtensorMap tm_a, tm_b;
+    int rc = map_unit(&tm_a, x, n, h, w, cin, x_ld, b);
+    if (rc) return rc;
+    uint64_t bd[2] = {(uint64_t)4 * cin, (uint64_t)4 * cout_pad};
+    uint64_t bs[1] = {(uint64_t)4 * cin * 2};
+    uint32_t bb[2] = {64, (uint32_t)n_tile};
+    rc = encode_tmap_bf16(&tm_b, w_packed, 2, bd, bs, bb);
+    if (rc) return rc;
+
+    IgemmFpropParams p;
+    memset(&p, 0, sizeof(p));
+    p.bw = b.bw, p.bh = b.bh, p.bn = b.bn, p.tiles_w = b.tiles_w, p.tiles_h = b.tiles_h;
+    p.gw = w, p.gh = h, p.gn = n;
+    p.n_tile = n_tile, p.cout = cout, p.kc_per_tap = cin / 64, p.ntaps = 4;
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px)
+            for (int ty = 0; ty < 2; ++ty)
+                for (int tx = 0; tx < 2; ++tx) {
+                    int i = (py * 2 + px) * 4 + ty * 2 + tx;
+                    p.tap_c[i] = 0, p.tap_w[i] = kTd[px][tx], p.tap_p[i] = 0, p.tap_h[i] = kTd[py][ty];
+                }
+    p.b_rows_per_phase = cout_pad;
+    const long long wo = 2LL * w;
+    p.out_sn = 4LL * h * w * y_ld, p.out_sh = 2 * wo * y_ld, p.out_sw = 2LL * y_ld;
+    for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) p.out_phase_off[py * 2 + px] = (py * wo + px) * y_ld;
+    p.bias = bias, p.act = act, p.slope = slope, p.out_f32 = y_f32, p.out = y;
+    return launch_igemm_fprop(tm_a, tm_b, p, b.tiles_w * b.tiles_h * b.tiles_n, cout_pad / n_tile, 4,
+                              (cudaStream_t)stream);
+}
+
+static int wgrad_common(const void* u, int un, int uh, int uw, int cu, int u_ld, const void* s, int sh, int sw,
+                        int cs, int s_ld, int stride, float* dw, int splitk, cudaStream_t stream, const char* who) {
+    PAI_REQUIRE(u && s && dw, "%s: null pointer", who);
+    PAI_REQUIRE(cu % 128 == 0 && cs % 64 == 0, "%s: channel counts (%d rows, %d cols) must be multiples of 128 / 64",
+                who, cu, cs);
+    PAI_REQUIRE(aligned16(u) && aligned16(s) && u_ld % 8 == 0 && s_ld % 8 == 0, "%s: operands must be 16 B aligned",
+                who);
+    PixBox b = pick_box(uw, uh, un, 64);
+    CUtensorMap tm_u, tm_s;
+    int rc = map_unit(&tm_u, u, un, uh, uw, cu, u_ld, b);
+    if (rc) return rc;
+    if (stride == 2) {
+        PAI_REQUIRE(s_ld == cs && sh % 2 == 0 && sw % 2 == 0, "%s: the stride-2 operand must be dense with even h,w",
+                    who);
+        rc = map_split(&tm_s, s, un, sh, sw, cs, b);
+    } else {
+        rc = map_unit(&tm_s, s, un, sh, sw, cs, s_ld, b);
+    }
+    if (rc) return rc;
+    IgemmWgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.bw = b.bw, p.bh = b.bh, p.bn = b.bn, p.tiles_w = b.tiles_w, p.tiles_h = b.tiles_h, p.tiles_n = b.tiles_n;
+    p.n_tile = cs <= 256 ? cs : (cs % 256 == 0 ? 256 : (cs % 128 == 0 ? 128 : 64));
+    p.cu = cu, p.cs = cs, p.out = dw;
+    for (int ky = 0; ky < 4; ++ky)
+        for (int kx = 0; kx < 4; ++kx) {
+            int t = ky * 4 + kx;
+            if (stride == 2) {
+                int qx, px, qy, py;
+                s2_tap(kx, &qx, &px);
+                s2_tap(ky, &qy, &py);
+                p.tap_c[t] = px * cs, p.tap_w[t] = qx, p.tap_p[t] = py, p.tap_h[t] = qy;
+            } else {
+                p.tap_c[t] = 0, p.tap_w[t] = kx - 1, p.tap_p[t] = 0, p.tap_h[t] = ky - 1;
+            }
+        }
+    const int total_tiles = b.tiles_w * b.tiles_h * b.tiles_n;
+    if (splitk <= 0) {
+        const int base = (cu / 128) * (cs / p.n_tile) * 16;
+        splitk = (2 * 148 + base - 1) / base;
+        if (splitk > total_tiles / 4) splitk = total_tiles / 4;
+        if (splitk < 1) splitk = 1;
+    }
+    if (splitk > total_tiles) splitk = total_tiles;
+    return launch_igemm_wgrad(tm_u, tm_s, p, 16, splitk, stream);
+}
+
+int pai_conv4x4_wgrad(const void* x, int n, int h, int w, int cin, int x_ld, const void* gy, int cout, int gy_ld,
+                      int stride, float* dw, int splitk, void* stream) {
+    PAI_REQUIRE(stride == 1 || stride == 2, "pai_conv4x4_wgrad: stride must be 1 or 2");
+    const int ho = stride == 2 ? h / 2 : h - 1, wo = stride == 2 ? w / 2 : w - 1;
+    return wgrad_common(gy, n, ho, wo, cout, gy_ld, x, h, w, cin, x_ld, stride, dw, splitk, (cudaStream_t)stream,
+                        "pai_conv4x4_wgrad");
+}
+
+int pai_convT4x4s2_wgrad(const void* x, int n, int h, int w, int cin, int x_ld, const void* gy, int cout, int gy_ld,
+                         float* dw, int splitk, void* stream) {
+    return wgrad_common(x, n, h, w, cin, x_ld, gy, 2 * h, 2 * w, cout, gy_ld, 2, dw, splitk, (cudaStream_t)stream,
+                        "pai_convT4x4s2_wgrad");
+}
+
+}  // extern "C"

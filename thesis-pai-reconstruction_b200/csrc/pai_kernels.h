@@ -1,0 +1,45 @@
+// Internal launcher interfaces shared by the .cu translation units (not part of the C-ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pai_b200.h"
+
+namespace pai {
+
+struct IgemmFpropParams {
+    int bw, bh, bn;            // TMA box on the pixel grid, bw*bh*bn == 128
+    int tiles_w, tiles_h;      // tiles along w / h (tiles along n follow from gridDim.y)
+    int gw, gh, gn;            // valid pixel-grid extents (rows outside are not stored)
+    int n_tile;                // output channels per CTA (multiple of 16, <= 256)
+    int cout;                  // valid output channels
+    int kc_per_tap, ntaps;     // 64-channel K blocks per tap, taps per phase
+    int stages;
+    int tap_c[16], tap_w[16], tap_p[16], tap_h[16];  // per (phase * ntaps + tap): A-box coordinate offsets
+    int b_rows_per_phase;      // rows of the packed weight matrix per phase (cout_pad)
+    long long out_sn, out_sh, out_sw;  // output element strides per pixel-grid step
+    long long out_phase_off[4];
+    const float* bias;
+    int act;
+    float slope;
+    int out_f32;
+    void* out;
+};
+
+struct IgemmWgradParams {
+    int bw, bh, bn;            // pixel box, bw*bh*bn == 64
+    int tiles_w, tiles_h, tiles_n;
+    int n_tile;                // cs channels per CTA (64, 128 or 256)
+    int cu, cs;                // channel counts of the unshifted / shifted operand
+    int stages;
+    int tap_c[16], tap_w[16], tap_p[16], tap_h[16];
+    float* out;                // [ntaps][cu][cs] fp32, accumulated with atomics
+};
+
+int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFpropParams p, int m_tiles,
+                       int n_tiles, int phases, cudaStream_t stream);
+int launch_igemm_wgrad(const CUtensorMap& tm_u, const CUtensorMap& tm_s, IgemmWgradParams p, int ntaps, int splitk,
+                       cudaStream_t stream);
+
+}  // namespace pai

@@ -1,0 +1,401 @@
+// SSIM / PSNR / MSE metric + loss kernels (memory-bound path of the north star).
+//
+// Replaces torchmetrics==0.11.4 `structural_similarity_index_measure`, `peak_signal_noise_ratio`,
+// `mean_squared_error` as bound by the reference in models/utils.py:38-47 (data_range=1.0) and used by
+// models/wrapper.py:53-63,150-156,166-173 and report.py:78-96,146,188-217 (algorithm: SURVEY.md App. A).
+//
+// One pass over an image pair yields everything report.py needs: the per-image SSIM (mean of the map
+// over rows/cols 5..dim-6), the 16 depth-band SSIMs (rows 16d+5..16d+10), the squared error (PSNR, MSE,
+// RMSE) and, optionally, the full reflect-padded SSIM map.
+//
+// Tile = 22 x 64 map pixels from a 32 x 74 input patch (reflect indexing at the image border):
+//   stage A  global -> smem float4 (p, t, p*p + t*t, p*t), coalesced, optional de-normalisation
+//   stage B  horizontal 11-tap Gaussian, lane <-> input row, warp <-> run of 8 columns, packed FFMA2
+//   stage C  vertical 11-tap Gaussian, lane <-> column, SSIM formula, warp-shuffle reductions
+// Only sigma_p^2 + sigma_t^2 enters SSIM, so 4 planes are filtered instead of torchmetrics' 5.
+#include <math.h>
+
+#include "pai_common.cuh"
+#include "pai_kernels.h"
+
+namespace pai {
+
+static constexpr int TH = 22, TW = 64;          // output tile
+static constexpr int IH = TH + 10, IW = TW + 10;  // input patch 32 x 74
+static constexpr int IN_PITCH = 75;               // float4 units; odd -> conflict-free lane<->row access
+static constexpr int H_PITCH = 33;                // float4 units per column of the h-pass result
+static constexpr int RG = 6;                      // output rows per thread in stage C (4 groups: 6,6,6,4)
+static constexpr int kSsimThreads = 256;
+static constexpr size_t kSsimSmem = (size_t)(IH * IN_PITCH + TW * H_PITCH) * sizeof(float4);
+
+__constant__ float c_gauss[11];
+
+struct Gauss {
+    float g[11];
+};
+static Gauss host_gauss() {
+    // torchmetrics _gaussian(kernel_size=11, sigma=1.5): exp(-((i-5)/sigma)^2 / 2), normalised
+    Gauss k;
+    double s = 0, v[11];
+    for (int i = 0; i < 11; ++i) {
+        double d = (i - 5) / 1.5;
+        v[i] = exp(-0.5 * d * d);
+        s += v[i];
+    }
+    for (int i = 0; i < 11; ++i) k.g[i] = (float)(v[i] / s);
+    return k;
+}
+static int upload_gauss() {
+    static bool done = false;
+    if (!done) {
+        Gauss k = host_gauss();
+        PAI_CUDA_OK(cudaMemcpyToSymbol(c_gauss, k.g, sizeof(k.g)));
+        done = true;
+    }
+    return 0;
+}
+
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(d)
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+          "l"(reinterpret_cast<unsigned long long&>(c)));
+    return reinterpret_cast<float2&>(d);
+}
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
+
+template <typename T>
+__device__ __forceinline__ float load_val(const T* p, size_t i);
+template <>
+__device__ __forceinline__ float load_val<float>(const float* p, size_t i) {
+    return __ldg(p + i);
+}
+template <>
+__device__ __forceinline__ float load_val<__nv_bfloat16>(const __nv_bfloat16* p, size_t i) {
+    return __bfloat162float(p[i]);
+}
+__device__ __forceinline__ float denorm(float x) { return fminf(fmaxf(fmaf(x, 0.5f, 0.5f), 0.f), 1.f); }
+
+struct SsimTerms {
+    float a1, a2, b1, b2;
+};
+__device__ __forceinline__ SsimTerms ssim_terms(float4 m) {
+    const float c1 = 1e-4f, c2 = 9e-4f;
+    const float mpp = m.x * m.x, mtt = m.y * m.y, mpt = m.x * m.y;
+    SsimTerms s;
+    s.a1 = 2.f * mpt + c1;
+    s.a2 = 2.f * (m.w - mpt) + c2;
+    s.b1 = mpp + mtt + c1;
+    s.b2 = (m.z - mpp - mtt) + c2;
+    return s;
+}
+
+// ---- stages B and C, shared by the three kernels ------------------------------------------------
+// in: [IH][IN_PITCH] float4 planes;  hbuf: [TW][H_PITCH] float4
+__device__ __forceinline__ void hpass(const float4* __restrict__ in, float4* __restrict__ hbuf) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float4* row = in + lane * IN_PITCH + warp * 8;
+    float2 xa[18], xb[18];
+#pragma unroll
+    for (int j = 0; j < 18; ++j) {
+        float4 v = row[j];
+        xa[j] = make_float2(v.x, v.y);
+        xb[j] = make_float2(v.z, v.w);
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+            const float2 g = make_float2(c_gauss[k], c_gauss[k]);
+            sa = fma2(xa[o + k], g, sa);
+            sb = fma2(xb[o + k], g, sb);
+        }
+        hbuf[(warp * 8 + o) * H_PITCH + lane] = make_float4(sa.x, sa.y, sb.x, sb.y);
+    }
+}
+// thread <-> (column, row group); returns the filtered planes of up to RG rows
+__device__ __forceinline__ void vpass(const float4* __restrict__ hbuf, int col, int rg, float4 (&out)[RG]) {
+    const float4* c = hbuf + col * H_PITCH + rg * RG;
+    float2 xa[RG + 10], xb[RG + 10];
+#pragma unroll
+    for (int j = 0; j < RG + 10; ++j) {
+        float4 v = (rg * RG + j < IH) ? c[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+        xa[j] = make_float2(v.x, v.y);
+        xb[j] = make_float2(v.z, v.w);
+    }
+#pragma unroll
+    for (int o = 0; o < RG; ++o) {
+        float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+            const float2 g = make_float2(c_gauss[k], c_gauss[k]);
+            sa = fma2(xa[o + k], g, sa);
+            sb = fma2(xb[o + k], g, sb);
+        }
+        out[o] = make_float4(sa.x, sa.y, sb.x, sb.y);
+    }
+}
+
+template <typename T, bool DENORM>
+__device__ __forceinline__ void load_pair_patch(const T* __restrict__ pred, const T* __restrict__ target,
+                                                size_t img_off, int h, int w, int y0, int x0, float4* in) {
+    for (int i = threadIdx.x; i < IH * IW; i += kSsimThreads) {
+        const int r = i / IW, c = i - r * IW;
+        const int gy = reflect_idx(y0 - 5 + r, h), gx = reflect_idx(x0 - 5 + c, w);
+        const size_t o = img_off + (size_t)gy * w + gx;
+        float p = load_val<T>(pred, o), t = load_val<T>(target, o);
+        if (DENORM) {
+            p = denorm(p);
+            t = denorm(t);
+        }
+        in[r * IN_PITCH + c] = make_float4(p, t, fmaf(p, p, t * t), p * t);
+    }
+}
+
+// =============================================================================================
+// forward: ssim_sum[n], band_sum[n][16] (optional), sse[n], full map (optional)
+template <typename T, bool DENORM>
+__global__ void __launch_bounds__(kSsimThreads)
+ssim_fwd_kernel(const T* __restrict__ pred, const T* __restrict__ target, int h, int w, int band_rows,
+                float* __restrict__ ssim_sum, float* __restrict__ band_sum, float* __restrict__ sse,
+                float* __restrict__ full_map) {
+    extern __shared__ float4 smem4[];
+    float4* in = smem4;
+    float4* hbuf = smem4 + IH * IN_PITCH;
+    __shared__ float acc[18];
+    const int img = blockIdx.z, y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
+    const size_t img_off = (size_t)img * h * w;
+    if (threadIdx.x < 18) acc[threadIdx.x] = 0.f;
+    load_pair_patch<T, DENORM>(pred, target, img_off, h, w, y0, x0, in);
+    __syncthreads();
+    hpass(in, hbuf);
+    __syncthreads();
+
+    const int col = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    float4 m[RG];
+    vpass(hbuf, col, rg, m);
+    const int gx = x0 + col;
+    const bool col_in = gx < w, col_int = gx >= 5 && gx < w - 5;
+    float s_sum = 0.f, e_sum = 0.f, b_sum[2] = {0.f, 0.f};
+    const int gy_first = y0 + rg * RG;
+    const int band0 = band_sum != nullptr ? gy_first / band_rows : 0;
+#pragma unroll
+    for (int o = 0; o < RG; ++o) {
+        const int lr = rg * RG + o, gy = y0 + lr;
+        if (lr < TH && gy < h && col_in) {
+            const SsimTerms t = ssim_terms(m[o]);
+            const float s = __fdividef(t.a1 * t.a2, t.b1 * t.b2);
+            if (full_map != nullptr) full_map[img_off + (size_t)gy * w + gx] = s;
+            const float4 ctr = in[(lr + 5) * IN_PITCH + col + 5];
+            const float d = ctr.x - ctr.y;
+            e_sum = fmaf(d, d, e_sum);
+            if (col_int && gy >= 5 && gy < h - 5) s_sum += s;
+            if (band_sum != nullptr && col_int) {
+                const int b = gy / band_rows, br = gy - b * band_rows;
+                if (br >= 5 && br < band_rows - 5) b_sum[b - band0] += s;
+            }
+        }
+    }
+    s_sum = warp_sum(s_sum);
+    e_sum = warp_sum(e_sum);
+    if (band_sum != nullptr) {
+        b_sum[0] = warp_sum(b_sum[0]);
+        b_sum[1] = warp_sum(b_sum[1]);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&acc[0], s_sum);
+        atomicAdd(&acc[1], e_sum);
+        if (band_sum != nullptr) {
+            if (band0 < 16) atomicAdd(&acc[2 + band0], b_sum[0]);
+            if (band0 + 1 < 16) atomicAdd(&acc[3 + band0], b_sum[1]);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(ssim_sum + img, acc[0]);
+    if (threadIdx.x == 1) atomicAdd(sse + img, acc[1]);
+    if (band_sum != nullptr && threadIdx.x >= 2 && threadIdx.x < 18 && acc[threadIdx.x] != 0.f)
+        atomicAdd(band_sum + (size_t)img * 16 + (threadIdx.x - 2), acc[threadIdx.x]);
+}
+
+// =============================================================================================
+// backward, pass 1: coef[n,h,w] = g_ssim[n] * (a, b, c, 0) at the interior window centres, else 0
+// (a = dS/dG(p), b = dS/dG(p^2), c = dS/dG(pt); SURVEY.md Appendix A "Gradient").
+template <typename T, bool DENORM>
+__global__ void __launch_bounds__(kSsimThreads)
+ssim_bwd_coef_kernel(const T* __restrict__ pred, const T* __restrict__ target, int h, int w,
+                     const float* __restrict__ g_ssim, float4* __restrict__ coef) {
+    extern __shared__ float4 smem4[];
+    float4* in = smem4;
+    float4* hbuf = smem4 + IH * IN_PITCH;
+    const int img = blockIdx.z, y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
+    const size_t img_off = (size_t)img * h * w;
+    load_pair_patch<T, DENORM>(pred, target, img_off, h, w, y0, x0, in);
+    __syncthreads();
+    hpass(in, hbuf);
+    __syncthreads();
+    const int col = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    float4 m[RG];
+    vpass(hbuf, col, rg, m);
+    const int gx = x0 + col;
+    const float gs = g_ssim[img];
+#pragma unroll
+    for (int o = 0; o < RG; ++o) {
+        const int lr = rg * RG + o, gy = y0 + lr;
+        if (lr < TH && gy < h && gx < w) {
+            float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gx >= 5 && gx < w - 5 && gy >= 5 && gy < h - 5) {
+                const SsimTerms t = ssim_terms(m[o]);
+                const float inv = 1.f / (t.b1 * t.b2);
+                const float s = t.a1 * t.a2 * inv;
+                out.x = gs * (2.f * m[o].y * (t.a2 - t.a1) * inv - 2.f * m[o].x * s * (t.b2 - t.b1) * inv);
+                out.y = gs * (-s / t.b2);
+                out.z = gs * (2.f * t.a1 * inv);
+            }
+            coef[img_off + (size_t)gy * w + gx] = out;
+        }
+    }
+}
+
+// backward, pass 2: grad = G*(a) + 2 p G*(b) + t G*(c) + g_sse[n] * 2 (p - t), chained through the
+// de-normalisation clamp(0.5 x + 0.5, 0, 1) when DENORM (models/utils.py:11).
+template <typename T, bool DENORM>
+__global__ void __launch_bounds__(kSsimThreads)
+ssim_bwd_apply_kernel(const T* __restrict__ pred, const T* __restrict__ target, int h, int w,
+                      const float4* __restrict__ coef, const float* __restrict__ g_sse, T* __restrict__ grad) {
+    extern __shared__ float4 smem4[];
+    float4* in = smem4;
+    float4* hbuf = smem4 + IH * IN_PITCH;
+    const int img = blockIdx.z, y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
+    const size_t img_off = (size_t)img * h * w;
+    for (int i = threadIdx.x; i < IH * IW; i += kSsimThreads) {
+        const int r = i / IW, c = i - r * IW;
+        const int gy = y0 - 5 + r, gx = x0 - 5 + c;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gy >= 0 && gy < h && gx >= 0 && gx < w) v = __ldg(coef + img_off + (size_t)gy * w + gx);
+        in[r * IN_PITCH + c] = v;
+    }
+    __syncthreads();
+    hpass(in, hbuf);
+    __syncthreads();
+    const int col = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    float4 m[RG];
+    vpass(hbuf, col, rg, m);
+    const int gx = x0 + col;
+    const float ge = g_sse != nullptr ? g_sse[img] : 0.f;
+#pragma unroll
+    for (int o = 0; o < RG; ++o) {
+        const int lr = rg * RG + o, gy = y0 + lr;
+        if (lr < TH && gy < h && gx < w) {
+            const size_t idx = img_off + (size_t)gy * w + gx;
+            float xp = load_val<T>(pred, idx), xt = load_val<T>(target, idx);
+            float p = xp, t = xt, chain = 1.f;
+            if (DENORM) {
+                const float u = fmaf(xp, 0.5f, 0.5f);
+                chain = (u >= 0.f && u <= 1.f) ? 0.5f : 0.f;
+                p = denorm(xp);
+                t = denorm(xt);
+            }
+            const float g = m[o].x + 2.f * p * m[o].y + t * m[o].z + ge * 2.f * (p - t);
+            if (sizeof(T) == 4)
+                reinterpret_cast<float*>(grad)[idx] = g * chain;
+            else
+                reinterpret_cast<__nv_bfloat16*>(grad)[idx] = __float2bfloat16_rn(g * chain);
+        }
+    }
+}
+
+template <typename T, bool DENORM>
+static int fwd_launch(const void* pred, const void* target, int n, int h, int w, int band_rows, float* ssim_sum,
+                      float* band_sum, float* sse, float* full_map, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        PAI_CUDA_OK(cudaFuncSetAttribute(ssim_fwd_kernel<T, DENORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kSsimSmem));
+        attr = true;
+    }
+    dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH, n);
+    ssim_fwd_kernel<T, DENORM><<<grid, kSsimThreads, kSsimSmem, st>>>(
+        (const T*)pred, (const T*)target, h, w, band_rows, ssim_sum, band_sum, sse, full_map);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <typename T, bool DENORM>
+static int bwd_launch(const void* pred, const void* target, int n, int h, int w, const float* g_ssim,
+                      const float* g_sse, float4* coef, void* grad, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        PAI_CUDA_OK(cudaFuncSetAttribute(ssim_bwd_coef_kernel<T, DENORM>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSsimSmem));
+        PAI_CUDA_OK(cudaFuncSetAttribute(ssim_bwd_apply_kernel<T, DENORM>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSsimSmem));
+        attr = true;
+    }
+    dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH, n);
+    ssim_bwd_coef_kernel<T, DENORM><<<grid, kSsimThreads, kSsimSmem, st>>>((const T*)pred, (const T*)target, h, w,
+                                                                            g_ssim, coef);
+    PAI_CUDA_OK(cudaGetLastError());
+    ssim_bwd_apply_kernel<T, DENORM><<<grid, kSsimThreads, kSsimSmem, st>>>((const T*)pred, (const T*)target, h, w,
+                                                                             coef, g_sse, (T*)grad);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace pai
+
+using namespace pai;
+
+extern "C" {
+
+int pai_ssim_psnr_fwd(const void* pred, const void* target, int dtype, int n, int h, int w, int denormalize,
+                      float* ssim_sum, float* band_sum, float* sse, float* full_map, void* stream) {
+    PAI_REQUIRE(pred && target && ssim_sum && sse, "pai_ssim_psnr_fwd: null pointer");
+    PAI_REQUIRE(n >= 0 && h > 10 && w > 10, "pai_ssim_psnr_fwd: images must be larger than the 11x11 window (got %dx%d)",
+                h, w);
+    PAI_REQUIRE(dtype == PAI_DTYPE_F32 || dtype == PAI_DTYPE_BF16, "pai_ssim_psnr_fwd: bad dtype %d", dtype);
+    int band_rows = 0;
+    if (band_sum != nullptr) {
+        PAI_REQUIRE(h % 16 == 0 && h / 16 > 10, "pai_ssim_psnr_fwd: depth bands need h %% 16 == 0 and h/16 > 10 (h=%d)", h);
+        band_rows = h / 16;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return 0;
+    if (int rc = upload_gauss()) return rc;
+    PAI_CUDA_OK(cudaMemsetAsync(ssim_sum, 0, sizeof(float) * n, st));
+    PAI_CUDA_OK(cudaMemsetAsync(sse, 0, sizeof(float) * n, st));
+    if (band_sum) PAI_CUDA_OK(cudaMemsetAsync(band_sum, 0, sizeof(float) * 16 * n, st));
+    if (dtype == PAI_DTYPE_F32)
+        return denormalize ? fwd_launch<float, true>(pred, target, n, h, w, band_rows, ssim_sum, band_sum, sse, full_map, st)
+                           : fwd_launch<float, false>(pred, target, n, h, w, band_rows, ssim_sum, band_sum, sse, full_map, st);
+    return denormalize
+               ? fwd_launch<__nv_bfloat16, true>(pred, target, n, h, w, band_rows, ssim_sum, band_sum, sse, full_map, st)
+               : fwd_launch<__nv_bfloat16, false>(pred, target, n, h, w, band_rows, ssim_sum, band_sum, sse, full_map, st);
+}
+
+int pai_ssim_psnr_bwd(const void* pred, const void* target, int dtype, int n, int h, int w, int denormalize,
+                      const float* g_ssim_sum, const float* g_sse, void* workspace, void* grad_pred, void* stream) {
+    PAI_REQUIRE(pred && target && g_ssim_sum && workspace && grad_pred, "pai_ssim_psnr_bwd: null pointer");
+    PAI_REQUIRE(n >= 0 && h > 10 && w > 10, "pai_ssim_psnr_bwd: images must be larger than the 11x11 window");
+    PAI_REQUIRE(dtype == PAI_DTYPE_F32 || dtype == PAI_DTYPE_BF16, "pai_ssim_psnr_bwd: bad dtype %d", dtype);
+    PAI_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "pai_ssim_psnr_bwd: workspace must be 16 B aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return 0;
+    if (int rc = upload_gauss()) return rc;
+    float4* coef = reinterpret_cast<float4*>(workspace);
+    if (dtype == PAI_DTYPE_F32)
+        return denormalize ? bwd_launch<float, true>(pred, target, n, h, w, g_ssim_sum, g_sse, coef, grad_pred, st)
+                           : bwd_launch<float, false>(pred, target, n, h, w, g_ssim_sum, g_sse, coef, grad_pred, st);
+    return denormalize ? bwd_launch<__nv_bfloat16, true>(pred, target, n, h, w, g_ssim_sum, g_sse, coef, grad_pred, st)
+                       : bwd_launch<__nv_bfloat16, false>(pred, target, n, h, w, g_ssim_sum, g_sse, coef, grad_pred, st);
+}
+
+long long pai_ssim_bwd_workspace_bytes(int n, int h, int w) { return (long long)n * h * w * 16; }
+
+}  // extern "C"

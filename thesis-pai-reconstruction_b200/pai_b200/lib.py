@@ -1,0 +1,56 @@
+"""ctypes binding of libpai_b200.so (the C-ABI declared in include/pai_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpai_b200.so")
+
+c_int, c_float, c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+
+# name -> argtypes, exactly the declarations of include/pai_b200.h
+SIGNATURES = {
+    "pai_version": [],
+    "pai_conv4x4_fprop": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
+                          c_int, c_float, c_void_p, c_int, c_int, c_int, c_void_p],
+    "pai_convT4x4s2_fprop": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int,
+                             c_float, c_void_p, c_int, c_int, c_int, c_void_p],
+    "pai_conv4x4_wgrad": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
+                          c_int, c_void_p],
+    "pai_convT4x4s2_wgrad": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int,
+                             c_void_p],
+}
+
+_lib = None
+launches = 0  # number of kernels this process asked the library to launch (bench.py reports it)
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with thesis-pai-reconstruction_b200/csrc/build.sh "
+                "(or __graft_entry__.build()); there is no CPU or PyTorch fallback")
+        lib = ctypes.CDLL(LIB_PATH)
+        lib.pai_last_error.restype = ctypes.c_char_p
+        lib.pai_last_error.argtypes = []
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = c_int
+        _lib = lib
+    return _lib
+
+
+def call(name: str, *args, kernels: int = 1) -> None:
+    global launches
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"{name} failed ({rc}): {lib.pai_last_error().decode()}")
+    launches += kernels

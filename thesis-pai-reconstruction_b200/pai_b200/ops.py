@@ -1,0 +1,132 @@
+"""Tensor-level wrappers over the C-ABI (pai_b200.lib) and the weight packers.
+
+Activations and gradients are NHWC bf16 ``torch.Tensor``s ``[N, H, W, C]`` (possibly a channel slice
+``buf[..., c0:c1]`` of a wider concat buffer -- only the last-dim stride 1 and a uniform pixel stride
+are required).  PyTorch owns every buffer; the library only enqueues kernels on the current stream.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import lib
+
+ACT_NONE, ACT_LEAKY, ACT_RELU, ACT_TANH = 0, 1, 2, 3
+# ConvTranspose2d(4,2,1) sub-pixel phases: T[parity] = ((k, d), (k, d))
+_T_K = ((1, 3), (0, 2))
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _nhwc(t: torch.Tensor):
+    """-> (n, h, w, c, ld) of an NHWC view whose pixels are ``ld`` elements apart."""
+    assert t.dim() == 4 and t.stride(3) == 1, "expected an NHWC tensor with unit channel stride"
+    n, h, w, c = t.shape
+    if w > 1:
+        ld = t.stride(2)
+    elif h > 1:
+        ld = t.stride(1)
+    elif n > 1:
+        ld = t.stride(0)
+    else:
+        ld = c
+    assert (w == 1 or t.stride(2) == ld) and (h == 1 or t.stride(1) == w * ld) and (n == 1 or t.stride(0) == h * w * ld), \
+        f"not a uniformly strided NHWC view: shape {tuple(t.shape)} strides {t.stride()}"
+    return n, h, w, c, ld
+
+
+def pick_n_tile(cout: int) -> int:
+    if cout >= 128:
+        return 128
+    if cout >= 64:
+        return 64
+    return 16 * ((cout + 15) // 16)
+
+
+def pad_to(cout: int, n_tile: int) -> int:
+    return n_tile * ((cout + n_tile - 1) // n_tile)
+
+
+# ------------------------------------------------------------------------------------------ packing
+def pack_conv_weight(w: torch.Tensor, n_tile: int | None = None) -> torch.Tensor:
+    """Conv2d weight ``[Cout, Cin, 4, 4]`` (any strides) -> bf16 ``[cout_pad, 16*Cin]`` with
+    ``out[co, (ky*4+kx)*Cin + ci] = w[co, ci, ky, kx]`` (include/pai_b200.h, pai_conv4x4_fprop)."""
+    cout, cin = w.shape[0], w.shape[1]
+    n_tile = n_tile or pick_n_tile(cout)
+    cp = pad_to(cout, n_tile)
+    out = torch.zeros(cp, 16 * cin, dtype=torch.bfloat16, device=w.device)
+    out[:cout].view(cout, 4, 4, cin).copy_(w.permute(0, 2, 3, 1))
+    return out
+
+
+def pack_convT_weight(w: torch.Tensor, n_tile: int | None = None) -> torch.Tensor:
+    """ConvTranspose2d weight ``[Cin, Cout, 4, 4]`` -> bf16 ``[4, cout_pad, 4*Cin]`` with
+    ``out[py*2+px, co, (ty*2+tx)*Cin + ci] = w[ci, co, T[py][ty].k, T[px][tx].k]``."""
+    cin, cout = w.shape[0], w.shape[1]
+    n_tile = n_tile or pick_n_tile(cout)
+    cp = pad_to(cout, n_tile)
+    out = torch.zeros(4, cp, 4 * cin, dtype=torch.bfloat16, device=w.device)
+    for py in range(2):
+        for px in range(2):
+            sub = w[:, :, list(_T_K[py]), :][:, :, :, list(_T_K[px])]       # [ci, co, ty, tx]
+            out[py * 2 + px, :cout].view(cout, 2, 2, cin).copy_(sub.permute(1, 2, 3, 0))
+    return out
+
+
+# ------------------------------------------------------------------------------------------ fprop / dgrad
+def conv4x4_fprop(x, w_packed, cout, stride=2, bias=None, act=ACT_NONE, slope=0.2, out=None, out_f32=False,
+                  n_tile=None):
+    n, h, w, cin, ld = _nhwc(x)
+    n_tile = n_tile or pick_n_tile(cout)
+    cp = w_packed.shape[0]
+    ho, wo = (h // 2, w // 2) if stride == 2 else (h - 1, w - 1)
+    if out is None:
+        out = torch.empty(n, ho, wo, cout, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    on, oh, ow, oc, old = _nhwc(out)
+    assert (on, oh, ow, oc) == (n, ho, wo, cout)
+    lib.call("pai_conv4x4_fprop", _ptr(x), n, h, w, cin, ld, _ptr(w_packed), cout, cp, stride, _ptr(bias), act,
+             float(slope), _ptr(out), old, int(out.dtype == torch.float32), n_tile, _stream())
+    return out
+
+
+def convT4x4s2_fprop(x, w_packed, cout, bias=None, act=ACT_NONE, slope=0.2, out=None, out_f32=False, n_tile=None):
+    n, h, w, cin, ld = _nhwc(x)
+    n_tile = n_tile or pick_n_tile(cout)
+    cp = w_packed.shape[1]
+    if out is None:
+        out = torch.empty(n, 2 * h, 2 * w, cout, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    on, oh, ow, oc, old = _nhwc(out)
+    assert (on, oh, ow, oc) == (n, 2 * h, 2 * w, cout)
+    lib.call("pai_convT4x4s2_fprop", _ptr(x), n, h, w, cin, ld, _ptr(w_packed), cout, cp, _ptr(bias), act,
+             float(slope), _ptr(out), old, int(out.dtype == torch.float32), n_tile, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ wgrad
+def conv4x4_wgrad(x, gy, stride=2, dw=None, splitk=0):
+    """-> fp32 ``[16, Cout, Cin]`` (tap-major); ``dw.permute(1, 2, 0).view(Cout, Cin, 4, 4)`` is the
+    gradient in the reference's ``[Cout, Cin, kh, kw]`` layout."""
+    n, h, w, cin, ld = _nhwc(x)
+    gn, gh, gw, cout, gld = _nhwc(gy)
+    if dw is None:
+        dw = torch.zeros(16, cout, cin, dtype=torch.float32, device=x.device)
+    lib.call("pai_conv4x4_wgrad", _ptr(x), n, h, w, cin, ld, _ptr(gy), cout, gld, stride, _ptr(dw), splitk,
+             _stream())
+    return dw
+
+
+def convT4x4s2_wgrad(x, gy, dw=None, splitk=0):
+    """-> fp32 ``[16, Cin, Cout]``; ``dw.permute(1, 2, 0).view(Cin, Cout, 4, 4)`` is the reference layout."""
+    n, h, w, cin, ld = _nhwc(x)
+    gn, gh, gw, cout, gld = _nhwc(gy)
+    if dw is None:
+        dw = torch.zeros(16, cin, cout, dtype=torch.float32, device=x.device)
+    lib.call("pai_convT4x4s2_wgrad", _ptr(x), n, h, w, cin, ld, _ptr(gy), cout, gld, _ptr(dw), splitk, _stream())
+    return dw
