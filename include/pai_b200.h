@@ -72,6 +72,28 @@ int pai_conv4x4_wgrad(const void* x, int n, int h, int w, int cin, int x_ld, con
 int pai_convT4x4s2_wgrad(const void* x, int n, int h, int w, int cin, int x_ld, const void* gy, int cout, int gy_ld,
                          float* dw, int splitk, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * SSIM / PSNR / MSE metric and loss path (torchmetrics==0.11.4 functionals as bound by
+ * models/utils.py:38-47 with data_range=1.0; callers models/wrapper.py:53-63,150-156,166-173 and
+ * report.py:78-96,146,188-217).  11x11 Gaussian window (sigma 1.5), c1=1e-4, c2=9e-4, reflect pad 5.
+ *
+ * pai_ssim_psnr_fwd: pred/target are [n,h,w] single-channel planes (dtype PAI_DTYPE_F32|BF16);
+ *   denormalize != 0 applies models/utils.py:11 clamp(0.5*x+0.5, 0, 1) to both on load.
+ *   ssim_sum[n]   = sum of the SSIM map over rows/cols 5..dim-6 (per-image SSIM = / ((h-10)*(w-10)))
+ *   band_sum[n,16] (nullable) = per depth band d, the sum over rows d*h/16+5 .. (d+1)*h/16-6, cols 5..w-6
+ *                   (report.py:188-217 depth_ssim = / ((h/16-10)*(w-10)))
+ *   sse[n]        = sum (p-t)^2  (PSNR = 10 log10(numel/sse), MSE = sse/numel, RMSE = sqrt)
+ *   full_map[n,h,w] (nullable) = the reflect-padded SSIM image of return_full_image=True.
+ * pai_ssim_psnr_bwd: grad_pred[n,h,w] (same dtype as pred) = d/dpred of
+ *   sum_i g_ssim_sum[i]*ssim_sum[i] + g_sse[i]*sse[i]  (g_sse nullable), chained through the
+ *   de-normalisation when denormalize != 0.  workspace: pai_ssim_bwd_workspace_bytes(n,h,w) bytes.
+ */
+int pai_ssim_psnr_fwd(const void* pred, const void* target, int dtype, int n, int h, int w, int denormalize,
+                      float* ssim_sum, float* band_sum, float* sse, float* full_map, void* stream);
+int pai_ssim_psnr_bwd(const void* pred, const void* target, int dtype, int n, int h, int w, int denormalize,
+                      const float* g_ssim_sum, const float* g_sse, void* workspace, void* grad_pred, void* stream);
+long long pai_ssim_bwd_workspace_bytes(int n, int h, int w);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,12 @@ SIGNATURES = {
                           c_int, c_void_p],
     "pai_convT4x4s2_wgrad": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int,
                              c_void_p],
+    "pai_ssim_psnr_fwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                          c_void_p, c_void_p],
+    "pai_ssim_psnr_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                          c_void_p, c_void_p],
 }
+RESTYPES = {"pai_ssim_bwd_workspace_bytes": (ctypes.c_longlong, [c_int, c_int, c_int])}
 
 _lib = None
 launches = 0  # number of kernels this process asked the library to launch (bench.py reports it)
@@ -43,6 +48,10 @@ def load() -> ctypes.CDLL:
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = c_int
+        for name, (res, args) in RESTYPES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = res
         _lib = lib
     return _lib
 
