@@ -94,6 +94,51 @@ int pai_ssim_psnr_bwd(const void* pred, const void* target, int dtype, int n, in
                       const float* g_ssim_sum, const float* g_sse, void* workspace, void* grad_pred, void* stream);
 long long pai_ssim_bwd_workspace_bytes(int n, int h, int w);
 
+/* ---------------------------------------------------------------------------------------------
+ * BatchNorm2d (eps, momentum; models/pix2pix.py:70,106) split around the convolution kernels, the
+ * non-inplace pre-activations LeakyReLU(0.2)/ReLU (models/pix2pix.py:62,98) and the zero-copy skip
+ * concat (models/pix2pix.py:212).  x: [m pixels][c] bf16, `ld` elements between pixels.
+ *   pai_bn_stats      sums[0:c] = sum_x, sums[c:2c] = sum_x^2 (fp32; zeroed by the call)
+ *   pai_bn_finalize   training: batch mean / biased var from sums, running stats updated with
+ *                     `momentum` and the unbiased variance; eval: running stats are used.
+ *                     scale_shift[4c] = [gamma*invstd | beta - mean*gamma*invstd | mean | invstd]
+ *   pai_bn_apply_act  out1 = act1(scale*x + shift) and optionally out2 = act2(...) (each may be a
+ *                     channel slot of a wider buffer); scale_shift NULL = identity
+ *   pai_bn_bwd_reduce dz = g1*act1'(z) + g2*act2'(z) (g2 nullable), z = scale*x + shift;
+ *                     sums[0:c] = sum dz (= dbeta), sums[c:2c] = sum dz*xhat (= dgamma)
+ *   pai_bn_bwd_apply  dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)); scale_shift NULL = no
+ *                     normalisation (dx = dz: plain activation backward, sums[0:c] of the reduce = dbias)
+ *   pai_colsum        sums2c[0:c] = column sums of x (bias gradients); sums2c[c:2c] is scratch
+ */
+int pai_bn_stats(const void* x, long long m, int c, int ld, float* sums, void* stream);
+int pai_bn_finalize(const float* sums, long long m, int c, const float* gamma, const float* beta, float eps,
+                    float momentum, int training, float* running_mean, float* running_var, float* scale_shift,
+                    void* stream);
+int pai_bn_apply_act(const void* x, long long m, int c, int ld, const float* scale_shift, void* out1, int ld1,
+                     int act1, void* out2, int ld2, int act2, float slope, void* stream);
+int pai_bn_bwd_reduce(const void* x, long long m, int c, int ld, const float* scale_shift, const void* g1, int ldg1,
+                      int act1, const void* g2, int ldg2, int act2, float slope, float* sums, void* stream);
+int pai_bn_bwd_apply(const void* x, long long m, int c, int ld, const float* scale_shift, const void* g1, int ldg1,
+                     int act1, const void* g2, int ldg2, int act2, float slope, const float* sums,
+                     const float* gamma, void* dx, int lddx, void* stream);
+int pai_colsum(const void* x, long long m, int c, int ld, float* sums2c, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The four degenerate (1- or 2-channel-wide, HBM-bound) layers: enc0 Conv2d(1,64,4,2,1)
+ * (models/pix2pix.py:141-147), D0 Conv2d(2,64,4,2,1) on cat([x,y],1) (models/wrapper.py:229,237),
+ * dec7 ConvTranspose2d(128,1,4,2,1) (models/pix2pix.py:186-192) and D4 Conv2d(512,1,4,1,1)
+ * (models/wrapper.py:233).  Planes are single-channel fp32 [n,ih,iw]; the wide operand is NHWC bf16
+ * on the [n,oh,ow] grid; (dy,dx) of tap t=(ky,kx) is (ky-1,kx-1), or (1-ky,1-kx) when flip.
+ *   pai_smallc_conv_fprop  out[n,oy,ox,c] = act(bias[c] + sum_{t,j} plane_j[n,s*oy+dy,s*ox+dx] * w[c][t][j])
+ *                          (enc0 / D0 forward; dec7 and D4 data gradients)
+ *   pai_smallc_conv_wgrad  dw[c][t][j] += sum_{n,y,x} a[n,y,x,c] * plane_j[n,s*y+dy,s*x+dx]   (dw fp32, accumulated)
+ */
+int pai_smallc_conv_fprop(const float* plane0, const float* plane1, int cin, int n, int ih, int iw, int oh, int ow,
+                          int stride, int flip, const float* w, const float* bias, int c, void* out1, int ld1,
+                          int act1, void* out2, int ld2, int act2, float slope, void* stream);
+int pai_smallc_conv_wgrad(const void* a, int lda, int c, const float* plane0, const float* plane1, int cin, int n,
+                          int ih, int iw, int oh, int ow, int stride, int flip, float* dw, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

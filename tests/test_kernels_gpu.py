@@ -1,0 +1,134 @@
+"""GPU unit parity of the BatchNorm / activation / degenerate-layer kernels (C-ABI through
+pai_b200.ops) against plain PyTorch fp32 formulations of the same reference ops
+(nn.BatchNorm2d, LeakyReLU/ReLU, Conv2d / ConvTranspose2d with 1-2 channel operands)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+torch.backends.cudnn.allow_tf32 = False
+
+
+def _ops():
+    from pai_b200 import ops
+    return ops
+
+
+def _rand(shape, seed, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).to(dtype)
+
+
+@pytest.mark.parametrize("n,h,w,c", [(2, 64, 64, 128), (8, 2, 2, 512), (2, 128, 128, 64), (3, 5, 7, 256)])
+def test_batchnorm_forward_backward(n, h, w, c):
+    ops = _ops()
+    x = _rand((n, h, w, c), 1, 2.0) + 0.5
+    gamma = torch.rand(c, device="cuda") + 0.5
+    beta = torch.randn(c, device="cuda")
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    m = n * h * w
+    sums = ops.bn_stats(x)
+    ss = ops.bn_finalize(sums, m, c, gamma, beta, rm, rv, training=True)
+    wide = torch.zeros(n, h, w, 2 * c, dtype=torch.bfloat16, device="cuda")
+    o1 = torch.empty(n, h, w, c, dtype=torch.bfloat16, device="cuda")
+    ops.bn_apply_act(x, ss, o1, ops.ACT_LEAKY, wide[..., c:], ops.ACT_RELU, slope=0.2)
+    # reference
+    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    rm_r, rv_r = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    z = F.batch_norm(xr, rm_r, rv_r, gr, br, True, 0.1, 1e-5)
+    y1, y2 = F.leaky_relu(z, 0.2), F.relu(z)
+    tol = 2e-2 * max(1.0, z.abs().max().item())
+    assert (o1.float().permute(0, 3, 1, 2) - y1).abs().max().item() < tol
+    assert (wide[..., c:].float().permute(0, 3, 1, 2) - y2).abs().max().item() < tol
+    assert wide[..., :c].abs().max().item() == 0
+    assert torch.allclose(rm, rm_r, atol=1e-4, rtol=1e-4) and torch.allclose(rv, rv_r, atol=1e-4, rtol=1e-3)
+    # backward
+    g1 = _rand((n, h, w, c), 2)
+    g2w = _rand((n, h, w, 2 * c), 3)
+    g2 = g2w[..., c:]
+    (y1 * g1.float().permute(0, 3, 1, 2) + y2 * g2.float().permute(0, 3, 1, 2)).sum().backward()
+    s2 = ops.bn_bwd_reduce(x, ss, g1, ops.ACT_LEAKY, g2, ops.ACT_RELU, slope=0.2)
+    dx = torch.empty_like(x)
+    ops.bn_bwd_apply(x, ss, g1, ops.ACT_LEAKY, g2, ops.ACT_RELU, s2, gamma, dx, slope=0.2)
+    ref = xr.grad.permute(0, 2, 3, 1)
+    assert (dx.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    assert torch.allclose(s2[:c], br.grad, rtol=2e-2, atol=2e-2 * br.grad.abs().max().item())
+    assert torch.allclose(s2[c:], gr.grad, rtol=2e-2, atol=2e-2 * gr.grad.abs().max().item())
+    # eval mode uses the running statistics
+    ss_e = ops.bn_finalize(None, m, c, gamma, beta, rm, rv, training=False)
+    ops.bn_apply_act(x, ss_e, o1, ops.ACT_NONE)
+    ze = F.batch_norm(x.float().permute(0, 3, 1, 2), rm, rv, gamma, beta, False, 0.1, 1e-5)
+    assert (o1.float().permute(0, 3, 1, 2) - ze).abs().max().item() < 2e-2 * max(1.0, ze.abs().max().item())
+
+
+def test_activation_backward_without_norm_and_colsum():
+    ops = _ops()
+    x = _rand((2, 16, 16, 64), 4)
+    g = _rand((2, 16, 16, 64), 5)
+    s = ops.bn_bwd_reduce(x, None, g, ops.ACT_LEAKY, slope=0.2)
+    dx = torch.empty_like(x)
+    ops.bn_bwd_apply(x, None, g, ops.ACT_LEAKY, None, ops.ACT_NONE, s, None, dx, slope=0.2)
+    ref = g.float() * torch.where(x.float() > 0, 1.0, 0.2)
+    assert (dx.float() - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
+    assert torch.allclose(s[:64], ref.sum((0, 1, 2)), rtol=1e-3, atol=1e-2)
+    assert torch.allclose(ops.colsum(x), x.float().sum((0, 1, 2)), rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("cin,c,act", [(1, 64, 1), (2, 64, 1), (1, 128, 0)])
+def test_smallc_conv_fprop_and_wgrad(cin, c, act):
+    ops = _ops()
+    n, h, w = 2, 64, 48
+    planes = [torch.randn(n, h, w, device="cuda") for _ in range(cin)]
+    wt = torch.randn(c, cin, 4, 4, device="cuda") * 0.1
+    bias = torch.randn(c, device="cuda")
+    wtm = wt.permute(0, 2, 3, 1).reshape(c, 16, cin).contiguous()
+    o1 = torch.empty(n, h // 2, w // 2, c, dtype=torch.bfloat16, device="cuda")
+    o2 = torch.empty(n, h // 2, w // 2, 2 * c, dtype=torch.bfloat16, device="cuda")
+    ops.smallc_conv_fprop(planes, wtm, bias, o1, act, o2[..., c:], ops.ACT_RELU, stride=2)
+    xin = torch.stack(planes, 1)
+    ref = F.conv2d(xin, wt, bias, stride=2, padding=1)
+    r1 = F.leaky_relu(ref, 0.2) if act == 1 else ref
+    assert (o1.float().permute(0, 3, 1, 2) - r1).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+    assert (o2[..., c:].float().permute(0, 3, 1, 2) - F.relu(ref)).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+    # wgrad
+    gy = _rand((n, h // 2, w // 2, c), 7)
+    dw = ops.smallc_conv_wgrad(gy, planes, stride=2)
+    wr = wt.clone().requires_grad_(True)
+    F.conv2d(xin, wr, None, stride=2, padding=1).backward(gy.float().permute(0, 3, 1, 2))
+    got = dw.view(c, 4, 4, cin).permute(0, 3, 1, 2)
+    assert (got - wr.grad).abs().max().item() < 2e-3 * max(1.0, wr.grad.abs().max().item())
+
+
+def test_smallc_as_convT_cout1_gradients():
+    """dec7: ConvTranspose2d(128, 1, 4, 2, 1) data / weight gradient."""
+    ops = _ops()
+    n, h, w, cin = 2, 32, 32, 128
+    x = _rand((n, h, w, cin), 8)
+    wt = (torch.randn(cin, 1, 4, 4, device="cuda") * 0.1).requires_grad_(True)
+    g = torch.randn(n, 2 * h, 2 * w, device="cuda")
+    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    F.conv_transpose2d(xr, wt, None, stride=2, padding=1).backward(g.view(n, 1, 2 * h, 2 * w))
+    dx = torch.empty_like(x)
+    ops.smallc_conv_fprop([g], wt.detach().reshape(cin, 16, 1), None, dx, ops.ACT_NONE, stride=2)
+    ref = xr.grad.permute(0, 2, 3, 1)
+    assert (dx.float() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+    dw = ops.smallc_conv_wgrad(x, [g], stride=2)
+    assert (dw.view(cin, 1, 4, 4) - wt.grad).abs().max().item() < 2e-3 * max(1.0, wt.grad.abs().max().item())
+
+
+def test_smallc_as_stride1_cout1_gradients():
+    """D4: Conv2d(512, 1, 4, 1, 1, bias=False) data / weight gradient (flipped taps)."""
+    ops = _ops()
+    n, h, w, cin = 3, 16, 16, 512
+    x = _rand((n, h, w, cin), 9)
+    wt = (torch.randn(1, cin, 4, 4, device="cuda") * 0.1).requires_grad_(True)
+    g = torch.randn(n, h - 1, w - 1, device="cuda")
+    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    F.conv2d(xr, wt, None, stride=1, padding=1).backward(g.view(n, 1, h - 1, w - 1))
+    dx = torch.empty_like(x)
+    ops.smallc_conv_fprop([g], wt.detach()[0].reshape(cin, 16, 1), None, dx, ops.ACT_NONE, stride=1, flip=True)
+    ref = xr.grad.permute(0, 2, 3, 1)
+    assert (dx.float() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+    dw = ops.smallc_conv_wgrad(x, [g], stride=1, flip=True)
+    assert (dw.view(cin, 4, 4, 1).permute(3, 0, 1, 2) - wt.grad).abs().max().item() < 2e-3 * max(1.0, wt.grad.abs().max().item())

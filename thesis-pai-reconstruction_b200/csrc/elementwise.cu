@@ -1,0 +1,324 @@
+// BatchNorm2d (train / eval), pre-activation and activation-backward kernels on NHWC bf16 tensors.
+//
+// Reference call sites: nn.BatchNorm2d(eps=1e-5, momentum=0.1) after every Conv / ConvT of the U-Net
+// (models/pix2pix.py:70,106), the non-inplace pre-activations nn.LeakyReLU(0.2) / nn.ReLU()
+// (models/pix2pix.py:62,98) that consume the same BN output on the encoder and decoder side, the skip
+// torch.cat (models/pix2pix.py:212) and the PatchGAN LeakyReLU (models/wrapper.py:196-206).
+//
+// Layout: x is [m pixels][c channels] bf16 with `ld` elements between pixels (so outputs can land in
+// a channel slot of a concat buffer: zero-copy torch.cat).  Every thread owns 8 consecutive channels
+// (one 16-byte vector) and walks pixels with a grid stride; all kernels are HBM-bound streams.
+#include "pai_common.cuh"
+#include "pai_kernels.h"
+
+namespace pai {
+
+static constexpr int kEwThreads = 256;
+
+struct Vec8 {
+    float v[8];
+};
+__device__ __forceinline__ Vec8 load8(const __nv_bfloat16* p) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    Vec8 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        r.v[2 * i] = f.x;
+        r.v[2 * i + 1] = f.y;
+    }
+    return r;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const Vec8& r) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ Vec8 loadf8(const float* p) {
+    Vec8 r;
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    r.v[0] = a.x, r.v[1] = a.y, r.v[2] = a.z, r.v[3] = a.w, r.v[4] = b.x, r.v[5] = b.y, r.v[6] = b.z, r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ float act_fwd(float z, int act, float slope) {
+    if (act == PAI_ACT_LEAKY) return z > 0.f ? z : z * slope;
+    if (act == PAI_ACT_RELU) return fmaxf(z, 0.f);
+    return z;
+}
+__device__ __forceinline__ float act_grad(float z, int act, float slope) {
+    if (act == PAI_ACT_LEAKY) return z > 0.f ? 1.f : slope;
+    if (act == PAI_ACT_RELU) return z > 0.f ? 1.f : 0.f;
+    return 1.f;
+}
+
+// Block-level reduction of per-thread 8-channel partial sums (two quantities) followed by one
+// atomicAdd per channel: threads with equal (threadIdx.x % cv) own the same channels.
+__device__ __forceinline__ void block_reduce_2x8(const Vec8& a, const Vec8& b, int cv, int c, float* out) {
+    __shared__ float red[kEwThreads * 16];
+    float* mine = red + threadIdx.x * 16;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        mine[i] = a.v[i];
+        mine[8 + i] = b.v[i];
+    }
+    __syncthreads();
+    // thread t < cv*16 sums quantity (t / (cv*8)), channel (t % (cv*8)) over the kEwThreads/cv replicas
+    for (int t = threadIdx.x; t < cv * 16; t += kEwThreads) {
+        const int which = t / (cv * 8), ch = t - which * cv * 8;
+        const int vec = ch >> 3, lane = ch & 7;
+        float s = 0.f;
+        for (int r = vec; r < kEwThreads; r += cv) s += red[r * 16 + which * 8 + lane];
+        atomicAdd(out + which * c + ch, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kEwThreads)
+bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long m, int c, int ld, float* __restrict__ sums) {
+    const int cv = c >> 3;
+    const int vec = threadIdx.x % cv;
+    const long long ppb = kEwThreads / cv;  // pixels per block-iteration
+    Vec8 s, q;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s.v[i] = q.v[i] = 0.f;
+    for (long long pix = (long long)blockIdx.x * ppb + threadIdx.x / cv; pix < m; pix += (long long)gridDim.x * ppb) {
+        const Vec8 v = load8(x + pix * ld + vec * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            s.v[i] += v.v[i];
+            q.v[i] = fmaf(v.v[i], v.v[i], q.v[i]);
+        }
+    }
+    block_reduce_2x8(s, q, cv, c, sums);
+}
+
+// ss layout: [scale | shift | mean | invstd], each c floats
+__global__ void bn_finalize_kernel(const float* __restrict__ sums, long long m, int c, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, int training,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ ss) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c) return;
+    float mean, var;
+    if (training) {
+        mean = sums[ch] / (float)m;
+        var = fmaxf(sums[c + ch] / (float)m - mean * mean, 0.f);
+        if (running_mean != nullptr) {
+            const float unbiased = m > 1 ? var * ((float)m / (float)(m - 1)) : var;
+            running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
+            running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * unbiased;
+        }
+    } else {
+        mean = running_mean[ch];
+        var = running_var[ch];
+    }
+    const float invstd = rsqrtf(var + eps);
+    const float g = gamma != nullptr ? gamma[ch] : 1.f, b = beta != nullptr ? beta[ch] : 0.f;
+    ss[ch] = g * invstd;
+    ss[c + ch] = b - mean * g * invstd;
+    ss[2 * c + ch] = mean;
+    ss[3 * c + ch] = invstd;
+}
+
+__global__ void __launch_bounds__(kEwThreads)
+bn_apply_act_kernel(const __nv_bfloat16* __restrict__ x, long long m, int c, int ld, const float* __restrict__ ss,
+                    __nv_bfloat16* __restrict__ o1, int ld1, int act1, __nv_bfloat16* __restrict__ o2, int ld2,
+                    int act2, float slope) {
+    const int cv = c >> 3;
+    const int vec = threadIdx.x % cv;
+    const long long ppb = kEwThreads / cv;
+    Vec8 sc, sh;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sc.v[i] = 1.f, sh.v[i] = 0.f;
+    if (ss != nullptr) {
+        sc = loadf8(ss + vec * 8);
+        sh = loadf8(ss + c + vec * 8);
+    }
+    for (long long pix = (long long)blockIdx.x * ppb + threadIdx.x / cv; pix < m; pix += (long long)gridDim.x * ppb) {
+        const Vec8 v = load8(x + pix * ld + vec * 8);
+        Vec8 a, b;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float z = fmaf(v.v[i], sc.v[i], sh.v[i]);
+            a.v[i] = act_fwd(z, act1, slope);
+            b.v[i] = act_fwd(z, act2, slope);
+        }
+        store8(o1 + pix * ld1 + vec * 8, a);
+        if (o2 != nullptr) store8(o2 + pix * ld2 + vec * 8, b);
+    }
+}
+
+// dz = g1 * act1'(z) + g2 * act2'(z),  z = scale * x + shift,  xhat = (x - mean) * invstd
+template <bool APPLY>
+__global__ void __launch_bounds__(kEwThreads)
+bn_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long m, int c, int ld, const float* __restrict__ ss,
+              const __nv_bfloat16* __restrict__ g1, int ldg1, int act1, const __nv_bfloat16* __restrict__ g2,
+              int ldg2, int act2, float slope, float* __restrict__ sums, const float* __restrict__ gamma,
+              __nv_bfloat16* __restrict__ dx, int lddx) {
+    const int cv = c >> 3;
+    const int vec = threadIdx.x % cv;
+    const long long ppb = kEwThreads / cv;
+    Vec8 sc, sh, mu, is;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sc.v[i] = 1.f, sh.v[i] = 0.f, mu.v[i] = 0.f, is.v[i] = 1.f;
+    if (ss != nullptr) {
+        sc = loadf8(ss + vec * 8);
+        sh = loadf8(ss + c + vec * 8);
+        mu = loadf8(ss + 2 * c + vec * 8);
+        is = loadf8(ss + 3 * c + vec * 8);
+    }
+    Vec8 k0, k1, k2;  // APPLY: dx = k0 * dz + k1 + k2 * xhat   (k0 = gamma*invstd, k1 = -k0*mean(dz), k2 = -k0*mean(dz*xhat))
+    Vec8 s0, s1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s0.v[i] = s1.v[i] = 0.f;
+    if (APPLY) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (ss != nullptr) {
+                const float g = gamma != nullptr ? gamma[vec * 8 + i] : 1.f;
+                k0.v[i] = g * is.v[i];
+                k1.v[i] = -k0.v[i] * sums[vec * 8 + i] / (float)m;
+                k2.v[i] = -k0.v[i] * sums[c + vec * 8 + i] / (float)m;
+            } else {
+                k0.v[i] = 1.f, k1.v[i] = 0.f, k2.v[i] = 0.f;
+            }
+        }
+    }
+    for (long long pix = (long long)blockIdx.x * ppb + threadIdx.x / cv; pix < m; pix += (long long)gridDim.x * ppb) {
+        const Vec8 v = load8(x + pix * ld + vec * 8);
+        const Vec8 a = load8(g1 + pix * ldg1 + vec * 8);
+        Vec8 b;
+        if (g2 != nullptr) b = load8(g2 + pix * ldg2 + vec * 8);
+        Vec8 o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float z = fmaf(v.v[i], sc.v[i], sh.v[i]);
+            float dz = a.v[i] * act_grad(z, act1, slope);
+            if (g2 != nullptr) dz = fmaf(b.v[i], act_grad(z, act2, slope), dz);
+            const float xh = (v.v[i] - mu.v[i]) * is.v[i];
+            if (APPLY) {
+                o.v[i] = fmaf(k0.v[i], dz, fmaf(k2.v[i], xh, k1.v[i]));
+            } else {
+                s0.v[i] += dz;
+                s1.v[i] = fmaf(dz, xh, s1.v[i]);
+            }
+        }
+        if (APPLY) store8(dx + pix * lddx + vec * 8, o);
+    }
+    if (!APPLY) block_reduce_2x8(s0, s1, cv, c, sums);
+}
+
+// per-channel column sum of a bf16 [m, c] matrix (bias gradients)
+__global__ void __launch_bounds__(kEwThreads)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, long long m, int c, int ld, float* __restrict__ sums) {
+    const int cv = c >> 3;
+    const int vec = threadIdx.x % cv;
+    const long long ppb = kEwThreads / cv;
+    Vec8 s, q;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s.v[i] = q.v[i] = 0.f;
+    for (long long pix = (long long)blockIdx.x * ppb + threadIdx.x / cv; pix < m; pix += (long long)gridDim.x * ppb) {
+        const Vec8 v = load8(x + pix * ld + vec * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s.v[i] += v.v[i];
+    }
+    // reuse the 2-quantity reducer; the second quantity is discarded into sums[c..2c)
+    block_reduce_2x8(s, q, cv, c, sums);
+}
+
+static int ew_grid(long long m, int c) {
+    const long long ppb = kEwThreads / (c >> 3);
+    long long blocks = (m + ppb - 1) / ppb;
+    const long long cap = 148LL * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+static bool ew_ok(int c, const void* p, int ld) {
+    const int cv = c >> 3;
+    return c > 0 && c % 8 == 0 && cv <= kEwThreads && kEwThreads % cv == 0 && ld % 8 == 0 &&
+           (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+}
+
+}  // namespace pai
+
+using namespace pai;
+typedef __nv_bfloat16 bf16;
+
+extern "C" {
+
+int pai_bn_stats(const void* x, long long m, int c, int ld, float* sums, void* stream) {
+    PAI_REQUIRE(x && sums && m > 0, "pai_bn_stats: null pointer / empty input");
+    PAI_REQUIRE(ew_ok(c, x, ld), "pai_bn_stats: c=%d ld=%d must be multiples of 8 with (c/8) | 256, x 16 B aligned", c, ld);
+    cudaStream_t st = (cudaStream_t)stream;
+    PAI_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, st));
+    bn_stats_kernel<<<ew_grid(m, c), kEwThreads, 0, st>>>((const bf16*)x, m, c, ld, sums);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pai_bn_finalize(const float* sums, long long m, int c, const float* gamma, const float* beta, float eps,
+                    float momentum, int training, float* running_mean, float* running_var, float* scale_shift,
+                    void* stream) {
+    PAI_REQUIRE(scale_shift && (training ? sums != nullptr : (running_mean && running_var)),
+                "pai_bn_finalize: null pointer");
+    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, m, c, gamma, beta, eps, momentum,
+                                                                          training, running_mean, running_var,
+                                                                          scale_shift);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pai_bn_apply_act(const void* x, long long m, int c, int ld, const float* scale_shift, void* out1, int ld1,
+                     int act1, void* out2, int ld2, int act2, float slope, void* stream) {
+    PAI_REQUIRE(x && out1 && m > 0, "pai_bn_apply_act: null pointer / empty input");
+    PAI_REQUIRE(ew_ok(c, x, ld) && ew_ok(c, out1, ld1) && (out2 == nullptr || ew_ok(c, out2, ld2)),
+                "pai_bn_apply_act: bad channel count / stride / alignment (c=%d)", c);
+    bn_apply_act_kernel<<<ew_grid(m, c), kEwThreads, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, m, c, ld, scale_shift, (bf16*)out1, ld1, act1, (bf16*)out2, ld2, act2, slope);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pai_bn_bwd_reduce(const void* x, long long m, int c, int ld, const float* scale_shift, const void* g1, int ldg1,
+                      int act1, const void* g2, int ldg2, int act2, float slope, float* sums, void* stream) {
+    PAI_REQUIRE(x && g1 && sums && m > 0, "pai_bn_bwd_reduce: null pointer / empty input");
+    PAI_REQUIRE(ew_ok(c, x, ld) && ew_ok(c, g1, ldg1) && (g2 == nullptr || ew_ok(c, g2, ldg2)),
+                "pai_bn_bwd_reduce: bad channel count / stride / alignment (c=%d)", c);
+    cudaStream_t st = (cudaStream_t)stream;
+    PAI_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, st));
+    bn_bwd_kernel<false><<<ew_grid(m, c), kEwThreads, 0, st>>>((const bf16*)x, m, c, ld, scale_shift, (const bf16*)g1,
+                                                                ldg1, act1, (const bf16*)g2, ldg2, act2, slope, sums,
+                                                                nullptr, nullptr, 0);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pai_bn_bwd_apply(const void* x, long long m, int c, int ld, const float* scale_shift, const void* g1, int ldg1,
+                     int act1, const void* g2, int ldg2, int act2, float slope, const float* sums,
+                     const float* gamma, void* dx, int lddx, void* stream) {
+    PAI_REQUIRE(x && g1 && dx && m > 0 && (scale_shift == nullptr || sums != nullptr),
+                "pai_bn_bwd_apply: null pointer / empty input");
+    PAI_REQUIRE(ew_ok(c, x, ld) && ew_ok(c, g1, ldg1) && (g2 == nullptr || ew_ok(c, g2, ldg2)) && ew_ok(c, dx, lddx),
+                "pai_bn_bwd_apply: bad channel count / stride / alignment (c=%d)", c);
+    bn_bwd_kernel<true><<<ew_grid(m, c), kEwThreads, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, m, c, ld, scale_shift, (const bf16*)g1, ldg1, act1, (const bf16*)g2, ldg2, act2, slope,
+        const_cast<float*>(sums), gamma, (bf16*)dx, lddx);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pai_colsum(const void* x, long long m, int c, int ld, float* sums2c, void* stream) {
+    PAI_REQUIRE(x && sums2c && m > 0, "pai_colsum: null pointer / empty input");
+    PAI_REQUIRE(ew_ok(c, x, ld), "pai_colsum: bad channel count / stride / alignment (c=%d)", c);
+    cudaStream_t st = (cudaStream_t)stream;
+    PAI_CUDA_OK(cudaMemsetAsync(sums2c, 0, sizeof(float) * 2 * c, st));
+    colsum_kernel<<<ew_grid(m, c), kEwThreads, 0, st>>>((const bf16*)x, m, c, ld, sums2c);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

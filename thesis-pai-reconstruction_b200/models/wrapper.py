@@ -1,0 +1,158 @@
+"""Mirror of /root/reference/models/wrapper.py (``UnetWrapper``, ``DiscriminatorBlock``,
+``Discriminator``) on the B200 kernels.
+
+* the module tree, ``state_dict`` keys and constructor signatures are the reference's, so checkpoints
+  and ``main.py`` / ``report.py`` work unchanged;
+* ``Discriminator.forward`` is one fused autograd node (pai_b200.engine.DiscFunction);
+* ``training_step`` keeps the reference's order of operations (wrapper.py:117-162: D step on a
+  graph-free generator forward, then the G step) but evaluates the loss and the three logged metrics
+  from ONE pass of the SSIM/PSNR/MSE kernel instead of four torchmetrics calls.
+"""
+from typing import Literal
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from pai_b200 import engine, metrics
+
+from ._lightning import LightningModule
+from .utils import denormalize, init_weights, psnr, rmse, ssim  # noqa: F401  (re-exported like the reference)
+
+_ADAM = dict(lr=2e-4, betas=(0.5, 0.999), eps=1e-7)        # wrapper.py:98-111
+
+
+class UnetWrapper(LightningModule):
+    """U-net wrapper with the five reference loss types: "gan", "ssim", "psnr", "ssim+psnr", "mse"."""
+
+    def __init__(self, unet: nn.Module, loss_type: Literal["gan", "ssim", "psnr", "ssim+psnr", "mse"] = "gan"):
+        super().__init__()
+        self.automatic_optimization = False
+        self.unet = unet
+        self.loss_type = loss_type
+        self.discriminator = None
+        if loss_type == "gan":
+            # same construction order as the reference so a shared seed gives identical weights
+            self.discriminator = Discriminator()
+            self.discriminator.apply(init_weights)
+        self.unet.apply(init_weights)
+
+    def forward(self, x):
+        return self.unet(x)
+
+    # ---- losses ---------------------------------------------------------------------------------
+    def loss(self, x, pred, target):
+        kind = self.loss_type
+        if kind == "gan":
+            pred_label = self.discriminator(x, pred)
+            adversarial = F.binary_cross_entropy_with_logits(pred_label, torch.ones_like(pred_label))
+            return adversarial + 50 * F.l1_loss(pred, target)
+        if kind == "mse":
+            return F.mse_loss(pred, target)
+        if kind in ("ssim", "psnr", "ssim+psnr"):
+            s, p, _ = metrics.train_metrics(pred, target, denormalize=True)
+            return {"ssim": -s, "psnr": -p, "ssim+psnr": -(30 * s + p)}[kind]
+        return None
+
+    def discriminator_loss(self, pred_label: torch.Tensor, target_label: torch.Tensor) -> torch.Tensor:
+        fake = F.binary_cross_entropy_with_logits(pred_label, torch.zeros_like(pred_label))
+        real = F.binary_cross_entropy_with_logits(target_label, torch.ones_like(pred_label))
+        return fake + real
+
+    def configure_optimizers(self):
+        opt_g = torch.optim.Adam(self.unet.parameters(), **_ADAM)
+        if self.discriminator is None:
+            return opt_g
+        return opt_g, torch.optim.Adam(self.discriminator.parameters(), **_ADAM)
+
+    # ---- steps ----------------------------------------------------------------------------------
+    def training_step(self, batch, batch_idx):
+        x, target = batch
+        if self.loss_type == "gan":
+            opt_d = self.optimizers()[1]
+            self.toggle_optimizer(opt_d)            # generator frozen: its forward builds no graph
+            pred = self.unet(x)
+            target_label = self.discriminator(x, target)
+            pred_label = self.discriminator(x, pred)
+            d_loss = self.discriminator_loss(pred_label, target_label)
+            self.log("d_loss", d_loss, prog_bar=True)
+            self.discriminator.zero_grad(set_to_none=True)
+            self.manual_backward(d_loss)
+            opt_d.step()
+            self.untoggle_optimizer(opt_d)
+
+        opt_g = self.optimizers()
+        if isinstance(opt_g, list):
+            opt_g = opt_g[0]
+        self.toggle_optimizer(opt_g)                # discriminator frozen: its backward is dgrad-only
+        pred = self.unet(x)
+        s, p, r = metrics.train_metrics(pred, target, denormalize=True)   # one kernel: loss terms + metrics
+        kind = self.loss_type
+        if kind == "ssim":
+            loss = -s
+        elif kind == "psnr":
+            loss = -p
+        elif kind == "ssim+psnr":
+            loss = -(30 * s + p)
+        else:
+            loss = self.loss(x, pred, target)
+        self.log("loss", loss, prog_bar=True)
+        self.log("train_ssim", s, prog_bar=True)
+        self.log("train_psnr", p, prog_bar=True)
+        self.log("train_rmse", r, prog_bar=True)
+        self.unet.zero_grad(set_to_none=True)
+        self.manual_backward(loss)
+        opt_g.step()
+        self.untoggle_optimizer(opt_g)
+
+    def validation_step(self, batch, batch_idx):
+        x, target = batch
+        pred = self.forward(x)
+        s, p, r = metrics.train_metrics(pred.detach(), target, denormalize=True)
+        self.log("val_ssim", s, prog_bar=True)
+        self.log("val_psnr", p, prog_bar=True)
+        self.log("val_rmse", r, prog_bar=True)
+
+
+class DiscriminatorBlock(nn.Module):
+    """Conv4x4 s2 p1 (+ optional InstanceNorm) + LeakyReLU(0.2) -- parameter holder; the arithmetic of
+    a whole ``Discriminator`` runs in pai_b200.engine."""
+
+    def __init__(self, in_channels: int, out_channels: int, norm: bool = False):
+        super().__init__()
+        if norm:
+            raise RuntimeError("pai_b200: DiscriminatorBlock(norm=True) is never instantiated by the reference "
+                               "(wrapper.py:192,228-232) and has no B200 kernel")
+        self.block = nn.Sequential(
+            nn.Conv2d(in_channels, out_channels, kernel_size=4, stride=2, padding=1),
+            nn.Identity(),
+            nn.LeakyReLU(0.2),
+        )
+
+    def forward(self, x):
+        raise RuntimeError("pai_b200: DiscriminatorBlock is executed as part of Discriminator.forward")
+
+
+class Discriminator(nn.Module):
+    """PatchGAN discriminator, ``forward(x, y) -> logits [N, 1, H/16-1, W/16-1]``."""
+
+    def __init__(self, in_channels: int = 3):
+        super().__init__()
+        widths = (64, 128, 256, 512)
+        layers, cin = [], in_channels * 2
+        for wd in widths:
+            layers.append(DiscriminatorBlock(cin, wd))
+            cin = wd
+        layers.append(nn.Conv2d(cin, 1, kernel_size=4, padding=1, bias=False))
+        self.discriminator = nn.Sequential(*layers)
+        self._spec = None
+
+    def _engine_spec(self):
+        if self._spec is None:
+            convs = [blk.block[0] for blk in list(self.discriminator)[:-1]] + [self.discriminator[-1]]
+            self._spec = engine.DiscSpec(convs)
+        return self._spec
+
+    def forward(self, x, y):
+        spec = self._engine_spec()
+        return engine.DiscFunction.apply(spec, x, y, *spec.params())

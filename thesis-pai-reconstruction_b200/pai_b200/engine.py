@@ -1,0 +1,384 @@
+"""Whole-network fused forward / backward of the Pix2Pix U-Net generator and the PatchGAN
+discriminator on the B200 kernels, exposed as two ``torch.autograd.Function``s.
+
+Reference semantics (file:line in /root/reference):
+* ``Unet.forward``            models/pix2pix.py:198-216 (ctor :130-196): 8x [LeakyReLU -> Conv4x4 s2 -> BN],
+  8x [ReLU -> ConvT4x4 s2 -> BN] with skip concat, Tanh; the skips are the *un-activated* BN outputs.
+* ``Discriminator.forward``   models/wrapper.py:236-238 (blocks :196-206, :228-234).
+
+Data layout in HBM: activations and gradients NHWC bf16; every decoder input is ONE buffer
+``[N, h, w, 2C]`` whose first half is written by the previous decoder's BN+ReLU kernel and whose second
+half is written by the matching encoder's BN kernel (zero-copy ``torch.cat``).  Parameters stay fp32 in
+the reference's ``state_dict`` layout; bf16 GEMM packs are rebuilt when a parameter's version changes.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import ops
+from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH
+
+BN_EPS, BN_MOMENTUM, SLOPE = 1e-5, 0.1, 0.2
+
+
+# ------------------------------------------------------------------------------------------ pack cache
+class _PackCache:
+    """bf16 GEMM operand packs of fp32 master weights, keyed by (tag, parameter identity, version)."""
+
+    def __init__(self):
+        self._c = {}
+
+    def get(self, tag: str, p: torch.Tensor, fn):
+        key = (tag, id(p))
+        stamp = (p._version, p.data_ptr())
+        ent = self._c.get(key)
+        if ent is None or ent[0] != stamp:
+            with torch.no_grad():
+                ent = (stamp, fn(p.detach()))
+            self._c[key] = ent
+        return ent[1]
+
+
+_packs = _PackCache()
+
+
+def _fprop_pack(w):      # Conv2d weight [Cout, Cin, 4, 4]
+    return _packs.get("conv_f", w, ops.pack_conv_weight)
+
+
+def _dgrad_pack(w):      # Conv2d dgrad == ConvT fprop with the weight read as [in=Cout, out=Cin]
+    return _packs.get("conv_d", w, ops.pack_convT_weight)
+
+
+def _fpropT_pack(w):     # ConvTranspose2d weight [Cin, Cout, 4, 4]
+    return _packs.get("convT_f", w, ops.pack_convT_weight)
+
+
+def _dgradT_pack(w):     # ConvT dgrad == Conv fprop with the weight read as [out=Cin, in=Cout]
+    return _packs.get("convT_d", w, ops.pack_conv_weight)
+
+
+def _w_tap_major(w):     # [C, cin, 4, 4] -> fp32 [C, 16, cin] for the direct kernels
+    c, cin = w.shape[0], w.shape[1]
+    if cin == 1:
+        return w.detach().reshape(c, 16, 1)
+    return _packs.get("small", w, lambda t: t.permute(0, 2, 3, 1).reshape(c, 16, cin).contiguous())
+
+
+def _bf16(*shape, device):
+    return torch.empty(*shape, dtype=torch.bfloat16, device=device)
+
+
+class BNState:
+    """Live view of one nn.BatchNorm2d of the drop-in module tree (attributes are read through the
+    module so ``model.cuda()`` / ``load_state_dict`` are picked up)."""
+
+    def __init__(self, mod):
+        self.mod = mod
+
+    weight = property(lambda self: self.mod.weight)
+    bias = property(lambda self: self.mod.bias)
+    running_mean = property(lambda self: self.mod.running_mean)
+    running_var = property(lambda self: self.mod.running_var)
+    num_batches_tracked = property(lambda self: self.mod.num_batches_tracked)
+
+
+def _batchnorm(raw, bn: BNState, training: bool):
+    """-> scale_shift [4C] of BN over the pixels of ``raw``; updates running stats when training."""
+    m, c, _ = ops._mat(raw)
+    sums = ops.bn_stats(raw) if training else None
+    ss = ops.bn_finalize(sums, m, c, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
+                         training=training, eps=BN_EPS, momentum=BN_MOMENTUM)
+    if training:
+        bn.num_batches_tracked.add_(1)
+    return ss
+
+
+# ------------------------------------------------------------------------------------------ generator
+class UnetSpec:
+    """Shapes + parameter holders of a reference-layout Unet (built by models/pix2pix.py:Unet)."""
+
+    def __init__(self, enc_convs, enc_bns, dec_convs, dec_bns):
+        self.enc_convs, self.enc_bns = enc_convs, [None if b is None else BNState(b) for b in enc_bns]
+        self.dec_convs, self.dec_bns = dec_convs, [None if b is None else BNState(b) for b in dec_bns]
+        self.levels = len(enc_convs)
+        self.enc_ch = [c.weight.shape[0] for c in enc_convs]
+        self.in_ch = enc_convs[0].weight.shape[1]
+        self.out_ch = dec_convs[-1].weight.shape[1]
+        self.dec_out = [c.weight.shape[1] for c in dec_convs]
+        if self.in_ch != 1 or self.out_ch != 1:
+            raise RuntimeError("pai_b200: the B200 path supports in_channels == out_channels == 1 (grayscale PAI "
+                               f"images, main.py:26-27); got {self.in_ch}/{self.out_ch}. No fallback exists.")
+        for c in self.enc_ch + self.dec_out[:-1]:
+            if c % 64:
+                raise RuntimeError(f"pai_b200: channel counts must be multiples of 64 (got {c})")
+
+    def params(self) -> List[torch.Tensor]:
+        ps = []
+        for conv, bn in list(zip(self.enc_convs, self.enc_bns)) + list(zip(self.dec_convs, self.dec_bns)):
+            ps += [conv.weight, conv.bias]
+            if bn is not None:
+                ps += [bn.weight, bn.bias]
+        return ps
+
+
+class _Saved:
+    pass
+
+
+def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
+    """x: [N, 1, H, W] fp32 (cuda) -> (y [N, 1, H, W] fp32 in (-1, 1), saved-or-None)."""
+    L = spec.levels
+    n, _, h, w = x.shape
+    if h % (1 << L) or w % (1 << L):
+        raise RuntimeError(f"pai_b200: input {h}x{w} must be divisible by 2^{L}")
+    dev = x.device
+    x = x.contiguous().float()
+    plane = x.view(n, h, w)
+    ch = spec.enc_ch
+    hs = [h >> (i + 1) for i in range(L)]
+    ws = [w >> (i + 1) for i in range(L)]
+    s = _Saved()
+    # decoder j (>=1) reads cat[j]: [N, hs[L-1-j], ws[L-1-j], 2*C] with C = ch[L-1-j]
+    cat = [None] + [_bf16(n, hs[L - 1 - j], ws[L - 1 - j], 2 * ch[L - 1 - j], device=dev) for j in range(1, L)]
+    a_in = [None] * (L + 1)                    # a_in[i]: activated input of encoder i (i >= 1)
+    raw_e, ss_e = [None] * L, [None] * L
+    # ---- encoder 0 (no activation before, no BN after): skip = raw output
+    c0 = ch[0]
+    a_in[1] = _bf16(n, hs[0], ws[0], c0, device=dev)
+    conv0 = spec.enc_convs[0]
+    # The last decoder is a bare ConvTranspose2d (models/pix2pix.py:185-193): no ReLU in front of it, so
+    # its concat buffer cat[L-1] holds UN-activated values; every other decoder starts with a ReLU.
+    ops.smallc_conv_fprop([plane], _w_tap_major(conv0.weight), conv0.bias.detach(), a_in[1], ACT_LEAKY,
+                          cat[L - 1][..., c0:], ACT_NONE, stride=2, slope=SLOPE)
+    # ---- encoders 1..L-1
+    for i in range(1, L):
+        conv, bn = spec.enc_convs[i], spec.enc_bns[i]
+        if i < L - 1:
+            raw = ops.conv4x4_fprop(a_in[i], _fprop_pack(conv.weight), ch[i], stride=2, bias=conv.bias.detach())
+            if bn is not None:
+                ss = _batchnorm(raw, bn, training)
+            else:
+                ss = None
+            a_in[i + 1] = _bf16(n, hs[i], ws[i], ch[i], device=dev)
+            ops.bn_apply_act(raw, ss, a_in[i + 1], ACT_LEAKY, cat[L - 1 - i][..., ch[i]:], ACT_RELU, slope=SLOPE)
+            raw_e[i], ss_e[i] = raw, ss
+        else:
+            # bottleneck: Identity norm (models/pix2pix.py:157), only consumer is decoder 0's ReLU
+            dec_in0 = ops.conv4x4_fprop(a_in[i], _fprop_pack(conv.weight), ch[i], stride=2, bias=conv.bias.detach(),
+                                        act=ACT_RELU)
+    # ---- decoders 0..L-2 (BN), L-1 (Tanh)
+    raw_d, ss_d = [None] * L, [None] * L
+    d_in = dec_in0
+    for j in range(L - 1):
+        conv, bn = spec.dec_convs[j], spec.dec_bns[j]
+        co = spec.dec_out[j]
+        raw = ops.convT4x4s2_fprop(d_in, _fpropT_pack(conv.weight), co, bias=conv.bias.detach())
+        ss = _batchnorm(raw, bn, training)
+        ops.bn_apply_act(raw, ss, cat[j + 1][..., :co], ACT_RELU if j + 1 < L - 1 else ACT_NONE)
+        raw_d[j], ss_d[j] = raw, ss
+        d_in = cat[j + 1]
+    last = spec.dec_convs[L - 1]
+    y = ops.convT4x4s2_fprop(d_in, _fpropT_pack(last.weight), 1, bias=last.bias.detach(), act=ACT_TANH, out_f32=True)
+    y = y.view(n, 1, h, w)                      # NHWC with C == 1 is NCHW
+    if not save:
+        return y, None
+    s.plane, s.cat, s.a_in, s.raw_e, s.ss_e, s.raw_d, s.ss_d, s.dec_in0, s.y = plane, cat, a_in, raw_e, ss_e, raw_d, ss_d, dec_in0, y
+    return y, s
+
+
+def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
+    """-> list of gradients aligned with ``spec.params()`` (reference layouts, fp32)."""
+    L = spec.levels
+    ch = spec.enc_ch
+    y = s.y
+    n, _, h, w = y.shape
+    dev = y.device
+    g_pre = (grad_y.float() * (1.0 - y * y)).contiguous().view(n, h, w)        # through Tanh
+    grads = {}
+    # ---- last decoder: ConvT(2*c0 -> 1)
+    last = spec.dec_convs[L - 1]
+    cin_last = last.weight.shape[0]
+    dw = ops.smallc_conv_wgrad(s.cat[L - 1], [g_pre], stride=2)                 # [cin, 16, 1]
+    grads[(1, L - 1)] = (dw.view(cin_last, 1, 4, 4), g_pre.sum().reshape(1))
+    dcat = _bf16(*s.cat[L - 1].shape, device=dev)
+    ops.smallc_conv_fprop([g_pre], _w_tap_major(last.weight), None, dcat, ACT_NONE, stride=2)
+    # ---- decoders L-2 .. 0
+    dskip = [None] * L                          # dskip[i]: grad w.r.t. relu(skip_i) (second half of dcat)
+    for j in range(L - 2, -1, -1):
+        conv, bn = spec.dec_convs[j], spec.dec_bns[j]
+        co = spec.dec_out[j]
+        enc_i = L - 2 - j                       # encoder whose skip sits in cat[j+1]
+        dskip[enc_i] = dcat[..., co:]
+        g1 = dcat[..., :co]
+        raw, ss = s.raw_d[j], s.ss_d[j]
+        act_out = ACT_RELU if j + 1 < L - 1 else ACT_NONE     # consumer of this decoder's output
+        sums = ops.bn_bwd_reduce(raw, ss, g1, act_out)
+        d_raw = _bf16(*raw.shape, device=dev)
+        ops.bn_bwd_apply(raw, ss, g1, act_out, None, ACT_NONE, sums, bn.weight.detach(), d_raw)
+        d_in = s.cat[j] if j > 0 else s.dec_in0
+        cin = conv.weight.shape[0]
+        dwt = ops.convT4x4s2_wgrad(d_in, d_raw)                                  # [16, cin, co]
+        grads[(1, j)] = (dwt.permute(1, 2, 0).reshape(cin, co, 4, 4), torch.zeros(co, device=dev),
+                         sums[co:], sums[:co])
+        dcat = ops.conv4x4_fprop(d_raw, _dgradT_pack(conv.weight), cin, stride=2)   # grad w.r.t. decoder input
+    # ---- bottleneck encoder L-1: dec_in0 = relu(conv + bias)
+    i = L - 1
+    conv = spec.enc_convs[i]
+    sums = ops.bn_bwd_reduce(s.dec_in0, None, dcat, ACT_RELU)
+    d_raw = _bf16(*s.dec_in0.shape, device=dev)
+    ops.bn_bwd_apply(s.dec_in0, None, dcat, ACT_RELU, None, ACT_NONE, sums, None, d_raw)
+    dwc = ops.conv4x4_wgrad(s.a_in[i], d_raw, stride=2)                          # [16, co, ci]
+    grads[(0, i)] = (dwc.permute(1, 2, 0).reshape(ch[i], ch[i - 1], 4, 4), sums[:ch[i]].clone())
+    d_a = ops.convT4x4s2_fprop(d_raw, _dgrad_pack(conv.weight), ch[i - 1])
+    # ---- encoders L-2 .. 1
+    for i in range(L - 2, 0, -1):
+        conv, bn = spec.enc_convs[i], spec.enc_bns[i]
+        raw, ss = s.raw_e[i], s.ss_e[i]
+        sums = ops.bn_bwd_reduce(raw, ss, d_a, ACT_LEAKY, dskip[i], ACT_RELU, slope=SLOPE)
+        d_raw = _bf16(*raw.shape, device=dev)
+        ops.bn_bwd_apply(raw, ss, d_a, ACT_LEAKY, dskip[i], ACT_RELU, sums, None if bn is None else bn.weight.detach(),
+                         d_raw, slope=SLOPE)
+        dwc = ops.conv4x4_wgrad(s.a_in[i], d_raw, stride=2)
+        gw = dwc.permute(1, 2, 0).reshape(ch[i], ch[i - 1], 4, 4)
+        if bn is not None:
+            grads[(0, i)] = (gw, torch.zeros(ch[i], device=dev), sums[ch[i]:], sums[:ch[i]])
+        else:
+            grads[(0, i)] = (gw, sums[:ch[i]].clone())
+        d_a = ops.convT4x4s2_fprop(d_raw, _dgrad_pack(conv.weight), ch[i - 1])
+    # ---- encoder 0: a_in[1] = lrelu(e0) has the sign of e0, so it doubles as the activation mask
+    c0 = ch[0]
+    sums = ops.bn_bwd_reduce(s.a_in[1], None, d_a, ACT_LEAKY, dskip[0], ACT_NONE, slope=SLOPE)
+    d_raw = _bf16(*s.a_in[1].shape, device=dev)
+    ops.bn_bwd_apply(s.a_in[1], None, d_a, ACT_LEAKY, dskip[0], ACT_NONE, sums, None, d_raw, slope=SLOPE)
+    dw0 = ops.smallc_conv_wgrad(d_raw, [s.plane], stride=2)                      # [c0, 16, 1]
+    grads[(0, 0)] = (dw0.view(c0, 1, 4, 4), sums[:c0].clone())
+    out = []
+    for i in range(L):
+        out += list(grads[(0, i)])
+    for j in range(L):
+        out += list(grads[(1, j)])
+    return out
+
+
+class UnetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec: UnetSpec, training: bool, x: torch.Tensor, *params):
+        need = any(ctx.needs_input_grad[3:])
+        y, saved = unet_forward(spec, x, training, save=need)
+        ctx.spec, ctx.saved = spec, saved
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        if ctx.saved is None:
+            raise RuntimeError("pai_b200: generator backward requested but the forward ran without a graph")
+        grads = unet_backward(ctx.spec, ctx.saved, grad_y)
+        ctx.saved = None
+        need = ctx.needs_input_grad[3:]
+        return (None, None, None) + tuple(g if nd else None for g, nd in zip(grads, need))
+
+
+# ------------------------------------------------------------------------------------------ discriminator
+class DiscSpec:
+    def __init__(self, convs):
+        self.convs = convs                       # 4 stride-2 convs (bias) + final stride-1 conv (no bias)
+        self.ch = [c.weight.shape[0] for c in convs]
+        cin0 = convs[0].weight.shape[1]
+        if cin0 != 2:
+            raise RuntimeError("pai_b200: the B200 PatchGAN path takes cat([x, y]) of two 1-channel images "
+                               f"(Discriminator(in_channels=1), SURVEY.md Q1); the first conv has {cin0} inputs")
+        if self.ch[-1] != 1 or convs[-1].bias is not None:
+            raise RuntimeError("pai_b200: unexpected PatchGAN head")
+
+    def params(self):
+        ps = []
+        for c in self.convs[:-1]:
+            ps += [c.weight, c.bias]
+        ps.append(self.convs[-1].weight)
+        return ps
+
+
+def disc_forward(spec: DiscSpec, x: torch.Tensor, y: torch.Tensor, save: bool):
+    n, _, h, w = x.shape
+    dev = x.device
+    px = x.contiguous().float().view(n, h, w)
+    py = y.contiguous().float().view(n, h, w)
+    c0 = spec.convs[0]
+    hcur = _bf16(n, h // 2, w // 2, spec.ch[0], device=dev)
+    ops.smallc_conv_fprop([px, py], _w_tap_major(c0.weight), c0.bias.detach(), hcur, ACT_LEAKY, stride=2, slope=SLOPE)
+    hs = [hcur]
+    for k in range(1, len(spec.convs) - 1):
+        c = spec.convs[k]
+        hcur = ops.conv4x4_fprop(hcur, _fprop_pack(c.weight), spec.ch[k], stride=2, bias=c.bias.detach(),
+                                 act=ACT_LEAKY, slope=SLOPE)
+        hs.append(hcur)
+    head = spec.convs[-1]
+    logits = ops.conv4x4_fprop(hcur, _fprop_pack(head.weight), 1, stride=1, out_f32=True)
+    nb, lh, lw, _ = logits.shape
+    logits = logits.view(nb, 1, lh, lw)
+    if not save:
+        return logits, None
+    s = _Saved()
+    s.px, s.py, s.hs = px, py, hs
+    return logits, s
+
+
+def disc_backward(spec: DiscSpec, s: _Saved, g_logits: torch.Tensor, need_params: bool, need_y: bool):
+    dev = g_logits.device
+    n, _, lh, lw = g_logits.shape
+    g = g_logits.contiguous().float().view(n, lh, lw)
+    K = len(spec.convs)
+    head = spec.convs[-1]
+    h_last = s.hs[-1]
+    c_last = h_last.shape[3]
+    grads = [None] * (2 * (K - 1) + 1)
+    if need_params:
+        dwh = ops.smallc_conv_wgrad(h_last, [g], stride=1, flip=True)             # [c, 16, 1]
+        grads[-1] = dwh.view(c_last, 4, 4, 1).permute(3, 0, 1, 2)
+    dh = _bf16(*h_last.shape, device=dev)
+    ops.smallc_conv_fprop([g], _w_tap_major(head.weight.detach().permute(1, 0, 2, 3)), None, dh, ACT_NONE, stride=1,
+                          flip=True)
+    for k in range(K - 2, -1, -1):
+        conv = spec.convs[k]
+        hk = s.hs[k]                                # lrelu output: same sign as the pre-activation
+        ck = hk.shape[3]
+        sums = ops.bn_bwd_reduce(hk, None, dh, ACT_LEAKY, slope=SLOPE) if need_params else None
+        d_pre = _bf16(*hk.shape, device=dev)
+        ops.bn_bwd_apply(hk, None, dh, ACT_LEAKY, None, ACT_NONE, sums, None, d_pre, slope=SLOPE)
+        if k > 0:
+            if need_params:
+                dwc = ops.conv4x4_wgrad(s.hs[k - 1], d_pre, stride=2)
+                grads[2 * k] = dwc.permute(1, 2, 0).reshape(ck, s.hs[k - 1].shape[3], 4, 4)
+                grads[2 * k + 1] = sums[:ck].clone()
+            dh = ops.convT4x4s2_fprop(d_pre, _dgrad_pack(conv.weight), s.hs[k - 1].shape[3])
+        else:
+            if need_params:
+                dw0 = ops.smallc_conv_wgrad(d_pre, [s.px, s.py], stride=2)       # [c, 16, 2]
+                grads[0] = dw0.view(ck, 4, 4, 2).permute(0, 3, 1, 2)
+                grads[1] = sums[:ck].clone()
+            gy = None
+            if need_y:
+                h, w = s.px.shape[1], s.px.shape[2]
+                gxy = ops.convT4x4s2_fprop(d_pre, _dgrad_pack(conv.weight), 2, out_f32=True)   # [N, H, W, 2]
+                gy = gxy[..., 1].reshape(n, 1, h, w)
+    return grads, gy
+
+
+class DiscFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec: DiscSpec, x, y, *params):
+        need_params = any(ctx.needs_input_grad[3:])
+        need_y = ctx.needs_input_grad[2]
+        logits, saved = disc_forward(spec, x, y, save=need_params or need_y)
+        ctx.spec, ctx.saved, ctx.need_params, ctx.need_y = spec, saved, need_params, need_y
+        return logits
+
+    @staticmethod
+    def backward(ctx, g_logits):
+        grads, gy = disc_backward(ctx.spec, ctx.saved, g_logits, ctx.need_params, ctx.need_y)
+        ctx.saved = None
+        need = ctx.needs_input_grad[3:]
+        return (None, None, gy) + tuple(g if nd else None for g, nd in zip(grads, need))

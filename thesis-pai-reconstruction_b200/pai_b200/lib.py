@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpai_b200.so")
 
-c_int, c_float, c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p
+c_int, c_float, c_void_p, c_ll = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_longlong
 
 # name -> argtypes, exactly the declarations of include/pai_b200.h
 SIGNATURES = {
@@ -27,6 +27,20 @@ SIGNATURES = {
                           c_void_p, c_void_p],
     "pai_ssim_psnr_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                           c_void_p, c_void_p],
+    "pai_bn_stats": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p],
+    "pai_bn_finalize": [c_void_p, c_ll, c_int, c_void_p, c_void_p, c_float, c_float, c_int, c_void_p, c_void_p,
+                        c_void_p, c_void_p],
+    "pai_bn_apply_act": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
+                         c_float, c_void_p],
+    "pai_bn_bwd_reduce": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
+                          c_float, c_void_p, c_void_p],
+    "pai_bn_bwd_apply": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
+                         c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "pai_colsum": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p],
+    "pai_smallc_conv_fprop": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                              c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p],
+    "pai_smallc_conv_wgrad": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                              c_int, c_int, c_void_p, c_void_p],
 }
 RESTYPES = {"pai_ssim_bwd_workspace_bytes": (ctypes.c_longlong, [c_int, c_int, c_int])}
 

@@ -130,3 +130,94 @@ def convT4x4s2_wgrad(x, gy, dw=None, splitk=0):
         dw = torch.zeros(16, cin, cout, dtype=torch.float32, device=x.device)
     lib.call("pai_convT4x4s2_wgrad", _ptr(x), n, h, w, cin, ld, _ptr(gy), cout, gld, _ptr(dw), splitk, _stream())
     return dw
+
+
+# ------------------------------------------------------------------------------------------ BatchNorm / activations
+def _mat(t: torch.Tensor):
+    """NHWC (or [m, c]) view -> (m, c, ld)."""
+    if t.dim() == 4:
+        n, h, w, c, ld = _nhwc(t)
+        return n * h * w, c, ld
+    assert t.dim() == 2 and t.stride(1) == 1
+    return t.shape[0], t.shape[1], t.stride(0)
+
+
+def bn_stats(x, sums=None):
+    m, c, ld = _mat(x)
+    if sums is None:
+        sums = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+    lib.call("pai_bn_stats", _ptr(x), m, c, ld, _ptr(sums), _stream())
+    return sums
+
+
+def bn_finalize(sums, m, c, gamma, beta, running_mean, running_var, training=True, eps=1e-5, momentum=0.1, ss=None):
+    if ss is None:
+        ss = torch.empty(4 * c, dtype=torch.float32, device=gamma.device)
+    lib.call("pai_bn_finalize", _ptr(sums), m, c, _ptr(gamma), _ptr(beta), float(eps), float(momentum), int(training),
+             _ptr(running_mean), _ptr(running_var), _ptr(ss), _stream())
+    return ss
+
+
+def bn_apply_act(x, ss, out1, act1, out2=None, act2=ACT_NONE, slope=0.2):
+    m, c, ld = _mat(x)
+    m1, c1, ld1 = _mat(out1)
+    assert (m1, c1) == (m, c)
+    ld2 = 0
+    if out2 is not None:
+        m2, c2, ld2 = _mat(out2)
+        assert (m2, c2) == (m, c)
+    lib.call("pai_bn_apply_act", _ptr(x), m, c, ld, _ptr(ss), _ptr(out1), ld1, act1, _ptr(out2), ld2, act2,
+             float(slope), _stream())
+
+
+def bn_bwd_reduce(x, ss, g1, act1, g2=None, act2=ACT_NONE, slope=0.2):
+    m, c, ld = _mat(x)
+    _, _, ldg1 = _mat(g1)
+    ldg2 = _mat(g2)[2] if g2 is not None else 0
+    sums = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+    lib.call("pai_bn_bwd_reduce", _ptr(x), m, c, ld, _ptr(ss), _ptr(g1), ldg1, act1, _ptr(g2), ldg2, act2,
+             float(slope), _ptr(sums), _stream())
+    return sums
+
+
+def bn_bwd_apply(x, ss, g1, act1, g2, act2, sums, gamma, dx, slope=0.2):
+    m, c, ld = _mat(x)
+    _, _, ldg1 = _mat(g1)
+    ldg2 = _mat(g2)[2] if g2 is not None else 0
+    _, _, lddx = _mat(dx)
+    lib.call("pai_bn_bwd_apply", _ptr(x), m, c, ld, _ptr(ss), _ptr(g1), ldg1, act1, _ptr(g2), ldg2, act2,
+             float(slope), _ptr(sums), _ptr(gamma), _ptr(dx), lddx, _stream())
+    return dx
+
+
+def colsum(x):
+    m, c, ld = _mat(x)
+    sums = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+    lib.call("pai_colsum", _ptr(x), m, c, ld, _ptr(sums), _stream())
+    return sums[:c]
+
+
+# ------------------------------------------------------------------------------------------ degenerate layers
+def smallc_conv_fprop(planes, w, bias, out1, act1=ACT_NONE, out2=None, act2=ACT_NONE, stride=2, flip=False, slope=0.2):
+    """planes: 1 or 2 fp32 ``[n, ih, iw]`` tensors; w: fp32 ``[c, 16, cin]``; out: NHWC bf16 ``[n, oh, ow, c]``."""
+    p0 = planes[0]
+    p1 = planes[1] if len(planes) > 1 else None
+    n, ih, iw = p0.shape
+    on, oh, ow, c, ld1 = _nhwc(out1)
+    assert on == n and w.shape == (c, 16, len(planes)) and w.is_contiguous() and p0.is_contiguous()
+    ld2 = _nhwc(out2)[4] if out2 is not None else 0
+    lib.call("pai_smallc_conv_fprop", _ptr(p0), _ptr(p1), len(planes), n, ih, iw, oh, ow, stride, int(flip), _ptr(w),
+             _ptr(bias), c, _ptr(out1), ld1, act1, _ptr(out2), ld2, act2, float(slope), _stream())
+    return out1
+
+
+def smallc_conv_wgrad(a, planes, stride=2, flip=False):
+    """a: NHWC bf16 ``[n, oh, ow, c]``; planes: fp32 ``[n, ih, iw]`` x (1|2) -> fp32 ``[c, 16, cin]``."""
+    n, oh, ow, c, lda = _nhwc(a)
+    p0 = planes[0]
+    p1 = planes[1] if len(planes) > 1 else None
+    _, ih, iw = p0.shape
+    dw = torch.zeros(c, 16, len(planes), dtype=torch.float32, device=a.device)
+    lib.call("pai_smallc_conv_wgrad", _ptr(a), lda, c, _ptr(p0), _ptr(p1), len(planes), n, ih, iw, oh, ow, stride,
+             int(flip), _ptr(dw), _stream())
+    return dw
