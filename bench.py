@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- Pix2Pix GAN training throughput (images/sec at 256^2) on N B200s of one box.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): Pix2Pix U-Net (54.4 M params) + PatchGAN (2.76 M), one full GAN
+training step of the reference's ``UnetWrapper.training_step`` (models/wrapper.py:117-162: frozen-G forward,
+3 D forwards, 2 D backwards + 1 dgrad-only, G forward/backward, both Adam updates, SSIM/PSNR/RMSE logging) on
+synthetic 1x256x256 grayscale pairs, batch 64 per GPU, bf16 tensor-core compute with fp32 accumulation.
+
+One JSON line is printed by rank 0 (contract in the task statement): ``value`` = device-timed whole-job images/s
+with inputs resident in HBM, ``e2e`` = the same through the public API with pinned-host inputs (H2D every step)
+and a D2H read of the loss, ``roofline`` = the tcgen05 implicit-GEMM kernels' algorithmic TFLOP/s against the
+measured bf16 peak, ``cpu_baseline`` = the oracle's CPU restatement of the reference step on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "thesis-pai-reconstruction_b200"))
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+IMG = 256
+GAN_GFLOP_PER_IMAGE = 73.92          # BASELINE.md section 3 (algorithmic, 2*MAC)
+METRIC = "pix2pix_gan_train_images_per_sec_256x256"
+
+
+# ------------------------------------------------------------------------------------------ helpers
+def synthetic_pairs(n, seed, device="cpu"):
+    """smooth target in [-1, 1] + noisy input, deterministic per seed."""
+    g = torch.Generator().manual_seed(seed)
+    base = F.interpolate(torch.rand(n, 1, 32, 32, generator=g), size=IMG, mode="bilinear")
+    target = 2 * base - 1
+    x = (target + 0.5 * torch.randn(target.shape, generator=g)).clamp(-1, 1)
+    return x.to(device), target.to(device)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        med = sorted(self.samples)[len(self.samples) // 2] if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ------------------------------------------------------------------------------------------ CPU arms
+def cpu_reference_step_rate(steps, warmup, batch):
+    """The reference's training step on the host cores, via the oracle's CPU restatement
+    (oracle/pix2pix_port.py, pinned to the unmodified reference by tests/golden).  Returns images/s."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pix2pix_port as port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = port.init_state(0, in_channels=1, out_channels=1, loss_type="gan", disc_in_channels=1)
+    tr = port.OracleTrainer(sd, "gan")
+    x, target = port.synthetic_pairs(batch, seed=1234)
+    for _ in range(warmup):
+        tr.training_step(x, target)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        tr.training_step(x, target)
+        times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return batch * steps / total, total / steps, cores, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 8            # bounded sample of the 64-image per-GPU batch (config[0]'s CPU-runnable size)
+    steps = max(1, min(args.steps, 12))
+    warmup = max(1, min(args.warmup, 2))
+    rate, sec, cores, threads = cpu_reference_step_rate(steps, warmup, batch)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Pix2Pix U-Net + PatchGAN GAN training step, synthetic 1x256x256, batch 64 per GPU "
+                               "(reference arm: PyTorch CPU fp32, bounded sample of 8 images per step)"},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} GAN training steps of batch {batch} (oracle/pix2pix_port.py == reference "
+                                   f"models/wrapper.py:117-162 on torch CPU fp32, {threads} threads of {cores} cpus)"},
+        "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def build_model():
+    from models.pix2pix import Pix2Pix
+    from models.utils import init_weights
+    from models.wrapper import Discriminator
+    torch.manual_seed(0)
+    m = Pix2Pix(in_channels=1, out_channels=1, dropout=0.0, loss_type="gan")
+    m.discriminator = Discriminator(in_channels=1)          # 1-channel data
+    m.discriminator.apply(init_weights)
+    return m
+
+
+def ssim_sweep_roofline(device, peaks):
+    """BASELINE.json's second metric: the SSIM/PSNR/RMSE (+16 depth bands) metric kernel over the report.py
+    sweep (10 000 synthetic 256^2 fp32 pairs, 5.24 GB >> L2), algorithmic 524 288 B per pair."""
+    from pai_b200 import metrics
+    n = 10000
+    g = torch.Generator(device=device).manual_seed(7)
+    base = torch.rand(n, 1, IMG, IMG, device=device, generator=g)
+    pred = (base + 0.05 * torch.randn(n, 1, IMG, IMG, device=device, generator=g)).clamp_(0, 1)
+    for _ in range(3):
+        metrics._launch_fwd(pred, base, False, True, False)
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        metrics._launch_fwd(pred, base, False, True, False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    gbs = n * 524288 / (ms * 1e-3) / 1e9
+    del base, pred
+    return {"kernel": "ssim_fwd_kernel<float>", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+            "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "pairs": n, "ms_per_sweep": ms, "pairs_per_s": n / (ms * 1e-3),
+            "algorithmic_bytes_per_pair": 524288, "traffic": None}
+
+
+def run_ours(args):
+    from pai_b200 import dp, lib, ops
+    rank, local, world = dp.init_from_env()
+    if world != args.gpus:
+        if rank == 0:
+            print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib.load()
+    peaks, peak_kind = measured_peaks()
+    B = args.batch
+
+    model = build_model().to(dev)
+    dp.broadcast_parameters(model)
+    model.train()
+
+    nbatches = 4
+    host = [synthetic_pairs(B, seed=1234 + 100 * rank + i) for i in range(nbatches)]
+    host = [(x.pin_memory(), t.pin_memory()) for x, t in host]
+    resident = [(x.to(dev), t.to(dev)) for x, t in host]
+
+    def step_resident(i):
+        model.training_step(resident[i % nbatches], i)
+
+    def step_e2e(i):
+        x, t = host[i % nbatches]
+        model.training_step((x.to(dev, non_blocking=True), t.to(dev, non_blocking=True)), i)
+        return float(model.logged["loss"][-1])          # D2H read of the step's result
+
+    for i in range(args.warmup):
+        step_resident(i)
+    torch.cuda.synchronize()
+    model.logged.clear()
+
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(physical_index(local))
+    dp.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = lib.launches
+    ops.profile_start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step_resident(i)
+        model.logged.clear()
+    e1.record()
+    torch.cuda.synchronize()
+    dp.barrier()
+    prof = ops.profile_stop()
+    clocks = sampler.stop()
+    launches = lib.launches - launches0
+    ms_total = dp.allreduce_max(e0.elapsed_time(e1), dev)
+    ms_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- roofline of the implicit-GEMM kernels (per launch: algorithmic FLOP / event-timed duration)
+    kern = {}
+    for name, flops, a, b in prof:
+        k = kern.setdefault(name, [0.0, 0.0, 0])
+        k[0] += flops
+        k[1] += a.elapsed_time(b) * 1e-3
+        k[2] += 1
+    tot_f = sum(v[0] for v in kern.values())
+    tot_t = sum(v[1] for v in kern.values())
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    achieved = tot_f / tot_t / 1e12 if tot_t > 0 else 0.0
+    roofline = {
+        "kernel": "igemm_fprop_kernel + igemm_wgrad_kernel (tcgen05 implicit GEMM: conv/convT fprop, dgrad, wgrad)",
+        "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+        "peak_kind": f"{peak_kind} bf16_tflops_sustained (kernels timed inside a long step)", "traffic": None,
+        "launches_per_step": sum(v[2] for v in kern.values()) / args.steps,
+        "algorithmic_gflop_per_step": tot_f / args.steps / 1e9,
+        "share_of_step": tot_t / (ms_total * 1e-3),
+        "per_entry_point": {k: {"tflops": v[0] / v[1] / 1e12, "ms_per_step": v[1] * 1e3 / args.steps,
+                                "launches_per_step": v[2] / args.steps} for k, v in kern.items()},
+        "step_tflops_algorithmic": world * B * GAN_GFLOP_PER_IMAGE / (ms_step * 1e-3) / 1e3 / world,
+    }
+
+    # ---- timed region 2: end to end through the public API with host buffers
+    for i in range(2):
+        step_e2e(i)
+    dp.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+        model.logged.clear()
+    torch.cuda.synchronize()
+    e2e_s = dp.allreduce_max(time.perf_counter() - t0, dev)
+    e2e_value = world * B * args.steps / e2e_s
+    h2d = 2 * B * IMG * IMG * 4
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "Pix2Pix U-Net + PatchGAN GAN training step (reference UnetWrapper.training_step), "
+                               "synthetic 1x256x256 grayscale pairs, batch 64 per GPU",
+                   "batch_per_gpu": B, "global_batch": B * world, "image": "1x256x256", "loss_type": "gan",
+                   "parallelism": f"dp{world}", "precision": "bf16 operands, fp32 accumulate, fp32 master weights",
+                   "l2_policy": "per-step working set (activations + weights > 2 GB) is larger than the 126 MB L2; "
+                                "4 distinct input batches are cycled"},
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_s * 1e3 / args.steps},
+        "roofline": roofline,
+    }
+
+    if rank == 0:
+        try:
+            line["ssim_roofline"] = ssim_sweep_roofline(dev, peaks)
+        except Exception as ex:  # pragma: no cover
+            line["ssim_roofline"] = {"error": str(ex)}
+        if world == 1 and not args.no_cpu_baseline:
+            rate, sec, cores, threads = cpu_reference_step_rate(steps=3, warmup=1, batch=8)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+                "sample": f"3 GAN training steps of batch 8 (BASELINE.json configs[0]) after 1 warm-up, "
+                          f"{sec:.2f} s/step, torch CPU fp32 with {threads} threads on {cores} cpus"}
+        print(json.dumps(line), flush=True)
+    dp.barrier()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step (BASELINE.json: 64)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from pai_b200 import engine, metrics
+from pai_b200 import dp, engine, metrics
 
 from ._lightning import LightningModule
 from .utils import denormalize, init_weights, psnr, rmse, ssim  # noqa: F401  (re-exported like the reference)
@@ -39,6 +39,13 @@ class UnetWrapper(LightningModule):
 
     def forward(self, x):
         return self.unet(x)
+
+    def manual_backward(self, loss, *args, **kwargs):
+        """Backward, then (data-parallel runs only) average the gradients of the parameters being
+        trained over all ranks with one flat NCCL all-reduce -- the exchange Lightning's DDP strategy
+        would perform for main.py:123-136.  BatchNorm statistics stay per replica."""
+        super().manual_backward(loss, *args, **kwargs)
+        dp.allreduce_gradients(p for p in self.parameters() if p.requires_grad)
 
     # ---- losses ---------------------------------------------------------------------------------
     def loss(self, x, pred, target):

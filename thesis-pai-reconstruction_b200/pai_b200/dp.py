@@ -1,0 +1,79 @@
+"""Batch data parallelism over the GPUs of one box: one process per GPU, replicated parameters and
+optimiser state, per-replica BatchNorm statistics, gradient averaging with NCCL over NVLink/NVSwitch.
+
+The reference has no distributed code of its own; ``pl.Trainer`` (main.py:123-135) would run DDP over the
+visible GPUs without ``sync_batchnorm`` -- this module is that exchange for the manual-optimisation
+``training_step`` (models/wrapper.py:135,159 are the two ``manual_backward`` call sites)."""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+_enabled = False
+
+
+def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
+    """Reads RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* (torchrun) -> (rank, local_rank, world)."""
+    global _enabled
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    _enabled = world > 1
+    return rank, local, world
+
+
+def world_size() -> int:
+    return dist.get_world_size() if (_enabled and dist.is_initialized()) else 1
+
+
+def allreduce_gradients(params) -> int:
+    """In-place average of ``p.grad`` over all ranks; one flat all-reduce per dtype.  Returns the number
+    of elements exchanged (0 when not data-parallel)."""
+    if not (_enabled and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return 0
+    world = dist.get_world_size()
+    total = 0
+    for dtype in {g.dtype for g in grads}:
+        group = [g for g in grads if g.dtype == dtype]
+        flat = torch.cat([g.reshape(-1) for g in group])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(world)
+        off = 0
+        for g in group:
+            n = g.numel()
+            g.copy_(flat[off:off + n].view_as(g))
+            off += n
+        total += flat.numel()
+    return total
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
+    """Makes every replica start from rank ``src``'s parameters and buffers."""
+    if not (_enabled and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src)
+
+
+def barrier() -> None:
+    if _enabled and dist.is_initialized():
+        dist.barrier()
+
+
+def allreduce_max(value: float, device) -> float:
+    if not (_enabled and dist.is_initialized()) or dist.get_world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

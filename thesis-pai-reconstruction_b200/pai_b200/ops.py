@@ -17,6 +17,33 @@ ACT_NONE, ACT_LEAKY, ACT_RELU, ACT_TANH = 0, 1, 2, 3
 _T_K = ((1, 3), (0, 2))
 
 
+# Optional per-launch timing of the implicit-GEMM kernels (bench.py roofline): a list of
+# (name, algorithmic_flops, start_event, end_event) recorded on the launching stream.
+_prof = None
+
+
+def profile_start():
+    global _prof
+    _prof = []
+
+
+def profile_stop():
+    global _prof
+    out, _prof = _prof, None
+    return out or []
+
+
+def _igemm_call(name, flops, *args):
+    if _prof is None:
+        lib.call(name, *args)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lib.call(name, *args)
+    e1.record()
+    _prof.append((name, flops, e0, e1))
+
+
 def _ptr(t):
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
@@ -91,7 +118,7 @@ def conv4x4_fprop(x, w_packed, cout, stride=2, bias=None, act=ACT_NONE, slope=0.
         out = torch.empty(n, ho, wo, cout, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
     on, oh, ow, oc, old = _nhwc(out)
     assert (on, oh, ow, oc) == (n, ho, wo, cout)
-    lib.call("pai_conv4x4_fprop", _ptr(x), n, h, w, cin, ld, _ptr(w_packed), cout, cp, stride, _ptr(bias), act,
+    _igemm_call("pai_conv4x4_fprop", 2.0 * n * ho * wo * cout * 16 * cin, _ptr(x), n, h, w, cin, ld, _ptr(w_packed), cout, cp, stride, _ptr(bias), act,
              float(slope), _ptr(out), old, int(out.dtype == torch.float32), n_tile, _stream())
     return out
 
@@ -104,7 +131,7 @@ def convT4x4s2_fprop(x, w_packed, cout, bias=None, act=ACT_NONE, slope=0.2, out=
         out = torch.empty(n, 2 * h, 2 * w, cout, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
     on, oh, ow, oc, old = _nhwc(out)
     assert (on, oh, ow, oc) == (n, 2 * h, 2 * w, cout)
-    lib.call("pai_convT4x4s2_fprop", _ptr(x), n, h, w, cin, ld, _ptr(w_packed), cout, cp, _ptr(bias), act,
+    _igemm_call("pai_convT4x4s2_fprop", 2.0 * n * h * w * cout * 16 * cin, _ptr(x), n, h, w, cin, ld, _ptr(w_packed), cout, cp, _ptr(bias), act,
              float(slope), _ptr(out), old, int(out.dtype == torch.float32), n_tile, _stream())
     return out
 
@@ -117,7 +144,7 @@ def conv4x4_wgrad(x, gy, stride=2, dw=None, splitk=0):
     gn, gh, gw, cout, gld = _nhwc(gy)
     if dw is None:
         dw = torch.zeros(16, cout, cin, dtype=torch.float32, device=x.device)
-    lib.call("pai_conv4x4_wgrad", _ptr(x), n, h, w, cin, ld, _ptr(gy), cout, gld, stride, _ptr(dw), splitk,
+    _igemm_call("pai_conv4x4_wgrad", 2.0 * gn * gh * gw * cout * 16 * cin, _ptr(x), n, h, w, cin, ld, _ptr(gy), cout, gld, stride, _ptr(dw), splitk,
              _stream())
     return dw
 
@@ -128,7 +155,7 @@ def convT4x4s2_wgrad(x, gy, dw=None, splitk=0):
     gn, gh, gw, cout, gld = _nhwc(gy)
     if dw is None:
         dw = torch.zeros(16, cin, cout, dtype=torch.float32, device=x.device)
-    lib.call("pai_convT4x4s2_wgrad", _ptr(x), n, h, w, cin, ld, _ptr(gy), cout, gld, _ptr(dw), splitk, _stream())
+    _igemm_call("pai_convT4x4s2_wgrad", 2.0 * n * h * w * cout * 16 * cin, _ptr(x), n, h, w, cin, ld, _ptr(gy), cout, gld, _ptr(dw), splitk, _stream())
     return dw
 
 
