@@ -255,6 +255,12 @@ def run_ours(args):
         k[0] += flops
         k[1] += a.elapsed_time(b) * 1e-3
         k[2] += 1
+    if os.environ.get("PAI_BENCH_DUMP") and rank == 0:
+        per_step = len(prof) // args.steps
+        with open(os.environ["PAI_BENCH_DUMP"], "w") as f:
+            for name, flops, a, b in prof[-per_step:]:
+                ms = a.elapsed_time(b)
+                f.write(f"{name:24s} {flops / 1e9:10.2f} GFLOP {ms * 1e3:9.1f} us {flops / ms / 1e9 if ms > 0 else 0:8.1f} TFLOP/s\n")
     tot_f = sum(v[0] for v in kern.values())
     tot_t = sum(v[1] for v in kern.values())
     peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])

@@ -64,8 +64,7 @@ int pai_convT4x4s2_fprop(const void* x, int n, int h, int w, int cin, int x_ld, 
 /* Weight gradients (autograd of the two modules above).
  * pai_conv4x4_wgrad:   dw[ky*4+kx][co][ci] += sum_{n,oh,ow} gy[n,oh,ow,co] * x[n,stride*oh-1+ky,stride*ow-1+kx,ci]
  * pai_convT4x4s2_wgrad: dw[ky*4+kx][ci][co] += sum_{n,a,b} x[n,a,b,ci] * gy[n,2a-1+ky,2b-1+kx,co]
- *   dw is fp32 and is ACCUMULATED into (zero it first); channel counts: the first (row) one % 128 == 0,
- *   the second % 64 == 0.  x: [n,h,w,cin]; gy: the module's output gradient.
+ *   dw is fp32 and is ACCUMULATED into (zero it first); channel counts: both % 64 == 0.  x: [n,h,w,cin]; gy: the module's output gradient.
  */
 int pai_conv4x4_wgrad(const void* x, int n, int h, int w, int cin, int x_ld, const void* gy, int cout, int gy_ld,
                       int stride, float* dw, int splitk, void* stream);
@@ -138,6 +137,26 @@ int pai_smallc_conv_fprop(const float* plane0, const float* plane1, int cin, int
                           int act1, void* out2, int ld2, int act2, float slope, void* stream);
 int pai_smallc_conv_wgrad(const void* a, int lda, int c, const float* plane0, const float* plane1, int cin, int n,
                           int ih, int iw, int oh, int ow, int stride, int flip, float* dw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Degenerate layers as tensor-core GEMMs.  A convolution whose input (enc0, D0) or output (dec7, D0's
+ * data gradient) is 1-2 channels wide becomes  im2col / col2im of the thin side  +  a pointwise GEMM:
+ *   pai_im2col4x4      col[n,oy,ox, t*cin+j] = plane_j[n, s*oy+dy_t, s*ox+dx_t] (bf16, 64 channels, zero padded)
+ *   pai_pointwise_gemm y[r, co] = act(bias[co] + sum_ci x[r, ci] * w_packed[co][ci])  (1x1 conv over m rows;
+ *                      optional second bf16 output y2 with its own activation; m % 128 == 0)
+ *   pai_pointwise_wgrad dw[cu][cs] += sum_r u[r, cu] * s[r, cs]                         (m % 64 == 0)
+ *   pai_col2im4x4s2    out[n,2a+py,2b+px] = act(bias + sum of the 4 (tap, neighbour) partial products of
+ *                      p[n,h,w,16])  -- the transposed 4x4 stride-2 conv with one output channel.
+ */
+int pai_im2col4x4(const float* plane0, const float* plane1, int cin, int n, int ih, int iw, int oh, int ow, int stride,
+                  int flip, void* col, void* stream);
+int pai_pointwise_gemm(const void* x, long long m, int cin, int x_ld, const void* w_packed, int cout, int cout_pad,
+                       const float* bias, int act, float slope, void* y, int y_ld, int y_f32, void* y2, int y2_ld,
+                       int act2, int n_tile, void* stream);
+int pai_pointwise_wgrad(const void* u, long long m, int cu, int u_ld, const void* s, int cs, int s_ld, float* dw,
+                        int splitk, void* stream);
+int pai_col2im4x4s2(const float* p, int ldp, int n, int h, int w, const float* bias, int act, float* out,
+                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -52,7 +52,10 @@ def test_batchnorm_forward_backward(n, h, w, c):
     dx = torch.empty_like(x)
     ops.bn_bwd_apply(x, ss, g1, ops.ACT_LEAKY, g2, ops.ACT_RELU, s2, gamma, dx, slope=0.2)
     ref = xr.grad.permute(0, 2, 3, 1)
-    assert (dx.float() - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item())
+    err = (dx.float() - ref).abs()
+    tol = 2e-2 * max(1.0, ref.abs().max().item())
+    # an activation input within one ulp of 0 may land on the other side of the kink: allow isolated outliers
+    assert (err > tol).float().mean().item() < 1e-5 and err.mean().item() < 2e-3 * max(1.0, ref.abs().max().item())
     assert torch.allclose(s2[:c], br.grad, rtol=2e-2, atol=2e-2 * br.grad.abs().max().item())
     assert torch.allclose(s2[c:], gr.grad, rtol=2e-2, atol=2e-2 * gr.grad.abs().max().item())
     # eval mode uses the running statistics
@@ -132,3 +135,55 @@ def test_smallc_as_stride1_cout1_gradients():
     assert (dx.float() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
     dw = ops.smallc_conv_wgrad(x, [g], stride=1, flip=True)
     assert (dw.view(cin, 4, 4, 1).permute(3, 0, 1, 2) - wt.grad).abs().max().item() < 2e-3 * max(1.0, wt.grad.abs().max().item())
+
+
+def test_thin_conv_as_im2col_plus_pointwise_gemm():
+    """enc0 / D0: Conv2d(1|2 -> 64, 4, 2, 1) == im2col4x4 + pointwise GEMM (two fused outputs), and its wgrad."""
+    ops = _ops()
+    n, h, w, c = 2, 64, 64, 64
+    for cin in (1, 2):
+        planes = [torch.randn(n, h, w, device="cuda") for _ in range(cin)]
+        wt = torch.randn(c, cin, 4, 4, device="cuda") * 0.1
+        bias = torch.randn(c, device="cuda")
+        col = ops.im2col4x4(planes, h // 2, w // 2, stride=2)
+        wp = torch.zeros(c, 64, dtype=torch.bfloat16, device="cuda")
+        wp[:, :16 * cin] = wt.permute(0, 2, 3, 1).reshape(c, -1)
+        o2 = torch.zeros(n, h // 2, w // 2, 2 * c, dtype=torch.bfloat16, device="cuda")
+        o1 = ops.pointwise_gemm(col, wp, c, bias=bias, act=ops.ACT_LEAKY, out2=o2[..., c:], act2=ops.ACT_NONE)
+        xin = torch.stack(planes, 1).bfloat16().float()
+        ref = F.conv2d(xin, wt.bfloat16().float(), bias, stride=2, padding=1)
+        tol = 1e-2 * max(1.0, ref.abs().max().item())
+        assert (o1.float().permute(0, 3, 1, 2) - F.leaky_relu(ref, 0.2)).abs().max().item() < tol
+        assert (o2[..., c:].float().permute(0, 3, 1, 2) - ref).abs().max().item() < tol
+        assert o2[..., :c].abs().max().item() == 0
+        gy = _rand((n, h // 2, w // 2, c), 21)
+        dw = ops.pointwise_wgrad(gy, col)
+        wr = wt.clone().requires_grad_(True)
+        F.conv2d(xin, wr, None, stride=2, padding=1).backward(gy.float().permute(0, 3, 1, 2))
+        got = dw[:, :16 * cin].reshape(c, 4, 4, cin).permute(0, 3, 1, 2)
+        assert (got - wr.grad).abs().max().item() < 3e-3 * max(1.0, wr.grad.abs().max().item())
+
+
+def test_thin_convT_as_pointwise_gemm_plus_col2im():
+    """dec7: ConvTranspose2d(128 -> 1, 4, 2, 1) + Tanh forward, data gradient and weight gradient."""
+    ops = _ops()
+    n, h, w, cin = 2, 32, 32, 128
+    x = _rand((n, h, w, cin), 22)
+    wt = (torch.randn(cin, 1, 4, 4, device="cuda") * 0.05)
+    bias = torch.randn(1, device="cuda") * 0.1
+    wq = wt.bfloat16().float().requires_grad_(True)
+    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    ref = torch.tanh(F.conv_transpose2d(xr, wq, bias, stride=2, padding=1))
+    part = ops.pointwise_gemm(x, wt[:, 0].reshape(cin, 16).t().contiguous().bfloat16(), 16, out_f32=True)
+    y = ops.col2im4x4s2(part, bias, ops.ACT_TANH)
+    assert (y - ref[:, 0]).abs().max().item() < 2e-3
+    g = torch.randn(n, 2 * h, 2 * w, device="cuda")
+    F.conv_transpose2d(xr, wq, None, stride=2, padding=1).backward(g.view(n, 1, 2 * h, 2 * w))
+    gcol = ops.im2col4x4([g], h, w, stride=2)
+    wd = torch.zeros(cin, 64, dtype=torch.bfloat16, device="cuda")
+    wd[:, :16] = wt[:, 0].reshape(cin, 16)
+    dx = ops.pointwise_gemm(gcol, wd, cin)
+    refdx = xr.grad.permute(0, 2, 3, 1)
+    assert (dx.float() - refdx).abs().max().item() < 2e-2 * max(1.0, refdx.abs().max().item())
+    dw = ops.pointwise_wgrad(x, gcol)[:, :16].reshape(cin, 1, 4, 4)
+    assert (dw - wq.grad).abs().max().item() < 1e-2 * max(1.0, wq.grad.abs().max().item())

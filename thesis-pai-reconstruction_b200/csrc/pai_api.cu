@@ -105,6 +105,21 @@ static const int kTd[2][2] = {{0, -1}, {1, 0}};
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// Output-channel tile: the widest of 256/128/64/32/16 that divides cout_pad while still giving every
+// SM a tile (wider tiles re-read the activations less often from L2).
+static int auto_n_tile(int cout_pad, long long m_tiles_x_phases) {
+    static const int cand[5] = {256, 128, 64, 32, 16};
+    int best = 0;
+    for (int i = 0; i < 5; ++i) {
+        if (cout_pad % cand[i]) continue;
+        if (best == 0) best = cand[i];
+        if (m_tiles_x_phases * (cout_pad / cand[i]) >= 148) return cand[i];
+        best = cand[i] >= 128 ? cand[i] : best;      // small problems: do not go below 128 just to add CTAs
+        if (cand[i] <= 128) break;
+    }
+    return best;
+}
+
 }  // namespace pai
 
 using namespace pai;
@@ -120,8 +135,7 @@ int pai_conv4x4_fprop(const void* x, int n, int h, int w, int cin, int x_ld, con
     PAI_REQUIRE(x && w_packed && y, "pai_conv4x4_fprop: null pointer");
     PAI_REQUIRE(stride == 1 || stride == 2, "pai_conv4x4_fprop: stride must be 1 or 2 (got %d)", stride);
     PAI_REQUIRE(cin > 0 && cin % 64 == 0, "pai_conv4x4_fprop: cin must be a multiple of 64 (got %d)", cin);
-    PAI_REQUIRE(n_tile >= 16 && n_tile <= 256 && n_tile % 16 == 0 && cout_pad % n_tile == 0 && cout <= cout_pad,
-                "pai_conv4x4_fprop: bad n_tile %d / cout %d / cout_pad %d", n_tile, cout, cout_pad);
+    PAI_REQUIRE(cout_pad % 16 == 0 && cout <= cout_pad, "pai_conv4x4_fprop: bad cout %d / cout_pad %d", cout, cout_pad);
     PAI_REQUIRE(aligned16(x) && aligned16(w_packed) && x_ld % 8 == 0, "pai_conv4x4_fprop: x / w must be 16 B aligned");
     int ho, wo;
     if (stride == 2) {
@@ -134,6 +148,9 @@ int pai_conv4x4_fprop(const void* x, int n, int h, int w, int cin, int x_ld, con
         wo = w - 1;
     }
     PixBox b = pick_box(wo, ho, n, 128);
+    if (n_tile <= 0) n_tile = auto_n_tile(cout_pad, (long long)b.tiles_w * b.tiles_h * b.tiles_n);
+    PAI_REQUIRE(n_tile >= 16 && n_tile <= 256 && n_tile % 16 == 0 && cout_pad % n_tile == 0,
+                "pai_conv4x4_fprop: bad n_tile %d for cout_pad %d", n_tile, cout_pad);
     CUtensorMap tm_a, tm_b;
     int rc = stride == 2 ? map_split(&tm_a, x, n, h, w, cin, b) : map_unit(&tm_a, x, n, h, w, cin, x_ld, b);
     if (rc) return rc;
@@ -172,11 +189,13 @@ int pai_convT4x4s2_fprop(const void* x, int n, int h, int w, int cin, int x_ld, 
                          int n_tile, void* stream) {
     PAI_REQUIRE(x && w_packed && y, "pai_convT4x4s2_fprop: null pointer");
     PAI_REQUIRE(cin > 0 && cin % 64 == 0, "pai_convT4x4s2_fprop: cin must be a multiple of 64 (got %d)", cin);
-    PAI_REQUIRE(n_tile >= 16 && n_tile <= 256 && n_tile % 16 == 0 && cout_pad % n_tile == 0 && cout <= cout_pad,
-                "pai_convT4x4s2_fprop: bad n_tile %d / cout %d / cout_pad %d", n_tile, cout, cout_pad);
+    PAI_REQUIRE(cout_pad % 16 == 0 && cout <= cout_pad, "pai_convT4x4s2_fprop: bad cout %d / cout_pad %d", cout, cout_pad);
     PAI_REQUIRE(aligned16(x) && aligned16(w_packed) && x_ld % 8 == 0 && x_ld >= cin,
                 "pai_convT4x4s2_fprop: x / w must be 16 B aligned");
     PixBox b = pick_box(w, h, n, 128);
+    if (n_tile <= 0) n_tile = auto_n_tile(cout_pad, 4LL * b.tiles_w * b.tiles_h * b.tiles_n);
+    PAI_REQUIRE(n_tile >= 16 && n_tile <= 256 && n_tile % 16 == 0 && cout_pad % n_tile == 0,
+                "pai_convT4x4s2_fprop: bad n_tile %d for cout_pad %d", n_tile, cout_pad);
     CUtensorMap tm_a, tm_b;
     int rc = map_unit(&tm_a, x, n, h, w, cin, x_ld, b);
     if (rc) return rc;
@@ -208,11 +227,12 @@ int pai_convT4x4s2_fprop(const void* x, int n, int h, int w, int cin, int x_ld, 
                               (cudaStream_t)stream);
 }
 
+// stride: 2 = parity-split taps, 1 = unit-stride 4x4 taps, 0 = pointwise (a single tap at offset 0)
 static int wgrad_common(const void* u, int un, int uh, int uw, int cu, int u_ld, const void* s, int sh, int sw,
                         int cs, int s_ld, int stride, float* dw, int splitk, cudaStream_t stream, const char* who) {
     PAI_REQUIRE(u && s && dw, "%s: null pointer", who);
-    PAI_REQUIRE(cu % 128 == 0 && cs % 64 == 0, "%s: channel counts (%d rows, %d cols) must be multiples of 128 / 64",
-                who, cu, cs);
+    PAI_REQUIRE(cu % 64 == 0 && cs % 64 == 0, "%s: channel counts (%d rows, %d cols) must be multiples of 64", who, cu,
+                cs);
     PAI_REQUIRE(aligned16(u) && aligned16(s) && u_ld % 8 == 0 && s_ld % 8 == 0, "%s: operands must be 16 B aligned",
                 who);
     PixBox b = pick_box(uw, uh, un, 64);
@@ -240,19 +260,20 @@ static int wgrad_common(const void* u, int un, int uh, int uw, int cu, int u_ld,
                 s2_tap(kx, &qx, &px);
                 s2_tap(ky, &qy, &py);
                 p.tap_c[t] = px * cs, p.tap_w[t] = qx, p.tap_p[t] = py, p.tap_h[t] = qy;
-            } else {
+            } else if (stride == 1) {
                 p.tap_c[t] = 0, p.tap_w[t] = kx - 1, p.tap_p[t] = 0, p.tap_h[t] = ky - 1;
-            }
+            }   // stride 0: the single tap stays at offset 0
         }
+    const int ntaps = stride == 0 ? 1 : 16;
     const int total_tiles = b.tiles_w * b.tiles_h * b.tiles_n;
     if (splitk <= 0) {
-        const int base = (cu / 128) * (cs / p.n_tile) * 16;
+        const int base = ((cu + 127) / 128) * (cs / p.n_tile) * ntaps;
         splitk = (2 * 148 + base - 1) / base;
         if (splitk > total_tiles / 4) splitk = total_tiles / 4;
         if (splitk < 1) splitk = 1;
     }
     if (splitk > total_tiles) splitk = total_tiles;
-    return launch_igemm_wgrad(tm_u, tm_s, p, 16, splitk, stream);
+    return launch_igemm_wgrad(tm_u, tm_s, p, ntaps, splitk, stream);
 }
 
 int pai_conv4x4_wgrad(const void* x, int n, int h, int w, int cin, int x_ld, const void* gy, int cout, int gy_ld,
@@ -261,6 +282,50 @@ int pai_conv4x4_wgrad(const void* x, int n, int h, int w, int cin, int x_ld, con
     const int ho = stride == 2 ? h / 2 : h - 1, wo = stride == 2 ? w / 2 : w - 1;
     return wgrad_common(gy, n, ho, wo, cout, gy_ld, x, h, w, cin, x_ld, stride, dw, splitk, (cudaStream_t)stream,
                         "pai_conv4x4_wgrad");
+}
+
+int pai_pointwise_wgrad(const void* u, long long m, int cu, int u_ld, const void* s, int cs, int s_ld, float* dw,
+                        int splitk, void* stream) {
+    PAI_REQUIRE(m > 0 && m < (1LL << 31), "pai_pointwise_wgrad: bad row count");
+    // rows are independent: view them as an [n, 1, w] grid with w = 64-pixel boxes
+    const int w = 64;
+    PAI_REQUIRE(m % w == 0, "pai_pointwise_wgrad: row count must be a multiple of 64 (got %lld)", m);
+    return wgrad_common(u, (int)(m / w), 1, w, cu, u_ld, s, 1, w, cs, s_ld, 0, dw, splitk, (cudaStream_t)stream,
+                        "pai_pointwise_wgrad");
+}
+
+int pai_pointwise_gemm(const void* x, long long m, int cin, int x_ld, const void* w_packed, int cout, int cout_pad,
+                       const float* bias, int act, float slope, void* y, int y_ld, int y_f32, void* y2, int y2_ld,
+                       int act2, int n_tile, void* stream) {
+    PAI_REQUIRE(x && w_packed && y, "pai_pointwise_gemm: null pointer");
+    PAI_REQUIRE(cin > 0 && cin % 64 == 0, "pai_pointwise_gemm: cin must be a multiple of 64 (got %d)", cin);
+    PAI_REQUIRE(cout_pad % 16 == 0 && cout <= cout_pad, "pai_pointwise_gemm: bad cout %d / cout_pad %d", cout, cout_pad);
+    PAI_REQUIRE(aligned16(x) && aligned16(w_packed) && x_ld % 8 == 0 && x_ld >= cin, "pai_pointwise_gemm: alignment");
+    PAI_REQUIRE(m > 0 && m % 128 == 0 && m / 128 < (1LL << 31), "pai_pointwise_gemm: rows must be a multiple of 128 (got %lld)", m);
+    const int wbox = 128, n = (int)(m / wbox);
+    PixBox b = pick_box(wbox, 1, n, 128);
+    if (n_tile <= 0) n_tile = auto_n_tile(cout_pad, (long long)b.tiles_w * b.tiles_h * b.tiles_n);
+    PAI_REQUIRE(n_tile >= 16 && n_tile <= 256 && n_tile % 16 == 0 && cout_pad % n_tile == 0,
+                "pai_pointwise_gemm: bad n_tile %d for cout_pad %d", n_tile, cout_pad);
+    CUtensorMap tm_a, tm_b;
+    int rc = map_unit(&tm_a, x, n, 1, wbox, cin, x_ld, b);
+    if (rc) return rc;
+    uint64_t bd[2] = {(uint64_t)cin, (uint64_t)cout_pad};
+    uint64_t bs[1] = {(uint64_t)cin * 2};
+    uint32_t bb[2] = {64, (uint32_t)n_tile};
+    rc = encode_tmap_bf16(&tm_b, w_packed, 2, bd, bs, bb);
+    if (rc) return rc;
+    IgemmFpropParams p;
+    memset(&p, 0, sizeof(p));
+    p.bw = b.bw, p.bh = b.bh, p.bn = b.bn, p.tiles_w = b.tiles_w, p.tiles_h = b.tiles_h;
+    p.gw = wbox, p.gh = 1, p.gn = n;
+    p.n_tile = n_tile, p.cout = cout, p.kc_per_tap = cin / 64, p.ntaps = 1;
+    p.b_rows_per_phase = cout_pad;
+    p.out_sn = (long long)wbox * y_ld, p.out_sh = 0, p.out_sw = y_ld;
+    p.out2_sn = (long long)wbox * y2_ld, p.out2_sh = 0, p.out2_sw = y2_ld;
+    p.bias = bias, p.act = act, p.slope = slope, p.out_f32 = y_f32, p.out = y, p.out2 = y2, p.act2 = act2;
+    return launch_igemm_fprop(tm_a, tm_b, p, b.tiles_w * b.tiles_h * b.tiles_n, cout_pad / n_tile, 1,
+                              (cudaStream_t)stream);
 }
 
 int pai_convT4x4s2_wgrad(const void* x, int n, int h, int w, int cin, int x_ld, const void* gy, int cout, int gy_ld,

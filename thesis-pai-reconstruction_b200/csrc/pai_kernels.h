@@ -16,6 +16,7 @@ struct IgemmFpropParams {
     int cout;                  // valid output channels
     int kc_per_tap, ntaps;     // 64-channel K blocks per tap, taps per phase
     int stages;
+    int m_tiles, n_tiles, phases;  // tile grid walked by the persistent CTAs
     int tap_c[16], tap_w[16], tap_p[16], tap_h[16];  // per (phase * ntaps + tap): A-box coordinate offsets
     int b_rows_per_phase;      // rows of the packed weight matrix per phase (cout_pad)
     long long out_sn, out_sh, out_sw;  // output element strides per pixel-grid step
@@ -25,6 +26,10 @@ struct IgemmFpropParams {
     float slope;
     int out_f32;
     void* out;
+    // optional second bf16 output with its own activation and pixel strides (same grid mapping)
+    void* out2;
+    int act2;
+    long long out2_sn, out2_sh, out2_sw;
 };
 
 struct IgemmWgradParams {

@@ -25,19 +25,18 @@ BN_EPS, BN_MOMENTUM, SLOPE = 1e-5, 0.1, 0.2
 
 # ------------------------------------------------------------------------------------------ pack cache
 class _PackCache:
-    """bf16 GEMM operand packs of fp32 master weights, keyed by (tag, parameter identity, version)."""
-
-    def __init__(self):
-        self._c = {}
+    """bf16 GEMM operand packs of fp32 master weights.  The packs live ON the parameter object (so they die
+    with it -- ``id()`` of a freed tensor can be reused) and are rebuilt when its version counter or storage
+    changes (optimizer step, ``load_state_dict``, ``.cuda()``)."""
 
     def get(self, tag: str, p: torch.Tensor, fn):
-        key = (tag, id(p))
+        store = p.__dict__.setdefault("_pai_packs", {})
         stamp = (p._version, p.data_ptr())
-        ent = self._c.get(key)
+        ent = store.get(tag)
         if ent is None or ent[0] != stamp:
             with torch.no_grad():
                 ent = (stamp, fn(p.detach()))
-            self._c[key] = ent
+            store[tag] = ent
         return ent[1]
 
 
@@ -65,6 +64,28 @@ def _w_tap_major(w):     # [C, cin, 4, 4] -> fp32 [C, 16, cin] for the direct ke
     if cin == 1:
         return w.detach().reshape(c, 16, 1)
     return _packs.get("small", w, lambda t: t.permute(0, 2, 3, 1).reshape(c, 16, cin).contiguous())
+
+
+def _pad_cols(t, cols=64):
+    out = torch.zeros(t.shape[0], cols, dtype=torch.bfloat16, device=t.device)
+    out[:, :t.shape[1]] = t
+    return out
+
+
+def _thin_in_pack(w):    # Conv2d weight [C, cin<=2, 4, 4] -> bf16 [C, 64]: column = tap*cin + j (im2col order)
+    return _packs.get("thin_in", w, lambda t: _pad_cols(t.permute(0, 2, 3, 1).reshape(t.shape[0], -1)))
+
+
+def _thin_out_fprop_pack(w):   # ConvT weight [Cin, 1, 4, 4] -> bf16 [16, Cin]: row = tap (per-tap partial products)
+    return _packs.get("thin_out_f", w, lambda t: t[:, 0].reshape(t.shape[0], 16).t().contiguous().bfloat16())
+
+
+def _thin_out_dgrad_pack(w):   # ConvT weight [Cin, 1, 4, 4] -> bf16 [Cin, 64]: column = tap
+    return _packs.get("thin_out_d", w, lambda t: _pad_cols(t[:, 0].reshape(t.shape[0], 16)))
+
+
+def _thin_in_dgrad_pack(w, j):  # Conv2d weight [C, cin, 4, 4] -> bf16 [16, C]: row = tap, for input channel j
+    return _packs.get(f"thin_in_d{j}", w, lambda t: t[:, j].reshape(t.shape[0], 16).t().contiguous().bfloat16())
 
 
 def _bf16(*shape, device):
@@ -151,8 +172,10 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
     conv0 = spec.enc_convs[0]
     # The last decoder is a bare ConvTranspose2d (models/pix2pix.py:185-193): no ReLU in front of it, so
     # its concat buffer cat[L-1] holds UN-activated values; every other decoder starts with a ReLU.
-    ops.smallc_conv_fprop([plane], _w_tap_major(conv0.weight), conv0.bias.detach(), a_in[1], ACT_LEAKY,
-                          cat[L - 1][..., c0:], ACT_NONE, stride=2, slope=SLOPE)
+    # enc0 (1 input channel) = im2col of the plane + one tensor-core GEMM with two fused outputs
+    xcol = ops.im2col4x4([plane], hs[0], ws[0], stride=2)
+    ops.pointwise_gemm(xcol, _thin_in_pack(conv0.weight), c0, bias=conv0.bias.detach(), act=ACT_LEAKY, slope=SLOPE,
+                       out=a_in[1], out2=cat[L - 1][..., c0:], act2=ACT_NONE)
     # ---- encoders 1..L-1
     for i in range(1, L):
         conv, bn = spec.enc_convs[i], spec.enc_bns[i]
@@ -181,10 +204,13 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
         raw_d[j], ss_d[j] = raw, ss
         d_in = cat[j + 1]
     last = spec.dec_convs[L - 1]
-    y = ops.convT4x4s2_fprop(d_in, _fpropT_pack(last.weight), 1, bias=last.bias.detach(), act=ACT_TANH, out_f32=True)
-    y = y.view(n, 1, h, w)                      # NHWC with C == 1 is NCHW
+    # last decoder (1 output channel): 16 per-tap partial products per input pixel (GEMM, the wide input is
+    # read once) + col2im with bias and Tanh
+    part = ops.pointwise_gemm(d_in, _thin_out_fprop_pack(last.weight), 16, out_f32=True)
+    y = ops.col2im4x4s2(part, last.bias.detach(), ACT_TANH).view(n, 1, h, w)
     if not save:
         return y, None
+    s.xcol = xcol
     s.plane, s.cat, s.a_in, s.raw_e, s.ss_e, s.raw_d, s.ss_d, s.dec_in0, s.y = plane, cat, a_in, raw_e, ss_e, raw_d, ss_d, dec_in0, y
     return y, s
 
@@ -201,10 +227,10 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
     # ---- last decoder: ConvT(2*c0 -> 1)
     last = spec.dec_convs[L - 1]
     cin_last = last.weight.shape[0]
-    dw = ops.smallc_conv_wgrad(s.cat[L - 1], [g_pre], stride=2)                 # [cin, 16, 1]
-    grads[(1, L - 1)] = (dw.view(cin_last, 1, 4, 4), g_pre.sum().reshape(1))
-    dcat = _bf16(*s.cat[L - 1].shape, device=dev)
-    ops.smallc_conv_fprop([g_pre], _w_tap_major(last.weight), None, dcat, ACT_NONE, stride=2)
+    gcol = ops.im2col4x4([g_pre], h // 2, w // 2, stride=2)                      # [N, h/2, w/2, 64], 16 taps of g
+    dw = ops.pointwise_wgrad(s.cat[L - 1], gcol)                                 # [cin, 64]
+    grads[(1, L - 1)] = (dw[:, :16].reshape(cin_last, 1, 4, 4), g_pre.sum().reshape(1))
+    dcat = ops.pointwise_gemm(gcol, _thin_out_dgrad_pack(last.weight), cin_last)
     # ---- decoders L-2 .. 0
     dskip = [None] * L                          # dskip[i]: grad w.r.t. relu(skip_i) (second half of dcat)
     for j in range(L - 2, -1, -1):
@@ -253,8 +279,8 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
     sums = ops.bn_bwd_reduce(s.a_in[1], None, d_a, ACT_LEAKY, dskip[0], ACT_NONE, slope=SLOPE)
     d_raw = _bf16(*s.a_in[1].shape, device=dev)
     ops.bn_bwd_apply(s.a_in[1], None, d_a, ACT_LEAKY, dskip[0], ACT_NONE, sums, None, d_raw, slope=SLOPE)
-    dw0 = ops.smallc_conv_wgrad(d_raw, [s.plane], stride=2)                      # [c0, 16, 1]
-    grads[(0, 0)] = (dw0.view(c0, 1, 4, 4), sums[:c0].clone())
+    dw0 = ops.pointwise_wgrad(d_raw, s.xcol)                                     # [c0, 64]
+    grads[(0, 0)] = (dw0[:, :16].reshape(c0, 1, 4, 4), sums[:c0].clone())
     out = []
     for i in range(L):
         out += list(grads[(0, i)])
@@ -307,8 +333,9 @@ def disc_forward(spec: DiscSpec, x: torch.Tensor, y: torch.Tensor, save: bool):
     px = x.contiguous().float().view(n, h, w)
     py = y.contiguous().float().view(n, h, w)
     c0 = spec.convs[0]
-    hcur = _bf16(n, h // 2, w // 2, spec.ch[0], device=dev)
-    ops.smallc_conv_fprop([px, py], _w_tap_major(c0.weight), c0.bias.detach(), hcur, ACT_LEAKY, stride=2, slope=SLOPE)
+    xycol = ops.im2col4x4([px, py], h // 2, w // 2, stride=2)                    # cat([x, y]) never materialised
+    hcur = ops.pointwise_gemm(xycol, _thin_in_pack(c0.weight), spec.ch[0], bias=c0.bias.detach(), act=ACT_LEAKY,
+                              slope=SLOPE)
     hs = [hcur]
     for k in range(1, len(spec.convs) - 1):
         c = spec.convs[k]
@@ -322,7 +349,7 @@ def disc_forward(spec: DiscSpec, x: torch.Tensor, y: torch.Tensor, save: bool):
     if not save:
         return logits, None
     s = _Saved()
-    s.px, s.py, s.hs = px, py, hs
+    s.px, s.py, s.hs, s.xycol = px, py, hs, xycol
     return logits, s
 
 
@@ -356,14 +383,14 @@ def disc_backward(spec: DiscSpec, s: _Saved, g_logits: torch.Tensor, need_params
             dh = ops.convT4x4s2_fprop(d_pre, _dgrad_pack(conv.weight), s.hs[k - 1].shape[3])
         else:
             if need_params:
-                dw0 = ops.smallc_conv_wgrad(d_pre, [s.px, s.py], stride=2)       # [c, 16, 2]
-                grads[0] = dw0.view(ck, 4, 4, 2).permute(0, 3, 1, 2)
+                dw0 = ops.pointwise_wgrad(d_pre, s.xycol)                        # [c, 64], column = tap*2 + j
+                grads[0] = dw0[:, :32].reshape(ck, 4, 4, 2).permute(0, 3, 1, 2)
                 grads[1] = sums[:ck].clone()
             gy = None
             if need_y:
                 h, w = s.px.shape[1], s.px.shape[2]
-                gxy = ops.convT4x4s2_fprop(d_pre, _dgrad_pack(conv.weight), 2, out_f32=True)   # [N, H, W, 2]
-                gy = gxy[..., 1].reshape(n, 1, h, w)
+                part = ops.pointwise_gemm(d_pre, _thin_in_dgrad_pack(conv.weight, 1), 16, out_f32=True)
+                gy = ops.col2im4x4s2(part).view(n, 1, h, w)
     return grads, gy
 
 

@@ -69,49 +69,41 @@ def _nhwc(t: torch.Tensor):
     return n, h, w, c, ld
 
 
-def pick_n_tile(cout: int) -> int:
-    if cout >= 128:
-        return 128
-    if cout >= 64:
-        return 64
-    return 16 * ((cout + 15) // 16)
-
-
-def pad_to(cout: int, n_tile: int) -> int:
-    return n_tile * ((cout + n_tile - 1) // n_tile)
+def padded_cout(cout: int) -> int:
+    """Rows of a packed weight matrix: multiples of 64 (16 for the 1-2 channel heads); the library picks the
+    output-channel tile (256/128/64/32/16) that divides this."""
+    q = 64 if cout >= 64 else 16
+    return q * ((cout + q - 1) // q)
 
 
 # ------------------------------------------------------------------------------------------ packing
-def pack_conv_weight(w: torch.Tensor, n_tile: int | None = None) -> torch.Tensor:
+def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
     """Conv2d weight ``[Cout, Cin, 4, 4]`` (any strides) -> bf16 ``[cout_pad, 16*Cin]`` with
     ``out[co, (ky*4+kx)*Cin + ci] = w[co, ci, ky, kx]`` (include/pai_b200.h, pai_conv4x4_fprop)."""
     cout, cin = w.shape[0], w.shape[1]
-    n_tile = n_tile or pick_n_tile(cout)
-    cp = pad_to(cout, n_tile)
+    cp = padded_cout(cout)
     out = torch.zeros(cp, 16 * cin, dtype=torch.bfloat16, device=w.device)
     out[:cout].view(cout, 4, 4, cin).copy_(w.permute(0, 2, 3, 1))
     return out
 
 
-def pack_convT_weight(w: torch.Tensor, n_tile: int | None = None) -> torch.Tensor:
+def pack_convT_weight(w: torch.Tensor) -> torch.Tensor:
     """ConvTranspose2d weight ``[Cin, Cout, 4, 4]`` -> bf16 ``[4, cout_pad, 4*Cin]`` with
     ``out[py*2+px, co, (ty*2+tx)*Cin + ci] = w[ci, co, T[py][ty].k, T[px][tx].k]``."""
     cin, cout = w.shape[0], w.shape[1]
-    n_tile = n_tile or pick_n_tile(cout)
-    cp = pad_to(cout, n_tile)
+    cp = padded_cout(cout)
     out = torch.zeros(4, cp, 4 * cin, dtype=torch.bfloat16, device=w.device)
     for py in range(2):
         for px in range(2):
-            sub = w[:, :, list(_T_K[py]), :][:, :, :, list(_T_K[px])]       # [ci, co, ty, tx]
+            sub = w[:, :, _T_K[py][0]::2, _T_K[px][0]::2][:, :, :2, :2]      # [ci, co, ty, tx] (taps k, k+2)
             out[py * 2 + px, :cout].view(cout, 2, 2, cin).copy_(sub.permute(1, 2, 3, 0))
     return out
 
 
 # ------------------------------------------------------------------------------------------ fprop / dgrad
 def conv4x4_fprop(x, w_packed, cout, stride=2, bias=None, act=ACT_NONE, slope=0.2, out=None, out_f32=False,
-                  n_tile=None):
+                  n_tile=0):
     n, h, w, cin, ld = _nhwc(x)
-    n_tile = n_tile or pick_n_tile(cout)
     cp = w_packed.shape[0]
     ho, wo = (h // 2, w // 2) if stride == 2 else (h - 1, w - 1)
     if out is None:
@@ -123,9 +115,8 @@ def conv4x4_fprop(x, w_packed, cout, stride=2, bias=None, act=ACT_NONE, slope=0.
     return out
 
 
-def convT4x4s2_fprop(x, w_packed, cout, bias=None, act=ACT_NONE, slope=0.2, out=None, out_f32=False, n_tile=None):
+def convT4x4s2_fprop(x, w_packed, cout, bias=None, act=ACT_NONE, slope=0.2, out=None, out_f32=False, n_tile=0):
     n, h, w, cin, ld = _nhwc(x)
-    n_tile = n_tile or pick_n_tile(cout)
     cp = w_packed.shape[1]
     if out is None:
         out = torch.empty(n, 2 * h, 2 * w, cout, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
@@ -248,3 +239,54 @@ def smallc_conv_wgrad(a, planes, stride=2, flip=False):
     lib.call("pai_smallc_conv_wgrad", _ptr(a), lda, c, _ptr(p0), _ptr(p1), len(planes), n, ih, iw, oh, ow, stride,
              int(flip), _ptr(dw), _stream())
     return dw
+
+
+# ------------------------------------------------------------------------------------------ thin layers as GEMMs
+def im2col4x4(planes, oh, ow, stride=2, flip=False):
+    """1|2 fp32 planes ``[n, ih, iw]`` -> bf16 ``[n, oh, ow, 64]`` (channel = tap*cin + j, zero padded)."""
+    p0 = planes[0]
+    p1 = planes[1] if len(planes) > 1 else None
+    n, ih, iw = p0.shape
+    col = torch.empty(n, oh, ow, 64, dtype=torch.bfloat16, device=p0.device)
+    lib.call("pai_im2col4x4", _ptr(p0), _ptr(p1), len(planes), n, ih, iw, oh, ow, stride, int(flip), _ptr(col),
+             _stream())
+    return col
+
+
+def pointwise_gemm(x, w_packed, cout, bias=None, act=ACT_NONE, slope=0.2, out=None, out_f32=False, out2=None,
+                   act2=ACT_NONE, n_tile=0):
+    """1x1 convolution: ``y[..., co] = act(bias + x[..., :] @ w_packed[co, :])`` over all pixels of an NHWC tensor."""
+    m, cin, ld = _mat(x)
+    cp = w_packed.shape[0]
+    if out is None:
+        out = torch.empty(*x.shape[:-1], cout, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    mo, co, old = _mat(out)
+    assert (mo, co) == (m, cout)
+    old2 = 0
+    if out2 is not None:
+        m2, c2, old2 = _mat(out2)
+        assert (m2, c2) == (m, cout)
+    _igemm_call("pai_pointwise_gemm", 2.0 * m * cin * cout, _ptr(x), m, cin, ld, _ptr(w_packed), cout, cp, _ptr(bias),
+                act, float(slope), _ptr(out), old, int(out.dtype == torch.float32), _ptr(out2), old2, act2, n_tile,
+                _stream())
+    return out
+
+
+def pointwise_wgrad(u, s, splitk=0):
+    """-> fp32 ``[cu, cs]`` = sum over pixels of ``u[pix, :]^T s[pix, :]``."""
+    m, cu, uld = _mat(u)
+    ms, cs, sld = _mat(s)
+    assert ms == m
+    dw = torch.zeros(cu, cs, dtype=torch.float32, device=u.device)
+    _igemm_call("pai_pointwise_wgrad", 2.0 * m * cu * cs, _ptr(u), m, cu, uld, _ptr(s), cs, sld, _ptr(dw), splitk,
+                _stream())
+    return dw
+
+
+def col2im4x4s2(p, bias=None, act=ACT_NONE):
+    """fp32 per-tap partial products ``[n, h, w, >=16]`` -> fp32 ``[n, 2h, 2w]`` (transposed conv, 1 output channel)."""
+    n, h, w, c = p.shape
+    assert p.dtype == torch.float32 and p.stride(3) == 1 and c >= 16
+    out = torch.empty(n, 2 * h, 2 * w, dtype=torch.float32, device=p.device)
+    lib.call("pai_col2im4x4s2", _ptr(p), p.stride(2), n, h, w, _ptr(bias), act, _ptr(out), _stream())
+    return out
