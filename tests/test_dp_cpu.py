@@ -1,0 +1,62 @@
+"""World-size-2 gloo test of the data-parallel exchange (pai_b200/dp.py): gradient averaging after
+manual_backward and the initial parameter broadcast -- the N>1 host logic of bench.py, on CPU."""
+import os
+import socket
+
+import torch
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from pai_b200 import dp
+    r, _, w = dp.init_from_env(backend="gloo")
+    assert (r, w) == (rank, world) and dp.world_size() == world
+    torch.manual_seed(100 + rank)                      # different initial weights per rank on purpose
+    net = torch.nn.Sequential(torch.nn.Linear(8, 4), torch.nn.BatchNorm1d(4), torch.nn.Linear(4, 2))
+    dp.broadcast_parameters(net, src=0)
+    ref = [p.detach().clone() for p in net.parameters()]
+    x = torch.full((6, 8), float(rank + 1))
+    net(x).sum().backward()
+    local = [p.grad.clone() for p in net.parameters()]
+    n = dp.allreduce_gradients(net.parameters())
+    dp.barrier()
+    mx = dp.allreduce_max(float(rank), torch.device("cpu"))
+    q.put((rank, [t.numpy() for t in ref], [g.numpy() for g in local], [p.grad.numpy() for p in net.parameters()], n, mx))
+    torch.distributed.destroy_process_group()
+
+
+def test_gradient_allreduce_and_broadcast_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, ref0, loc0, avg0, n0, mx0), (_, ref1, loc1, avg1, n1, mx1) = out
+    for a, b in zip(ref0, ref1):                       # broadcast: both ranks start from rank 0's weights
+        assert (a == b).all()
+    for l0, l1, a0, a1 in zip(loc0, loc1, avg0, avg1):
+        want = (l0 + l1) / 2
+        assert abs(a0 - want).max() < 1e-6 and abs(a1 - want).max() < 1e-6
+    assert n0 == n1 == sum(a.size for a in avg0) and mx0 == mx1 == 1.0
+
+
+def test_single_process_is_a_no_op():
+    from pai_b200 import dp
+    lin = torch.nn.Linear(3, 3)
+    lin(torch.ones(2, 3)).sum().backward()
+    g = lin.weight.grad.clone()
+    assert dp.allreduce_gradients(lin.parameters()) == 0 and torch.equal(g, lin.weight.grad)
+    assert dp.world_size() == 1
