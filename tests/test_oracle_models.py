@@ -76,9 +76,15 @@ def test_three_training_steps(gz, loss_type, prefix):
 @pytest.mark.reference
 def test_against_live_reference(state):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import torchvision  # noqa: F401  (its import inspects sys.modules; do it before the namespace swap)
     sys.path.insert(0, os.path.join(root, "oracle", "shim"))
     sys.path.insert(0, "/root/reference")
     saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "models" or k.startswith("models.")}
+    # the reference's ``models`` is a namespace package (no __init__.py): a regular package of the same
+    # name anywhere on sys.path would win, so the drop-in package's directory steps aside for this test
+    pkg = os.path.join(root, "thesis-pai-reconstruction_b200")
+    hidden = [p for p in sys.path if os.path.abspath(p) == pkg]
+    sys.path[:] = [p for p in sys.path if os.path.abspath(p) != pkg]
     try:
         from models.pix2pix import Pix2Pix
         from models.wrapper import Discriminator
@@ -101,5 +107,6 @@ def test_against_live_reference(state):
         for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+        sys.path[:0] = hidden
         sys.path.remove("/root/reference")
         sys.path.remove(os.path.join(root, "oracle", "shim"))
