@@ -187,7 +187,7 @@ def ssim_sweep_roofline(device, peaks):
     ms = e0.elapsed_time(e1) / reps
     gbs = n * 524288 / (ms * 1e-3) / 1e9
     del base, pred
-    return {"kernel": "ssim_fwd_kernel<float>", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+    return {"kernel": "ssim_fwd_rows_kernel<float> (row-streaming, FFMA2 separable passes)", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "pairs": n, "ms_per_sweep": ms, "pairs_per_s": n / (ms * 1e-3),
             "algorithmic_bytes_per_pair": 524288, "traffic": None}
 

@@ -339,6 +339,20 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
         : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
     return reinterpret_cast<float2&>(d);
 }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;"
+        : "=l"(d)
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+    return reinterpret_cast<float2&>(d);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;"
+        : "=l"(d)
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+    return reinterpret_cast<float2&>(d);
+}
 __device__ __forceinline__ float ring_ld(const float* p) { return *p; }
 __device__ __forceinline__ float ring_ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 
@@ -395,6 +409,7 @@ ssim_fwd_rows_kernel(const T* __restrict__ pred, const T* __restrict__ target, i
     const int g_first = max(0, y_begin - 5) >> 3, g_last = (h - 1) >> 3;
     int g_issued = g_first - 1, g_waited = g_first - 1;
     float s_acc = 0.f, e_acc = 0.f;
+    int band_b0 = band_sum != nullptr ? y_begin / band_rows : 0, band_y0 = band_b0 * band_rows;
     const int hrow = lane & 7, run = (lane >> 3) + 4 * warp;
     const int x = tid;
 
@@ -486,10 +501,22 @@ ssim_fwd_rows_kernel(const T* __restrict__ pred, const T* __restrict__ target, i
             const int y = y0 + hrow;
             float sv[B];
             float part = 0.f;
+            // SSIM formula on pixel pairs (packed f32x2): the same arithmetic as ssim_terms(), half the
+            // FMA-pipe instructions
+            const float2 c1 = make_float2(1e-4f, 1e-4f), c2 = make_float2(9e-4f, 9e-4f), two = make_float2(2.f, 2.f);
 #pragma unroll
-            for (int o = 0; o < B; ++o) {
-                const SsimTerms t = ssim_terms(make_float4(ma[o].x, ma[o].y, mq[o].x, mq[o].y));
-                sv[o] = __fdividef(t.a1 * t.a2, t.b1 * t.b2);
+            for (int o = 0; o < B; o += 2) {
+                const float2 mp = make_float2(ma[o].x, ma[o + 1].x), mt = make_float2(ma[o].y, ma[o + 1].y);
+                const float2 eq = make_float2(mq[o].x, mq[o + 1].x), er = make_float2(mq[o].y, mq[o + 1].y);
+                const float2 mpt = mul2(mp, mt);
+                const float2 ss = fma2(mp, mp, mul2(mt, mt));              // mu_p^2 + mu_t^2
+                const float2 a1 = fma2(two, mpt, c1);
+                const float2 a2 = fma2(two, sub2(er, mpt), c2);
+                const float2 b1 = add2(ss, c1);
+                const float2 b2 = add2(sub2(eq, ss), c2);
+                const float2 num = mul2(a1, a2), den = mul2(b1, b2);
+                sv[o] = __fdividef(num.x, den.x);
+                sv[o + 1] = __fdividef(num.y, den.y);
             }
             if (run == 0) {
 #pragma unroll
@@ -512,8 +539,9 @@ ssim_fwd_rows_kernel(const T* __restrict__ pred, const T* __restrict__ target, i
             if (band_sum != nullptr) {
                 // the 8 rows of a batch touch at most two depth bands (band_rows > 10): two predicated warp
                 // reductions, one shared-memory atomic per warp and band
-                const int b0 = y0 / band_rows;
-                int br = y - b0 * band_rows;
+                while (y0 >= band_y0 + band_rows) band_y0 += band_rows, ++band_b0;
+                const int b0 = band_b0;
+                int br = y - band_y0;
                 const int sel = br >= band_rows;
                 if (sel) br -= band_rows;
                 const bool inband = y < y_end && br >= 5 && br < band_rows - 5;
