@@ -293,8 +293,20 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 }
 
 // =============================================================================================
-// wgrad: D[cu (128 rows), cs (n_tile cols)] = sum over pixels of U[pix, cu] * S[pix + tap, cs]
-// K-block = 64 pixels.  grid = (cu_blocks * cs_blocks, ntaps, splitk)
+// wgrad (stream-K, persistent): dW[tap][cu][cs] += sum over pixels of U[pix, cu] * S[pix + tap, cs]
+//
+// GEMM view: M = cu (mb 128-row blocks per tile), N = up to 256 columns made of `nbt` 64-channel
+// blocks that may belong to different taps (so narrow layers still run N = 256 and share the U tile
+// between taps), K = pixels in 64-pixel boxes.  Work unit = (tile, k-block); the units are dealt out in
+// equal contiguous ranges to one CTA per SM, so every SM gets the same amount of MMA work regardless
+// of the tile count; a CTA flushes its accumulators with vector reductions (red.global.add.v4.f32)
+// whenever its range leaves a tile.  mb = 2 keeps two 128 x 256 fp32 accumulators (all 512 TMEM
+// columns) on one B tile: 128 FLOP per byte staged from L2 instead of 85.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_s,
                    const IgemmWgradParams p) {
@@ -303,22 +315,16 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_consta
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tile = p.n_tile;
+    const int mb = p.mb, nbt = p.nbt;
     const uint32_t blk_bytes = 64 * 128;  // one [64 pixels x 64 channels] box
-    const uint32_t a_bytes = 2 * blk_bytes;
-    const uint32_t b_bytes = (uint32_t)(n_tile / 64) * blk_bytes;
-    const uint32_t stage_bytes = a_bytes + b_bytes;
+    const uint32_t a_bytes = 2 * mb * blk_bytes;
+    const uint32_t stage_bytes = a_bytes + nbt * blk_bytes;
     const int stages = p.stages;
+    const int n_cols = nbt * 64;
+    const uint32_t tmem_cols = tmem_cols_for(mb * 256);
 
-    const int cs_blocks = p.cs / n_tile;
-    const int cu0 = (blockIdx.x / cs_blocks) * 128;   // rows >= cu are TMA zero fill and never stored
-    const int cs0 = (blockIdx.x % cs_blocks) * n_tile;
-    const int tap = blockIdx.y;
-    const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-    const int per = (total_tiles + gridDim.z - 1) / gridDim.z;
-    const int t_begin = blockIdx.z * per;
-    const int t_end = min(total_tiles, t_begin + per);
-    const int num_kb = t_end - t_begin;
+    const long long units = (long long)p.tiles * p.kblocks;
+    const long long u_begin = units * blockIdx.x / gridDim.x, u_end = units * (blockIdx.x + 1) / gridDim.x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_u);
@@ -330,56 +336,72 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_consta
             mbar_init(&ps.empty[s], 1);
         }
         mbar_init(&ps.acc_full[0], 1);
+        mbar_init(&ps.acc_empty[0], 128);
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc(&ps.tmem_base, tmem_cols_for(n_tile));
+    if (warp == 2) tmem_alloc(&ps.tmem_base, tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = ps.tmem_base;
 
-    if (num_kb > 0) {
-        if (warp == 0) {
-            if (lane == 0) {
-                int stage = 0;
-                uint32_t phase = 0;
-                for (int t = t_begin; t < t_end; ++t) {
-                    int mt = t;
-                    const int tw = mt % p.tiles_w;
-                    mt /= p.tiles_w;
-                    const int th = mt % p.tiles_h;
-                    const int tn = mt / p.tiles_h;
-                    const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
-                    mbar_wait(&ps.empty[stage], phase ^ 1);
-                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                    uint8_t* sb = sa + a_bytes;
-                    mbar_expect_tx(&ps.full[stage], stage_bytes);
-                    tma_load_5d(sa, &tm_u, &ps.full[stage], cu0, w0, 0, h0, n0);
-                    tma_load_5d(sa + blk_bytes, &tm_u, &ps.full[stage], cu0 + 64, w0, 0, h0, n0);
-                    for (int nb = 0; nb < n_tile / 64; ++nb)
-                        tma_load_5d(sb + nb * blk_bytes, &tm_s, &ps.full[stage], p.tap_c[tap] + cs0 + nb * 64,
-                                    w0 + p.tap_w[tap], p.tap_p[tap], h0 + p.tap_h[tap], n0);
-                    if (++stage == stages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long u = u_begin; u < u_end; ++u) {
+                const int tile = (int)(u / p.kblocks);
+                int mt = (int)(u - (long long)tile * p.kblocks);
+                const int ng = tile % p.n_groups, cu0 = (tile / p.n_groups) * 128 * mb;
+                const int tw = mt % p.tiles_w;
+                mt /= p.tiles_w;
+                const int th = mt % p.tiles_h;
+                const int tn = mt / p.tiles_h;
+                const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+                mbar_wait(&ps.empty[stage], phase ^ 1);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                uint8_t* sb = sa + a_bytes;
+                mbar_expect_tx(&ps.full[stage], stage_bytes);
+                for (int i = 0; i < 2 * mb; ++i)   // rows >= cu are TMA zero fill and never stored
+                    tma_load_5d(sa + i * blk_bytes, &tm_u, &ps.full[stage], cu0 + i * 64, w0, 0, h0, n0);
+                for (int nb = 0; nb < nbt; ++nb) {
+                    const int blk = ng * nbt + nb, tap = blk / p.cs_blocks, cb = blk - tap * p.cs_blocks;
+                    tma_load_5d(sb + nb * blk_bytes, &tm_s, &ps.full[stage], p.tap_c[tap] + cb * 64, w0 + p.tap_w[tap],
+                                p.tap_p[tap], h0 + p.tap_h[tap], n0);
+                }
+                if (++stage == stages) {
+                    stage = 0;
+                    phase ^= 1;
                 }
             }
-        } else if (warp == 1) {
-            if (lane == 0) {
-                const uint32_t idesc = umma_idesc_bf16(128, n_tile, 1, 1);
-                int stage = 0;
-                uint32_t phase = 0;
-                for (int kb = 0; kb < num_kb; ++kb) {
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, n_cols, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            int seg = 0;
+            long long u = u_begin;
+            while (u < u_end) {
+                const long long tile_end = (u / p.kblocks + 1) * p.kblocks;
+                const long long seg_end = tile_end < u_end ? tile_end : u_end;
+                mbar_wait(&ps.acc_empty[0], (seg & 1) ^ 1);    // epilogue drained the previous segment
+                tc_fence_after();
+                bool first = true;
+                for (; u < seg_end; ++u) {
                     mbar_wait(&ps.full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
                     const uint32_t sb = sa + a_bytes;
+                    for (int a = 0; a < mb; ++a) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {  // 16 pixels (= 16 rows of 128 B) per MMA
-                        umma_bf16_ss(tmem_base, umma_desc_mnmajor_sw128(sa + k * 2048, blk_bytes),
-                                     umma_desc_mnmajor_sw128(sb + k * 2048, blk_bytes), idesc, (kb | k) != 0);
+                        for (int k = 0; k < 4; ++k) {  // 16 pixels (= 16 rows of 128 B) per MMA
+                            umma_bf16_ss(tmem_base + a * 256,
+                                         umma_desc_mnmajor_sw128(sa + a * 2 * blk_bytes + k * 2048, blk_bytes),
+                                         umma_desc_mnmajor_sw128(sb + k * 2048, blk_bytes), idesc, !(first && k == 0));
+                        }
                     }
+                    first = false;
                     umma_commit(&ps.empty[stage]);
                     if (++stage == stages) {
                         stage = 0;
@@ -387,30 +409,53 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_consta
                     }
                 }
                 umma_commit(&ps.acc_full[0]);
+                ++seg;
             }
-        } else if (warp >= 4) {
-            const int q = warp & 3;
-            const int r = q * 32 + lane;
-            float* o = p.out + ((size_t)tap * p.cu + (cu0 + r)) * (size_t)p.cs + cs0;
-            const bool row_ok = (cu0 + r) < p.cu;
-            mbar_wait(&ps.acc_full[0], 0);
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        int seg = 0;
+        long long u = u_begin;
+        while (u < u_end) {
+            const int tile = (int)(u / p.kblocks);
+            const long long tile_end = (long long)(tile + 1) * p.kblocks;
+            u = tile_end < u_end ? tile_end : u_end;
+            const int ng = tile % p.n_groups, cu0 = (tile / p.n_groups) * 128 * mb;
+            mbar_wait(&ps.acc_full[0], seg & 1);
             tc_fence_after();
-            for (int c = 0; c < n_tile; c += 16) {
-                uint32_t v[16];
-                __syncwarp();
-                tmem_ld_16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-                tmem_ld_wait();
-                if (!row_ok) continue;
+            for (int a = 0; a < mb; ++a) {
+                const int row = cu0 + a * 128 + r;
+                const bool row_ok = row < p.cu;
+                for (int nb = 0; nb < nbt; ++nb) {
+                    const int blk = ng * nbt + nb, tap = blk / p.cs_blocks, cb = blk - tap * p.cs_blocks;
+                    float* o = p.out + ((size_t)tap * p.cu + row) * (size_t)p.cs + cb * 64;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) atomicAdd(o + c + j, __uint_as_float(v[j]));
+                    for (int c = 0; c < 64; c += 16) {
+                        uint32_t v[16];
+                        __syncwarp();
+                        tmem_ld_16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 256 + nb * 64 + c), v);
+                        tmem_ld_wait();
+                        if (row_ok) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                red_add_v4(o + c + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                           __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        }
+                    }
+                }
             }
+            __syncwarp();
+            tc_fence_before();
+            mbar_arrive(&ps.acc_empty[0]);
+            ++seg;
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, tmem_cols_for(n_tile));
+        tmem_dealloc(tmem_base, tmem_cols);
     }
 }
 
@@ -445,18 +490,26 @@ int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFp
     return 0;
 }
 
-int launch_igemm_wgrad(const CUtensorMap& tm_u, const CUtensorMap& tm_s, IgemmWgradParams p, int ntaps, int splitk,
-                       cudaStream_t stream) {
-    const size_t stage_bytes = 2 * 8192 + (size_t)(p.n_tile / 64) * 8192;
+int launch_igemm_wgrad(const CUtensorMap& tm_u, const CUtensorMap& tm_s, IgemmWgradParams p, cudaStream_t stream) {
+    const size_t stage_bytes = (size_t)(2 * p.mb + p.nbt) * 8192;
     p.stages = pick_stages(stage_bytes, 196 * 1024);
     const size_t smem = stage_bytes * p.stages + 1024;
     static bool attr_done = false;
+    static int num_sms = 148;
     if (!attr_done) {
         PAI_CUDA_OK(cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        int dev = 0;
+        PAI_CUDA_OK(cudaGetDevice(&dev));
+        PAI_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         attr_done = true;
     }
-    dim3 grid(((p.cu + 127) / 128) * (p.cs / p.n_tile), ntaps, splitk);
-    igemm_wgrad_kernel<<<grid, kThreads, smem, stream>>>(tm_u, tm_s, p);
+    const long long units = (long long)p.tiles * p.kblocks;
+    // at least ~4 k-blocks per CTA so the pipeline fill / accumulator flush is amortised
+    long long grid = units / 4 > p.tiles ? units / 4 : p.tiles;
+    if (grid > num_sms) grid = num_sms;
+    if (grid < 1) grid = 1;
+    if (p.max_ctas > 0 && grid > p.max_ctas) grid = p.max_ctas;
+    igemm_wgrad_kernel<<<(int)grid, kThreads, smem, stream>>>(tm_u, tm_s, p);
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }

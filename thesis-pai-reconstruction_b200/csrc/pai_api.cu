@@ -250,7 +250,6 @@ static int wgrad_common(const void* u, int un, int uh, int uw, int cu, int u_ld,
     IgemmWgradParams p;
     memset(&p, 0, sizeof(p));
     p.bw = b.bw, p.bh = b.bh, p.bn = b.bn, p.tiles_w = b.tiles_w, p.tiles_h = b.tiles_h, p.tiles_n = b.tiles_n;
-    p.n_tile = cs <= 256 ? cs : (cs % 256 == 0 ? 256 : (cs % 128 == 0 ? 128 : 64));
     p.cu = cu, p.cs = cs, p.out = dw;
     for (int ky = 0; ky < 4; ++ky)
         for (int kx = 0; kx < 4; ++kx) {
@@ -265,15 +264,15 @@ static int wgrad_common(const void* u, int un, int uh, int uw, int cu, int u_ld,
             }   // stride 0: the single tap stays at offset 0
         }
     const int ntaps = stride == 0 ? 1 : 16;
-    const int total_tiles = b.tiles_w * b.tiles_h * b.tiles_n;
-    if (splitk <= 0) {
-        const int base = ((cu + 127) / 128) * (cs / p.n_tile) * ntaps;
-        splitk = (2 * 148 + base - 1) / base;
-        if (splitk > total_tiles / 4) splitk = total_tiles / 4;
-        if (splitk < 1) splitk = 1;
-    }
-    if (splitk > total_tiles) splitk = total_tiles;
-    return launch_igemm_wgrad(tm_u, tm_s, p, ntaps, splitk, stream);
+    p.kblocks = b.tiles_w * b.tiles_h * b.tiles_n;
+    p.cs_blocks = cs / 64;
+    const int nb_total = ntaps * p.cs_blocks;
+    p.nbt = nb_total % 4 == 0 ? 4 : (nb_total % 2 == 0 ? 2 : 1);
+    p.n_groups = nb_total / p.nbt;
+    p.mb = cu > 128 ? 2 : 1;
+    p.tiles = ((cu + 128 * p.mb - 1) / (128 * p.mb)) * p.n_groups;
+    p.max_ctas = splitk > 0 ? splitk * p.tiles : 0;
+    return launch_igemm_wgrad(tm_u, tm_s, p, stream);
 }
 
 int pai_conv4x4_wgrad(const void* x, int n, int h, int w, int cin, int x_ld, const void* gy, int cout, int gy_ld,

@@ -35,16 +35,21 @@ struct IgemmFpropParams {
 struct IgemmWgradParams {
     int bw, bh, bn;            // pixel box, bw*bh*bn == 64
     int tiles_w, tiles_h, tiles_n;
-    int n_tile;                // cs channels per CTA (64, 128 or 256)
+    int kblocks;               // tiles_w * tiles_h * tiles_n 64-pixel K blocks
+    int mb;                    // 128-row blocks of cu per tile (1 or 2)
+    int nbt;                   // 64-channel B blocks per tile (N = 64 * nbt <= 256)
+    int cs_blocks;             // cs / 64
+    int n_groups;              // ntaps * cs_blocks / nbt
+    int tiles;                 // ceil(cu / (128 * mb)) * n_groups
+    int max_ctas;              // 0 = one per SM; the legacy `splitk` argument caps the CTA count (tests)
     int cu, cs;                // channel counts of the unshifted / shifted operand
     int stages;
     int tap_c[16], tap_w[16], tap_p[16], tap_h[16];
-    float* out;                // [ntaps][cu][cs] fp32, accumulated with atomics
+    float* out;                // [ntaps][cu][cs] fp32, accumulated with vector reductions
 };
 
 int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFpropParams p, int m_tiles,
                        int n_tiles, int phases, cudaStream_t stream);
-int launch_igemm_wgrad(const CUtensorMap& tm_u, const CUtensorMap& tm_s, IgemmWgradParams p, int ntaps, int splitk,
-                       cudaStream_t stream);
+int launch_igemm_wgrad(const CUtensorMap& tm_u, const CUtensorMap& tm_s, IgemmWgradParams p, cudaStream_t stream);
 
 }  // namespace pai
