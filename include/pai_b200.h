@@ -158,6 +158,25 @@ int pai_pointwise_wgrad(const void* u, long long m, int cu, int u_ld, const void
 int pai_col2im4x4s2(const float* p, int ldp, int n, int h, int w, const float* bias, int act, float* out,
                     void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer step: torch.optim.Adam(lr=2e-4, betas=(0.5,0.999), eps=1e-7) of
+ * UnetWrapper.configure_optimizers / training_step (models/wrapper.py:97-115,136,160), fused with
+ * the bf16 operand repack of the implicit-GEMM kernels.  step_size = lr / (1 - beta1^t),
+ * inv_bias_correction2_sqrt = 1 / sqrt(1 - beta2^t); parameters, gradients and moments are fp32.
+ *   pai_adam_pack_conv4x4  w [a, b, 4, 4] (Conv2d: a = Cout, b = Cin; ConvTranspose2d: a = Cin, b = Cout):
+ *                          Adam update in place (skipped when grad == NULL: pack only), then
+ *                          pack1[a, (ky*4+kx)*b + b'] and pack2[py*2+px, b', (ty*2+tx)*a + a'] (either may
+ *                          be NULL; pack2 has b_pad rows per phase; padding rows are left untouched)
+ *   pai_adam_multi         the same update for `count` small dense tensors in one launch (host arrays of
+ *                          device pointers)
+ */
+int pai_adam_pack_conv4x4(float* w, const float* grad, float* exp_avg, float* exp_avg_sq, int a, int b, float beta1,
+                          float beta2, float step_size, float inv_bias_correction2_sqrt, float eps, void* pack1,
+                          void* pack2, int b_pad, void* stream);
+int pai_adam_multi(int count, float* const* params, const float* const* grads, float* const* exp_avgs,
+                   float* const* exp_avg_sqs, const int* numels, float beta1, float beta2, float step_size,
+                   float inv_bias_correction2_sqrt, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

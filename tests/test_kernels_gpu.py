@@ -187,3 +187,40 @@ def test_thin_convT_as_pointwise_gemm_plus_col2im():
     assert (dx.float() - refdx).abs().max().item() < 2e-2 * max(1.0, refdx.abs().max().item())
     dw = ops.pointwise_wgrad(x, gcol)[:, :16].reshape(cin, 1, 4, 4)
     assert (dw - wq.grad).abs().max().item() < 1e-2 * max(1.0, wq.grad.abs().max().item())
+
+
+@pytest.mark.parametrize("a,b", [(128, 64), (512, 256), (1, 512), (96, 40)])
+def test_fused_adam_matches_torch_and_repacks(a, b):
+    """FusedAdam (pai_adam_pack_conv4x4 + pai_adam_multi) vs torch.optim.Adam with the reference's
+    hyper-parameters (models/wrapper.py:98-111), and the packs it rewrites vs the Python packers."""
+    from pai_b200 import engine, ops
+    from pai_b200.optim import FusedAdam
+    torch.manual_seed(3)
+    hyper = dict(lr=2e-4, betas=(0.5, 0.999), eps=1e-7)
+    w = torch.nn.Parameter((torch.randn(a, b, 4, 4, device="cuda") * 0.02))
+    bias = torch.nn.Parameter(torch.randn(a, device="cuda"))
+    thin = torch.nn.Parameter(torch.randn(64, 1, 4, 4, device="cuda") * 0.02)
+    ref = [torch.nn.Parameter(t.detach().clone()) for t in (w, bias, thin)]
+    opt, opt_ref = FusedAdam([w, bias, thin], **hyper), torch.optim.Adam(ref, **hyper)
+    # populate the pack cache the way the engine does
+    engine._fprop_pack(w)
+    if a % 8 == 0:
+        engine._dgrad_pack(w)
+    engine._thin_in_pack(thin)
+    for it in range(3):
+        for p, r in zip((w, bias, thin), ref):
+            g = torch.randn_like(p) * (10.0 ** (-it))
+            p.grad, r.grad = g.clone(), g.clone()
+        opt.step()
+        opt_ref.step()
+        for p, r in zip((w, bias, thin), ref):
+            assert torch.allclose(p, r, rtol=1e-5, atol=1e-7), (it, (p - r).abs().max())
+        assert torch.equal(engine._fprop_pack(w), ops.pack_conv_weight(w.detach()))
+        if a % 8 == 0:
+            assert torch.equal(engine._dgrad_pack(w), ops.pack_convT_weight(w.detach()))
+        assert torch.equal(engine._thin_in_pack(thin), engine._pad_cols(thin.detach().permute(0, 2, 3, 1).reshape(64, -1)))
+    sd, sd_ref = opt.state_dict(), opt_ref.state_dict()
+    assert sd["state"].keys() == sd_ref["state"].keys()
+    for k in sd["state"]:
+        assert torch.allclose(sd["state"][k]["exp_avg_sq"], sd_ref["state"][k]["exp_avg_sq"], rtol=1e-4, atol=1e-12)
+        assert float(sd["state"][k]["step"]) == float(sd_ref["state"][k]["step"])

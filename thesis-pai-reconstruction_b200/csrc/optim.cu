@@ -1,0 +1,191 @@
+// Fused Adam update + bf16 GEMM-operand repack for the 4x4 convolution weights, and a multi-tensor Adam
+// for the small parameters (biases, BatchNorm affine).
+//
+// Reference: torch.optim.Adam(lr=2e-4, betas=(0.5, 0.999), eps=1e-7) built by
+// UnetWrapper.configure_optimizers (models/wrapper.py:97-115) and stepped in training_step
+// (models/wrapper.py:136,160).  The arithmetic follows torch's single-tensor Adam:
+//   m += (g - m) * (1 - b1);  v = v * b2 + (1 - b2) * g * g;
+//   p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// The implicit-GEMM kernels read bf16 K-major packs of every weight [A, B, 4, 4] (fp32 master, reference
+// layout):  P1[a, (ky*4+kx)*B + b]              (Conv2d fprop / ConvTranspose2d dgrad operand)
+//           P2[py*2+px, b, (ty*2+tx)*A + a]     (ConvTranspose2d fprop / Conv2d dgrad operand, 4 sub-pixel
+//                                                phases, tap k = T[parity][t] of SURVEY.md Appendix B)
+// One pass over the weight does the update and rewrites both packs, instead of an optimizer pass plus two
+// strided copies.
+#include "pai_common.cuh"
+#include "pai_kernels.h"
+
+namespace pai {
+
+struct AdamHyper {
+    float one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_sqrt, eps;
+};
+
+__device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, const AdamHyper& h) {
+    m = fmaf(g - m, h.one_minus_b1, m);
+    v = fmaf(v, h.b2, h.one_minus_b2 * g * g);
+    const float denom = fmaf(sqrtf(v), h.inv_bc2_sqrt, h.eps);
+    return p - h.step_size * (m / denom);
+}
+
+static constexpr int kTA = 32, kTB = 32, kPackThreads = 256;
+
+// grid (ceil(B/32), ceil(A/32)); smem: s1[16][32 a][32 b] and s2[16][32 b][32 a] bf16 (2 x 32 KB)
+__global__ void __launch_bounds__(kPackThreads)
+adam_pack_conv4x4_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
+                         float* __restrict__ v, int A, int B, AdamHyper hy, __nv_bfloat16* __restrict__ p1,
+                         __nv_bfloat16* __restrict__ p2, int b_pad) {
+    extern __shared__ __nv_bfloat16 pk_smem[];
+    __nv_bfloat16* s1 = pk_smem;                       // [tap][a][b]
+    __nv_bfloat16* s2 = pk_smem + 16 * kTA * kTB;      // [tap][b][a]
+    const int a0 = blockIdx.y * kTA, b0 = blockIdx.x * kTB;
+    const int tid = threadIdx.x;
+    // ---- pass 1: float4 = 4 taps of one (a, b); a row of the tile is 32 b x 16 taps = 128 float4
+    for (int i = tid; i < kTA * 128; i += kPackThreads) {
+        const int al = i >> 7, r = i & 127, bl = r >> 2, t4 = (r & 3) * 4;
+        const int a = a0 + al, b = b0 + bl;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a < A && b < B) {
+            const size_t off = ((size_t)a * B + b) * 16 + t4;
+            x = *reinterpret_cast<const float4*>(w + off);
+            if (g != nullptr) {
+                const float4 gg = *reinterpret_cast<const float4*>(g + off);
+                float4 mm = *reinterpret_cast<const float4*>(m + off);
+                float4 vv = *reinterpret_cast<const float4*>(v + off);
+                x.x = adam_update(x.x, gg.x, mm.x, vv.x, hy);
+                x.y = adam_update(x.y, gg.y, mm.y, vv.y, hy);
+                x.z = adam_update(x.z, gg.z, mm.z, vv.z, hy);
+                x.w = adam_update(x.w, gg.w, mm.w, vv.w, hy);
+                *reinterpret_cast<float4*>(w + off) = x;
+                *reinterpret_cast<float4*>(m + off) = mm;
+                *reinterpret_cast<float4*>(v + off) = vv;
+            }
+        }
+        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat16 hb = __float2bfloat16_rn(xs[j]);
+            s1[((t4 + j) * kTA + al) * kTB + bl] = hb;
+            s2[((t4 + j) * kTB + bl) * kTA + al] = hb;
+        }
+    }
+    __syncthreads();
+    // ---- pass 2: 16-byte chunks (8 bf16).  P1 rows: (tap, a) -> 32 consecutive b
+    if (p1 != nullptr) {
+        for (int i = tid; i < 16 * kTA * 4; i += kPackThreads) {
+            const int c = i & 3, al = (i >> 2) & 31, tap = i >> 7;
+            const int a = a0 + al, b = b0 + c * 8;
+            if (a < A && b < B) {
+                __nv_bfloat16* dst = p1 + (size_t)a * (16 * B) + (size_t)tap * B + b;
+                const __nv_bfloat16* src = s1 + (tap * kTA + al) * kTB + c * 8;
+                if (b + 8 <= B && (B & 7) == 0) {
+                    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+                } else {
+                    for (int j = 0; j < 8 && b + j < B; ++j) dst[j] = src[j];
+                }
+            }
+        }
+    }
+    // P2 rows: (phase, t, b) -> 32 consecutive a;  k = 0,1,2,3 -> (parity, t) = (1,0),(0,0),(1,1),(0,1)
+    if (p2 != nullptr) {
+        for (int i = tid; i < 16 * kTB * 4; i += kPackThreads) {
+            const int c = i & 3, bl = (i >> 2) & 31, tap = i >> 7;
+            const int ky = tap >> 2, kx = tap & 3;
+            const int py = (ky & 1) ^ 1, ty = ky >> 1, px = (kx & 1) ^ 1, tx = kx >> 1;
+            const int a = a0 + c * 8, b = b0 + bl;
+            if (a < A && b < B) {
+                __nv_bfloat16* dst = p2 + ((size_t)(py * 2 + px) * b_pad + b) * (size_t)(4 * A) + (size_t)(ty * 2 + tx) * A + a;
+                const __nv_bfloat16* src = s2 + (tap * kTB + bl) * kTA + c * 8;
+                if (a + 8 <= A && (A & 7) == 0) {
+                    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+                } else {
+                    for (int j = 0; j < 8 && a + j < A; ++j) dst[j] = src[j];
+                }
+            }
+        }
+    }
+}
+
+// ---- multi-tensor Adam for the small parameters --------------------------------------------------
+static constexpr int kMaxTensors = 48;
+struct AdamTable {
+    float* p[kMaxTensors];
+    const float* g[kMaxTensors];
+    float* m[kMaxTensors];
+    float* v[kMaxTensors];
+    int n[kMaxTensors];
+    int count;
+};
+
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const __grid_constant__ AdamTable t, AdamHyper hy) {
+    for (int k = blockIdx.y; k < t.count; k += gridDim.y) {
+        float* p = t.p[k];
+        const float* g = t.g[k];
+        float* m = t.m[k];
+        float* v = t.v[k];
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < t.n[k]; i += gridDim.x * blockDim.x) {
+            float mm = m[i], vv = v[i];
+            p[i] = adam_update(p[i], g[i], mm, vv, hy);
+            m[i] = mm;
+            v[i] = vv;
+        }
+    }
+}
+
+}  // namespace pai
+
+using namespace pai;
+
+extern "C" {
+
+int pai_adam_pack_conv4x4(float* w, const float* grad, float* exp_avg, float* exp_avg_sq, int a, int b, float beta1,
+                          float beta2, float step_size, float inv_bias_correction2_sqrt, float eps, void* pack1,
+                          void* pack2, int b_pad, void* stream) {
+    PAI_REQUIRE(w != nullptr && a > 0 && b > 0, "pai_adam_pack_conv4x4: null weight / empty shape");
+    PAI_REQUIRE(grad == nullptr || (exp_avg != nullptr && exp_avg_sq != nullptr),
+                "pai_adam_pack_conv4x4: optimizer state missing");
+    PAI_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(exp_avg) & 15) == 0 && (reinterpret_cast<uintptr_t>(exp_avg_sq) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(pack1) & 15) == 0 && (reinterpret_cast<uintptr_t>(pack2) & 15) == 0,
+                "pai_adam_pack_conv4x4: pointers must be 16 B aligned");
+    PAI_REQUIRE(pack2 == nullptr || b_pad >= b, "pai_adam_pack_conv4x4: b_pad %d < b %d", b_pad, b);
+    static bool attr = false;
+    const int smem = 2 * 16 * kTA * kTB * (int)sizeof(__nv_bfloat16);
+    if (!attr) {
+        PAI_CUDA_OK(cudaFuncSetAttribute(adam_pack_conv4x4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    AdamHyper hy = {1.f - beta1, beta2, 1.f - beta2, step_size, inv_bias_correction2_sqrt, eps};
+    dim3 grid((b + kTB - 1) / kTB, (a + kTA - 1) / kTA);
+    adam_pack_conv4x4_kernel<<<grid, kPackThreads, smem, (cudaStream_t)stream>>>(
+        w, grad, exp_avg, exp_avg_sq, a, b, hy, (__nv_bfloat16*)pack1, (__nv_bfloat16*)pack2, b_pad);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pai_adam_multi(int count, float* const* params, const float* const* grads, float* const* exp_avgs,
+                   float* const* exp_avg_sqs, const int* numels, float beta1, float beta2, float step_size,
+                   float inv_bias_correction2_sqrt, float eps, void* stream) {
+    PAI_REQUIRE(count >= 0 && (count == 0 || (params && grads && exp_avgs && exp_avg_sqs && numels)),
+                "pai_adam_multi: null table");
+    AdamHyper hy = {1.f - beta1, beta2, 1.f - beta2, step_size, inv_bias_correction2_sqrt, eps};
+    for (int base = 0; base < count; base += kMaxTensors) {
+        AdamTable t;
+        t.count = count - base < kMaxTensors ? count - base : kMaxTensors;
+        int max_n = 1;
+        for (int i = 0; i < t.count; ++i) {
+            t.p[i] = params[base + i], t.g[i] = grads[base + i], t.m[i] = exp_avgs[base + i], t.v[i] = exp_avg_sqs[base + i];
+            t.n[i] = numels[base + i];
+            PAI_REQUIRE(t.p[i] && t.g[i] && t.m[i] && t.v[i] && t.n[i] >= 0, "pai_adam_multi: bad entry %d", base + i);
+            if (t.n[i] > max_n) max_n = t.n[i];
+        }
+        int bx = (max_n + 255) / 256;
+        if (bx > 64) bx = 64;
+        adam_multi_kernel<<<dim3(bx, t.count), 256, 0, (cudaStream_t)stream>>>(t, hy);
+        PAI_CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -15,6 +15,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from pai_b200 import dp, engine, metrics
+from pai_b200.optim import FusedAdam
 
 from ._lightning import LightningModule
 from .utils import denormalize, init_weights, psnr, rmse, ssim  # noqa: F401  (re-exported like the reference)
@@ -67,10 +68,12 @@ class UnetWrapper(LightningModule):
         return fake + real
 
     def configure_optimizers(self):
-        opt_g = torch.optim.Adam(self.unet.parameters(), **_ADAM)
+        # FusedAdam is torch.optim.Adam (same hyper-parameters, state_dict and arithmetic) stepped by the
+        # fused update + weight-repack kernels; on CPU parameters it IS torch.optim.Adam
+        opt_g = FusedAdam(self.unet.parameters(), **_ADAM)
         if self.discriminator is None:
             return opt_g
-        return opt_g, torch.optim.Adam(self.discriminator.parameters(), **_ADAM)
+        return opt_g, FusedAdam(self.discriminator.parameters(), **_ADAM)
 
     # ---- steps ----------------------------------------------------------------------------------
     def training_step(self, batch, batch_idx):

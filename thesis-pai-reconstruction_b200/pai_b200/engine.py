@@ -42,6 +42,36 @@ class _PackCache:
 
 _packs = _PackCache()
 
+_P1_TAGS, _P2_TAGS = ("conv_f", "convT_d"), ("conv_d", "convT_f")
+
+
+def fused_pack_targets(p: torch.Tensor):
+    """-> (pack1, pack2, b_pad) of a ``[A, B, 4, 4]`` weight whose cached packs are the two big GEMM operands
+    (``pai_adam_pack_conv4x4`` rewrites them in the optimizer step), or None when the parameter has no packs
+    or thin-layer packs (those are rebuilt lazily by the Python packers)."""
+    store = p.__dict__.get("_pai_packs")
+    if not store or p.dim() != 4 or tuple(p.shape[2:]) != (4, 4):
+        return None
+    p1 = p2 = None
+    for tag, ent in store.items():
+        if tag in _P1_TAGS:
+            p1 = ent[1]
+        elif tag in _P2_TAGS:
+            p2 = ent[1]
+        else:
+            return None
+    if p1 is None and p2 is None:
+        return None
+    return p1, p2, (p2.shape[1] if p2 is not None else 0)
+
+
+def restamp_packs(p: torch.Tensor) -> None:
+    """Marks the cached packs of ``p`` as current (called after a kernel rewrote them in place)."""
+    store = p.__dict__["_pai_packs"]
+    stamp = (p._version, p.data_ptr())
+    for tag in store:
+        store[tag] = (stamp, store[tag][1])
+
 
 def _fprop_pack(w):      # Conv2d weight [Cout, Cin, 4, 4]
     return _packs.get("conv_f", w, ops.pack_conv_weight)
