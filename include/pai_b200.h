@@ -42,12 +42,15 @@ int pai_version(void);
  *   w_packed: bf16 [cout_pad][16*cin], w_packed[co][(ky*4+kx)*cin + ci] = W[co,ci,ky,kx];
  *             rows cout..cout_pad-1 zero, cout_pad % n_tile == 0.
  *   y: [n,ho,wo,*] (ho = h/2 | h-1), bf16 or fp32 (y_f32), pixel stride y_ld.
+ *   splitk_ws: NULL, or a ZEROED fp32 buffer of n*ho*wo*cout elements.  When given and the layer has too few
+ *             output tiles to occupy the GPU (the <= 8x8 U-Net levels), the K loop is split over SMs, partial
+ *             sums meet in the workspace and a second small kernel applies bias/activation into y.
  *   The same routine is the data-gradient of ConvTranspose2d(4,2,1) (models/pix2pix.py:99-105) when
  *   fed dL/dy and the ConvT weight [Cin_T,Cout_T,4,4] read as a Conv weight [out=Cin_T, in=Cout_T].
  */
 int pai_conv4x4_fprop(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
                       int cout_pad, int stride, const float* bias, int act, float slope, void* y, int y_ld,
-                      int y_f32, int n_tile, void* stream);
+                      int y_f32, int n_tile, float* splitk_ws, void* stream);
 
 /* pai_convT4x4s2_fprop: nn.ConvTranspose2d(cin, cout, kernel_size=4, stride=2, padding=1)
  *   (models/pix2pix.py:99-105,186-192), run as 4 sub-pixel phases:
@@ -59,7 +62,7 @@ int pai_conv4x4_fprop(const void* x, int n, int h, int w, int cin, int x_ld, con
  */
 int pai_convT4x4s2_fprop(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
                          int cout_pad, const float* bias, int act, float slope, void* y, int y_ld, int y_f32,
-                         int n_tile, void* stream);
+                         int n_tile, float* splitk_ws, void* stream);
 
 /* Weight gradients (autograd of the two modules above).
  * pai_conv4x4_wgrad:   dw[ky*4+kx][co][ci] += sum_{n,oh,ow} gy[n,oh,ow,co] * x[n,stride*oh-1+ky,stride*ow-1+kx,ci]

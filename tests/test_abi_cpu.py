@@ -45,7 +45,7 @@ def test_version_and_error_channel_without_gpu(so):
     so.pai_last_error.restype = ctypes.c_char_p
     assert so.pai_version() >= 100
     # argument validation happens before any CUDA call, so it is testable without a device
-    rc = so.pai_conv4x4_fprop(None, 1, 8, 8, 64, 64, None, 64, 64, 2, None, 0, ctypes.c_float(0.2), None, 64, 0, 64, None)
+    rc = so.pai_conv4x4_fprop(None, 1, 8, 8, 64, 64, None, 64, 64, 2, None, 0, ctypes.c_float(0.2), None, 64, 0, 64, None, None)
     assert rc != 0 and b"null pointer" in so.pai_last_error()
     rc = so.pai_ssim_psnr_fwd(ctypes.c_void_p(16), ctypes.c_void_p(16), 0, 1, 8, 8, 0, ctypes.c_void_p(16), None,
                               ctypes.c_void_p(16), None, None)

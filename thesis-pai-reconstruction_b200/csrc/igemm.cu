@@ -23,7 +23,8 @@
 
 namespace pai {
 
-static constexpr int kThreads = 256;
+static constexpr int kThreads = 256;       // wgrad: 4 control/idle warps + 4 epilogue warps
+static constexpr int kFpropThreads = 384;  // fprop: 4 control/idle warps + 8 epilogue warps
 static constexpr int kMaxStages = 8;
 
 struct __align__(8) PipeSmem {
@@ -47,6 +48,11 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
     return v;
 }
 
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+
 // 16 consecutive channels of one pixel -> bf16, vectorised when aligned and fully inside the tensor
 __device__ __forceinline__ void store_bf16_16(__nv_bfloat16* o, const float (&f)[16], int act, float slope, bool vec,
                                               int valid) {
@@ -66,16 +72,49 @@ __device__ __forceinline__ void store_bf16_16(__nv_bfloat16* o, const float (&f)
     }
 }
 
+// 64 fp32 accumulator columns of one row -> (+bias) -> activation -> bf16 -> one XOR-swizzled 128-byte row
+// of the warp's transpose tile.  ACT is a template parameter so the element loop carries no dispatch.
+template <int ACT>
+__device__ __forceinline__ float act_t(float v, float slope) {
+    if (ACT == PAI_ACT_LEAKY) return fmaxf(v, v * slope);      // slope in (0, 1)
+    if (ACT == PAI_ACT_RELU) return fmaxf(v, 0.f);
+    if (ACT == PAI_ACT_TANH) return tanhf(v);
+    return v;
+}
+template <int ACT>
+__device__ __forceinline__ void bias_act_pack(const uint32_t (&v)[64], const float* __restrict__ bias, float slope,
+                                              uint4* tile, int lane) {
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[8 * ch + k]);
+        if (bias != nullptr) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * ch));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * ch) + 1);
+            f[0] += b0.x, f[1] += b0.y, f[2] += b0.z, f[3] += b0.w;
+            f[4] += b1.x, f[5] += b1.y, f[6] += b1.z, f[7] += b1.w;
+        }
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(act_t<ACT>(f[2 * k], slope), act_t<ACT>(f[2 * k + 1], slope));
+            w[k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        tile[lane * 8 + (ch ^ (lane & 7))] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 // =============================================================================================
 // Persistent: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The fp32
 // accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Tile order: output-channel tile fastest, so CTAs running at the same time share the A tile in L2.
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFpropThreads, 1)
 igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const IgemmFpropParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ PipeSmem ps;
-    __shared__ uint4 stage_buf[4][32 * 8];   // per epilogue warp: 32 rows x 128 B, XOR-swizzled 16-byte chunks
+    __shared__ uint4 stage_buf[8][32 * 8];   // per epilogue warp: 32 rows x 128 B, XOR-swizzled 16-byte chunks
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -86,7 +125,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     const int stages = p.stages;
     const int num_kb = p.ntaps * p.kc_per_tap;
     const uint32_t acc_cols = tmem_cols_for(n_tile);
-    const int total_tiles = p.n_tiles * p.m_tiles * p.phases;
+    const int total_tiles = p.n_tiles * p.m_tiles * p.phases * p.splitk;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a);
@@ -99,7 +138,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&ps.acc_full[a], 1);
-            mbar_init(&ps.acc_empty[a], 128);
+            mbar_init(&ps.acc_empty[a], 256);
         }
         mbar_fence_init();
     }
@@ -114,17 +153,16 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int nt = t % p.n_tiles;
-                int r = t / p.n_tiles;
-                int mt = r % p.m_tiles;
-                const int phase_idx = r / p.m_tiles;
-                const int tw = mt % p.tiles_w;
-                mt /= p.tiles_w;
-                const int th = mt % p.tiles_h;
-                const int tn = mt / p.tiles_h;
+                int ks, tt, nt, r, mt, phase_idx, tw, th, tn;
+                p.fd_splitk.divmod(t, tt, ks);
+                p.fd_n_tiles.divmod(tt, r, nt);
+                p.fd_m_tiles.divmod(r, phase_idx, mt);
+                p.fd_tiles_w.divmod(mt, mt, tw);
+                p.fd_tiles_h.divmod(mt, tn, th);
                 const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
                 const int col0 = nt * n_tile;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb_end = num_kb * (ks + 1) / p.splitk;
+                for (int kb = num_kb * ks / p.splitk; kb < kb_end; ++kb) {
                     const int tap = kb / p.kc_per_tap;
                     const int kc = kb - tap * p.kc_per_tap;
                     const int ti = phase_idx * p.ntaps + tap;
@@ -154,7 +192,9 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 mbar_wait(&ps.acc_empty[a], acc_phase ^ 1);   // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + a * acc_cols;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int ks = t - p.fd_splitk.quot(t) * p.splitk;
+                const int kb_begin = num_kb * ks / p.splitk, kb_end = num_kb * (ks + 1) / p.splitk;
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&ps.full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
@@ -162,7 +202,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         umma_bf16_ss(tmem_d, umma_desc_kmajor_sw128(sa + k * 32), umma_desc_kmajor_sw128(sb + k * 32),
-                                     idesc, (kb | k) != 0);
+                                     idesc, (kb != kb_begin) || (k != 0));
                     }
                     umma_commit(&ps.empty[stage]);
                     if (++stage == stages) {
@@ -174,21 +214,23 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             }
         }
     } else if (warp >= 4) {
-        const int q = warp & 3;  // TMEM lane quarter this warp may read
+        // 8 epilogue warps: warp w may read TMEM lanes (w % 4) * 32 .. +31, so the two warps of a lane quarter
+        // split the work items (64-column chunk x output, or 16-column steps on the generic path) between them
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
         const int r = q * 32 + lane;
         const int wi = r % p.bw;
         const int hi = (r / p.bw) % p.bh;
         const int ni = r / (p.bw * p.bh);
+        const int n_out = p.out2 != nullptr ? 2 : 1;
         int it = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-            const int nt = t % p.n_tiles;
-            int rr = t / p.n_tiles;
-            int mt = rr % p.m_tiles;
-            const int phase_idx = rr / p.m_tiles;
-            const int tw = mt % p.tiles_w;
-            mt /= p.tiles_w;
-            const int th = mt % p.tiles_h;
-            const int tn = mt / p.tiles_h;
+            int nt, rr, mt, phase_idx, tw, th, tn;
+            const int tt = p.fd_splitk.quot(t);
+            p.fd_n_tiles.divmod(tt, rr, nt);
+            p.fd_m_tiles.divmod(rr, phase_idx, mt);
+            p.fd_tiles_w.divmod(mt, mt, tw);
+            p.fd_tiles_h.divmod(mt, tn, th);
             const int col0 = nt * n_tile;
             const int gw = tw * p.bw + wi, gh = th * p.bh + hi, gn = tn * p.bn + ni;
             const bool row_ok = (gw < p.gw) && (gh < p.gh) && (gn < p.gn);
@@ -202,42 +244,34 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             const uint32_t tmem_d = tmem_base + a * acc_cols + ((uint32_t)(q * 32) << 16);
             const bool vec_ok = ((p.cout & 7) == 0) && ((off & 7) == 0) && ((off2 & 7) == 0);
             const bool all_vec = __all_sync(0xffffffffu, vec_ok || !row_ok);
-            for (int c = 0; c < n_tile; c += 64) {
-                const int cw = min(64, n_tile - c);
+            const bool fast = !p.out_f32 && all_vec && (n_tile & 63) == 0 && col0 + n_tile <= p.cout &&
+                              (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+            if (fast) {
                 // ---- coalesced path: 64 channels of 32 rows are transposed through a swizzled smem tile so
                 // that 8 lanes write one full 128-byte row segment (4 rows per store instruction)
-                if (!p.out_f32 && cw == 64 && all_vec && col0 + c + 64 <= p.cout) {
-                    float f[64];
+                uint4* tile = stage_buf[warp - 4];
+                int item = 0;
+                for (int c = 0; c < n_tile; c += 64) {
+                    for (int which = 0; which < n_out; ++which, ++item) {
+                        if ((item & 1) != half) continue;
+                        uint32_t v[64];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t v[16];
-                        tmem_ld_16(tmem_d + (uint32_t)(c + 16 * j), v);
+                        for (int j = 0; j < 4; ++j)
+                            tmem_ld_16(tmem_d + (uint32_t)(c + 16 * j), *reinterpret_cast<uint32_t(*)[16]>(&v[16 * j]));
                         tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            float x = __uint_as_float(v[i]);
-                            if (p.bias != nullptr) x += __ldg(p.bias + col0 + c + 16 * j + i);
-                            f[16 * j + i] = x;
-                        }
-                    }
-                    uint4* tile = stage_buf[q];
-#pragma unroll 1
-                    for (int which = 0; which < 2; ++which) {
                         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(which == 0 ? p.out : p.out2);
-                        if (dst == nullptr) break;
                         const int act = which == 0 ? p.act : p.act2;
                         const long long my_off = which == 0 ? off : off2;
-#pragma unroll
-                        for (int ch = 0; ch < 8; ++ch) {
-                            uint32_t w[4];
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                __nv_bfloat162 h = __floats2bfloat162_rn(apply_act(f[8 * ch + 2 * k], act, p.slope),
-                                                                         apply_act(f[8 * ch + 2 * k + 1], act, p.slope));
-                                w[k] = *reinterpret_cast<uint32_t*>(&h);
-                            }
-                            tile[lane * 8 + (ch ^ (lane & 7))] = make_uint4(w[0], w[1], w[2], w[3]);
-                        }
+                        const float* bias_c = p.bias != nullptr ? p.bias + col0 + c : nullptr;
+                        // activation / bias dispatch hoisted out of the 64-element loop
+                        if (act == PAI_ACT_LEAKY)
+                            bias_act_pack<PAI_ACT_LEAKY>(v, bias_c, p.slope, tile, lane);
+                        else if (act == PAI_ACT_RELU)
+                            bias_act_pack<PAI_ACT_RELU>(v, bias_c, p.slope, tile, lane);
+                        else if (act == PAI_ACT_TANH)
+                            bias_act_pack<PAI_ACT_TANH>(v, bias_c, p.slope, tile, lane);
+                        else
+                            bias_act_pack<PAI_ACT_NONE>(v, bias_c, p.slope, tile, lane);
                         __syncwarp();
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -249,10 +283,12 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         }
                         __syncwarp();
                     }
-                    continue;
                 }
-                // ---- generic path (fp32 output, narrow or ragged tiles)
-                for (int cc = c; cc < c + cw; cc += 16) {
+            } else {
+                // ---- generic path (fp32 output, narrow or ragged tiles, split-K accumulation)
+                int step = 0;
+                for (int cc = 0; cc < n_tile; cc += 16, ++step) {
+                    if ((step & 1) != half) continue;
                     uint32_t v[16];
                     __syncwarp();
                     tmem_ld_16(tmem_d + (uint32_t)cc, v);
@@ -265,11 +301,27 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         if (p.bias != nullptr && col0 + cc + j < p.cout) x += __ldg(p.bias + col0 + cc + j);
                         f[j] = x;
                     }
-                    if (p.out_f32) {
+                    if (p.accumulate) {
                         float* o = reinterpret_cast<float*>(p.out) + off + cc;
+                        if (col0 + cc + 16 <= p.cout && ((off + cc) & 3) == 0) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (col0 + cc + j < p.cout) o[j] = apply_act(f[j], p.act, p.slope);
+                            for (int j = 0; j < 16; j += 4) red_add_v4(o + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (col0 + cc + j < p.cout) atomicAdd(o + j, f[j]);
+                        }
+                    } else if (p.out_f32) {
+                        float* o = reinterpret_cast<float*>(p.out) + off + cc;
+                        if (col0 + cc + 16 <= p.cout && ((off + cc) & 3) == 0 && p.act == PAI_ACT_NONE) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (col0 + cc + j < p.cout) o[j] = apply_act(f[j], p.act, p.slope);
+                        }
                     } else {
                         store_bf16_16(reinterpret_cast<__nv_bfloat16*>(p.out) + off + cc, f, p.act, p.slope,
                                       vec_ok && col0 + cc + 16 <= p.cout, p.cout - (col0 + cc));
@@ -281,7 +333,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             }
             __syncwarp();
             tc_fence_before();
-            mbar_arrive(&ps.acc_empty[a]);      // 128 arrivals release the accumulator to the MMA warp
+            mbar_arrive(&ps.acc_empty[a]);      // 256 arrivals release the accumulator to the MMA warp
         }
     }
     tc_fence_before();
@@ -302,11 +354,6 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 // of the tile count; a CTA flushes its accumulators with vector reductions (red.global.add.v4.f32)
 // whenever its range leaves a tile.  mb = 2 keeps two 128 x 256 fp32 accumulators (all 512 TMEM
 // columns) on one B tile: 128 FLOP per byte staged from L2 instead of 85.
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
-                 : "memory");
-}
-
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_s,
                    const IgemmWgradParams p) {
@@ -477,15 +524,45 @@ int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFp
     static bool attr_done = false;
     static int num_sms = 148;
     if (!attr_done) {
-        PAI_CUDA_OK(cudaFuncSetAttribute(igemm_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        PAI_CUDA_OK(cudaFuncSetAttribute(igemm_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 194 * 1024));
         int dev = 0;
         PAI_CUDA_OK(cudaGetDevice(&dev));
         PAI_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
         attr_done = true;
     }
-    const long long total = (long long)m_tiles * n_tiles * phases;
+    if (p.splitk < 1) p.splitk = 1;
+    p.fd_splitk = make_fastdiv(p.splitk), p.fd_n_tiles = make_fastdiv(n_tiles), p.fd_m_tiles = make_fastdiv(m_tiles);
+    p.fd_tiles_w = make_fastdiv(p.tiles_w), p.fd_tiles_h = make_fastdiv(p.tiles_h);
+    const long long total = (long long)m_tiles * n_tiles * phases * p.splitk;
     const int grid = (int)(total < num_sms ? total : num_sms);
-    igemm_fprop_kernel<<<grid, kThreads, smem, stream>>>(tm_a, tm_b, p);
+    igemm_fprop_kernel<<<grid, kFpropThreads, smem, stream>>>(tm_a, tm_b, p);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// split-K finish: y = act(ws + bias) over a dense fp32 workspace [pixels][cout]
+__global__ void __launch_bounds__(256)
+splitk_finish_kernel(const float* __restrict__ ws, long long total, int cout, const float* __restrict__ bias, int act,
+                     float slope, void* __restrict__ y, int y_ld, int y_f32) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pix = i / cout;
+        const int c = (int)(i - pix * cout);
+        float v = ws[i];
+        if (bias != nullptr) v += bias[c];
+        v = apply_act(v, act, slope);
+        if (y_f32)
+            reinterpret_cast<float*>(y)[pix * y_ld + c] = v;
+        else
+            reinterpret_cast<__nv_bfloat16*>(y)[pix * y_ld + c] = __float2bfloat16_rn(v);
+    }
+}
+
+int launch_splitk_finish(const float* ws, long long pixels, int cout, const float* bias, int act, float slope, void* y,
+                         int y_ld, int y_f32, cudaStream_t stream) {
+    const long long total = pixels * cout;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    splitk_finish_kernel<<<(int)blocks, 256, 0, stream>>>(ws, total, cout, bias, act, slope, y, y_ld, y_f32);
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -120,6 +120,16 @@ static int auto_n_tile(int cout_pad, long long m_tiles_x_phases) {
     return best;
 }
 
+// Split-K factor for layers too small to give every SM an output tile (the <= 8x8 levels of the U-Net):
+// the K loop (taps x channel blocks) is cut into slices that run on different SMs and meet in an fp32
+// workspace.  Returns 1 when the layer has enough tiles or no workspace was supplied.
+static int pick_splitk(const void* ws, long long tiles, int num_kb) {
+    if (ws == nullptr || tiles > 74 || num_kb < 8) return 1;
+    long long s = 148 / tiles;
+    if (s > num_kb / 2) s = num_kb / 2;
+    return s < 2 ? 1 : (int)s;
+}
+
 }  // namespace pai
 
 using namespace pai;
@@ -131,7 +141,7 @@ int pai_version(void) { return 100; }
 
 int pai_conv4x4_fprop(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
                       int cout_pad, int stride, const float* bias, int act, float slope, void* y, int y_ld,
-                      int y_f32, int n_tile, void* stream) {
+                      int y_f32, int n_tile, float* splitk_ws, void* stream) {
     PAI_REQUIRE(x && w_packed && y, "pai_conv4x4_fprop: null pointer");
     PAI_REQUIRE(stride == 1 || stride == 2, "pai_conv4x4_fprop: stride must be 1 or 2 (got %d)", stride);
     PAI_REQUIRE(cin > 0 && cin % 64 == 0, "pai_conv4x4_fprop: cin must be a multiple of 64 (got %d)", cin);
@@ -178,15 +188,24 @@ int pai_conv4x4_fprop(const void* x, int n, int h, int w, int cin, int x_ld, con
             }
         }
     p.b_rows_per_phase = cout_pad;
+    const int m_tiles = b.tiles_w * b.tiles_h * b.tiles_n;
+    p.splitk = pick_splitk(splitk_ws, (long long)m_tiles * (cout_pad / n_tile), 16 * (cin / 64));
+    if (p.splitk > 1) {
+        p.out_sn = (long long)ho * wo * cout, p.out_sh = (long long)wo * cout, p.out_sw = cout;
+        p.out_f32 = 1, p.accumulate = 1, p.out = splitk_ws;
+        int rc2 = launch_igemm_fprop(tm_a, tm_b, p, m_tiles, cout_pad / n_tile, 1, (cudaStream_t)stream);
+        if (rc2) return rc2;
+        return launch_splitk_finish(splitk_ws, (long long)n * ho * wo, cout, bias, act, slope, y, y_ld, y_f32,
+                                    (cudaStream_t)stream);
+    }
     p.out_sn = (long long)ho * wo * y_ld, p.out_sh = (long long)wo * y_ld, p.out_sw = y_ld;
     p.bias = bias, p.act = act, p.slope = slope, p.out_f32 = y_f32, p.out = y;
-    return launch_igemm_fprop(tm_a, tm_b, p, b.tiles_w * b.tiles_h * b.tiles_n, cout_pad / n_tile, 1,
-                              (cudaStream_t)stream);
+    return launch_igemm_fprop(tm_a, tm_b, p, m_tiles, cout_pad / n_tile, 1, (cudaStream_t)stream);
 }
 
 int pai_convT4x4s2_fprop(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
                          int cout_pad, const float* bias, int act, float slope, void* y, int y_ld, int y_f32,
-                         int n_tile, void* stream) {
+                         int n_tile, float* splitk_ws, void* stream) {
     PAI_REQUIRE(x && w_packed && y, "pai_convT4x4s2_fprop: null pointer");
     PAI_REQUIRE(cin > 0 && cin % 64 == 0, "pai_convT4x4s2_fprop: cin must be a multiple of 64 (got %d)", cin);
     PAI_REQUIRE(cout_pad % 16 == 0 && cout <= cout_pad, "pai_convT4x4s2_fprop: bad cout %d / cout_pad %d", cout, cout_pad);
@@ -219,12 +238,21 @@ int pai_convT4x4s2_fprop(const void* x, int n, int h, int w, int cin, int x_ld, 
                 }
     p.b_rows_per_phase = cout_pad;
     const long long wo = 2LL * w;
-    p.out_sn = 4LL * h * w * y_ld, p.out_sh = 2 * wo * y_ld, p.out_sw = 2LL * y_ld;
+    const int m_tiles = b.tiles_w * b.tiles_h * b.tiles_n;
+    p.splitk = pick_splitk(splitk_ws, 4LL * m_tiles * (cout_pad / n_tile), 4 * (cin / 64));
+    const long long ld = p.splitk > 1 ? cout : y_ld;
+    p.out_sn = 4LL * h * w * ld, p.out_sh = 2 * wo * ld, p.out_sw = 2LL * ld;
     for (int py = 0; py < 2; ++py)
-        for (int px = 0; px < 2; ++px) p.out_phase_off[py * 2 + px] = (py * wo + px) * y_ld;
+        for (int px = 0; px < 2; ++px) p.out_phase_off[py * 2 + px] = (py * wo + px) * ld;
+    if (p.splitk > 1) {
+        p.out_f32 = 1, p.accumulate = 1, p.out = splitk_ws;
+        int rc2 = launch_igemm_fprop(tm_a, tm_b, p, m_tiles, cout_pad / n_tile, 4, (cudaStream_t)stream);
+        if (rc2) return rc2;
+        return launch_splitk_finish(splitk_ws, 4LL * n * h * w, cout, bias, act, slope, y, y_ld, y_f32,
+                                    (cudaStream_t)stream);
+    }
     p.bias = bias, p.act = act, p.slope = slope, p.out_f32 = y_f32, p.out = y;
-    return launch_igemm_fprop(tm_a, tm_b, p, b.tiles_w * b.tiles_h * b.tiles_n, cout_pad / n_tile, 4,
-                              (cudaStream_t)stream);
+    return launch_igemm_fprop(tm_a, tm_b, p, m_tiles, cout_pad / n_tile, 4, (cudaStream_t)stream);
 }
 
 // stride: 2 = parity-split taps, 1 = unit-stride 4x4 taps, 0 = pointwise (a single tap at offset 0)

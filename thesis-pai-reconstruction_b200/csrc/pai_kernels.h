@@ -8,6 +8,28 @@
 
 namespace pai {
 
+// Unsigned division by a runtime constant without the ~20-instruction hardware sequence:
+// q = (umulhi(n, mul) + n) >> shift, exact for n < 2^31.
+struct FastDiv {
+    uint32_t mul, shift, div;
+#ifdef __CUDACC__
+    __device__ __forceinline__ int quot(int n) const { return (int)((__umulhi((uint32_t)n, mul) + (uint32_t)n) >> shift); }
+    __device__ __forceinline__ void divmod(int n, int& q, int& r) const {
+        q = quot(n);
+        r = n - q * (int)div;
+    }
+#endif
+};
+inline FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.div = (uint32_t)d;
+    uint32_t s = 0;
+    while ((1u << s) < (uint32_t)d) ++s;
+    f.shift = s;
+    f.mul = (uint32_t)(((1ull << 32) * ((1ull << s) - (uint64_t)d)) / (uint64_t)d + 1);
+    return f;
+}
+
 struct IgemmFpropParams {
     int bw, bh, bn;            // TMA box on the pixel grid, bw*bh*bn == 128
     int tiles_w, tiles_h;      // tiles along w / h (tiles along n follow from gridDim.y)
@@ -30,6 +52,9 @@ struct IgemmFpropParams {
     void* out2;
     int act2;
     long long out2_sn, out2_sh, out2_sw;
+    FastDiv fd_splitk, fd_n_tiles, fd_m_tiles, fd_tiles_w, fd_tiles_h;   // filled by launch_igemm_fprop
+    int splitk;                // K slices per output tile (>1: partial sums are accumulated into fp32 `out`)
+    int accumulate;            // generic fp32 path adds into `out` (red.add) instead of storing
 };
 
 struct IgemmWgradParams {
@@ -50,6 +75,9 @@ struct IgemmWgradParams {
 
 int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFpropParams p, int m_tiles,
                        int n_tiles, int phases, cudaStream_t stream);
+// y[pix * ld + c] = act(ws[pix * c_count + c] + bias[c]) for a dense fp32 split-K workspace
+int launch_splitk_finish(const float* ws, long long pixels, int cout, const float* bias, int act, float slope, void* y,
+                         int y_ld, int y_f32, cudaStream_t stream);
 int launch_igemm_wgrad(const CUtensorMap& tm_u, const CUtensorMap& tm_s, IgemmWgradParams p, cudaStream_t stream);
 
 }  // namespace pai

@@ -16,9 +16,9 @@ c_int, c_float, c_void_p, c_ll = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, 
 SIGNATURES = {
     "pai_version": [],
     "pai_conv4x4_fprop": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
-                          c_int, c_float, c_void_p, c_int, c_int, c_int, c_void_p],
+                          c_int, c_float, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "pai_convT4x4s2_fprop": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int,
-                             c_float, c_void_p, c_int, c_int, c_int, c_void_p],
+                             c_float, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "pai_conv4x4_wgrad": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                           c_int, c_void_p],
     "pai_convT4x4s2_wgrad": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int,

@@ -101,6 +101,17 @@ def pack_convT_weight(w: torch.Tensor) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------ fprop / dgrad
+SPLITK_MAX_PIXELS = 74 * 128     # more output pixels than this always fill the GPU with tiles
+
+
+def _splitk_ws(pixels: int, cout: int, device):
+    """Zeroed fp32 split-K workspace for the small (<= 8x8) layers; None for layers that have enough tiles
+    (the library decides the split factor, include/pai_b200.h)."""
+    if pixels > SPLITK_MAX_PIXELS or cout < 16:
+        return None
+    return torch.zeros(pixels, cout, dtype=torch.float32, device=device)
+
+
 def conv4x4_fprop(x, w_packed, cout, stride=2, bias=None, act=ACT_NONE, slope=0.2, out=None, out_f32=False,
                   n_tile=0):
     n, h, w, cin, ld = _nhwc(x)
@@ -110,8 +121,9 @@ def conv4x4_fprop(x, w_packed, cout, stride=2, bias=None, act=ACT_NONE, slope=0.
         out = torch.empty(n, ho, wo, cout, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
     on, oh, ow, oc, old = _nhwc(out)
     assert (on, oh, ow, oc) == (n, ho, wo, cout)
+    ws = _splitk_ws(n * ho * wo, cout, x.device)
     _igemm_call("pai_conv4x4_fprop", 2.0 * n * ho * wo * cout * 16 * cin, _ptr(x), n, h, w, cin, ld, _ptr(w_packed), cout, cp, stride, _ptr(bias), act,
-             float(slope), _ptr(out), old, int(out.dtype == torch.float32), n_tile, _stream())
+             float(slope), _ptr(out), old, int(out.dtype == torch.float32), n_tile, _ptr(ws), _stream())
     return out
 
 
@@ -122,8 +134,9 @@ def convT4x4s2_fprop(x, w_packed, cout, bias=None, act=ACT_NONE, slope=0.2, out=
         out = torch.empty(n, 2 * h, 2 * w, cout, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
     on, oh, ow, oc, old = _nhwc(out)
     assert (on, oh, ow, oc) == (n, 2 * h, 2 * w, cout)
+    ws = _splitk_ws(4 * n * h * w, cout, x.device)
     _igemm_call("pai_convT4x4s2_fprop", 2.0 * n * h * w * cout * 16 * cin, _ptr(x), n, h, w, cin, ld, _ptr(w_packed), cout, cp, _ptr(bias), act,
-             float(slope), _ptr(out), old, int(out.dtype == torch.float32), n_tile, _stream())
+             float(slope), _ptr(out), old, int(out.dtype == torch.float32), n_tile, _ptr(ws), _stream())
     return out
 
 
