@@ -110,6 +110,8 @@ long long pai_ssim_bwd_workspace_bytes(int n, int h, int w);
  *                     sums[0:c] = sum dz (= dbeta), sums[c:2c] = sum dz*xhat (= dgamma)
  *   pai_bn_bwd_apply  dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)); scale_shift NULL = no
  *                     normalisation (dx = dz: plain activation backward, sums[0:c] of the reduce = dbias)
+ *   pai_act_bwd       layers without BatchNorm (enc0, bottleneck, PatchGAN blocks): dx = dz and
+ *                     sums2c[0:c] = sum dz (= dbias) in ONE pass; x only supplies the sign of the pre-activation
  *   pai_colsum        sums2c[0:c] = column sums of x (bias gradients); sums2c[c:2c] is scratch
  */
 int pai_bn_stats(const void* x, long long m, int c, int ld, float* sums, void* stream);
@@ -123,6 +125,8 @@ int pai_bn_bwd_reduce(const void* x, long long m, int c, int ld, const float* sc
 int pai_bn_bwd_apply(const void* x, long long m, int c, int ld, const float* scale_shift, const void* g1, int ldg1,
                      int act1, const void* g2, int ldg2, int act2, float slope, const float* sums,
                      const float* gamma, void* dx, int lddx, void* stream);
+int pai_act_bwd(const void* x, long long m, int c, int ld, const void* g1, int ldg1, int act1, const void* g2, int ldg2,
+                int act2, float slope, float* sums2c, void* dx, int lddx, void* stream);
 int pai_colsum(const void* x, long long m, int c, int ld, float* sums2c, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -224,3 +224,20 @@ def test_fused_adam_matches_torch_and_repacks(a, b):
     for k in sd["state"]:
         assert torch.allclose(sd["state"][k]["exp_avg_sq"], sd_ref["state"][k]["exp_avg_sq"], rtol=1e-4, atol=1e-12)
         assert float(sd["state"][k]["step"]) == float(sd_ref["state"][k]["step"])
+
+
+@pytest.mark.parametrize("with_g2", [False, True])
+def test_act_bwd_fused_bias_gradient(with_g2):
+    """pai_act_bwd (layers without BatchNorm) == separate reduce + apply == autograd of LeakyReLU / identity."""
+    ops = _ops()
+    n, h, w, c = 2, 16, 16, 64
+    pre = _rand((n, h, w, c), 11)
+    x = F.leaky_relu(pre.float(), 0.2).bfloat16()          # the saved activation has the sign of the pre-activation
+    g1, g2 = _rand((n, h, w, c), 12), (_rand((n, h, w, 2 * c), 13)[..., c:] if with_g2 else None)
+    dx = torch.empty(n, h, w, c, dtype=torch.bfloat16, device="cuda")
+    sums = ops.act_bwd(x, g1, ops.ACT_LEAKY, g2, ops.ACT_NONE, dx, slope=0.2)
+    want = g1.float() * torch.where(pre.float() > 0, 1.0, 0.2)
+    if with_g2:
+        want = want + g2.float()
+    assert (dx.float() - want).abs().max().item() < 2e-2
+    assert torch.allclose(sums[:c], want.reshape(-1, c).sum(0), rtol=1e-3, atol=1e-2)

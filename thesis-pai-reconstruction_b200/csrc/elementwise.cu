@@ -123,10 +123,17 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, long long m, 
     ss[3 * c + ch] = invstd;
 }
 
+template <int ACT>
+__device__ __forceinline__ float act_fwd_t(float z, float slope) {
+    if (ACT == PAI_ACT_LEAKY) return fmaxf(z, z * slope);      // slope in (0, 1)
+    if (ACT == PAI_ACT_RELU) return fmaxf(z, 0.f);
+    return z;
+}
+
+template <int ACT1, int ACT2 /* -1: no second output */>
 __global__ void __launch_bounds__(kEwThreads)
 bn_apply_act_kernel(const __nv_bfloat16* __restrict__ x, long long m, int c, int ld, const float* __restrict__ ss,
-                    __nv_bfloat16* __restrict__ o1, int ld1, int act1, __nv_bfloat16* __restrict__ o2, int ld2,
-                    int act2, float slope) {
+                    __nv_bfloat16* __restrict__ o1, int ld1, __nv_bfloat16* __restrict__ o2, int ld2, float slope) {
     const int cv = c >> 3;
     const int vec = threadIdx.x % cv;
     const long long ppb = kEwThreads / cv;
@@ -143,72 +150,118 @@ bn_apply_act_kernel(const __nv_bfloat16* __restrict__ x, long long m, int c, int
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float z = fmaf(v.v[i], sc.v[i], sh.v[i]);
-            a.v[i] = act_fwd(z, act1, slope);
-            b.v[i] = act_fwd(z, act2, slope);
+            a.v[i] = act_fwd_t<ACT1>(z, slope);
+            if (ACT2 >= 0) b.v[i] = act_fwd_t<(ACT2 >= 0 ? ACT2 : 0)>(z, slope);
         }
         store8(o1 + pix * ld1 + vec * 8, a);
-        if (o2 != nullptr) store8(o2 + pix * ld2 + vec * 8, b);
+        if (ACT2 >= 0) store8(o2 + pix * ld2 + vec * 8, b);
     }
 }
 
 // dz = g1 * act1'(z) + g2 * act2'(z),  z = scale * x + shift,  xhat = (x - mean) * invstd
-template <bool APPLY>
+// MODE 0: sums = (sum dz, sum dz*xhat);  MODE 1: dx from the finished sums;  MODE 2 (no BN): dx = dz and
+// sums[0:c] = sum dz in the same pass.  The activations and the presence of g2 / BN are template
+// parameters: the kernels are streams whose instruction count per byte decides whether HBM saturates.
+template <int ACT>
+__device__ __forceinline__ float act_grad_t(float z, float slope) {
+    if (ACT == PAI_ACT_LEAKY) return z > 0.f ? 1.f : slope;
+    if (ACT == PAI_ACT_RELU) return z > 0.f ? 1.f : 0.f;
+    return 1.f;
+}
+
+template <int ACT1, int ACT2 /* -1: no g2 */, bool BN, int MODE>
 __global__ void __launch_bounds__(kEwThreads)
 bn_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long m, int c, int ld, const float* __restrict__ ss,
-              const __nv_bfloat16* __restrict__ g1, int ldg1, int act1, const __nv_bfloat16* __restrict__ g2,
-              int ldg2, int act2, float slope, float* __restrict__ sums, const float* __restrict__ gamma,
-              __nv_bfloat16* __restrict__ dx, int lddx) {
+              const __nv_bfloat16* __restrict__ g1, int ldg1, const __nv_bfloat16* __restrict__ g2, int ldg2,
+              float slope, float* __restrict__ sums, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
+              int lddx) {
     const int cv = c >> 3;
     const int vec = threadIdx.x % cv;
     const long long ppb = kEwThreads / cv;
     Vec8 sc, sh, mu, is;
 #pragma unroll
     for (int i = 0; i < 8; ++i) sc.v[i] = 1.f, sh.v[i] = 0.f, mu.v[i] = 0.f, is.v[i] = 1.f;
-    if (ss != nullptr) {
+    if (BN) {
         sc = loadf8(ss + vec * 8);
         sh = loadf8(ss + c + vec * 8);
         mu = loadf8(ss + 2 * c + vec * 8);
         is = loadf8(ss + 3 * c + vec * 8);
     }
-    Vec8 k0, k1, k2;  // APPLY: dx = k0 * dz + k1 + k2 * xhat   (k0 = gamma*invstd, k1 = -k0*mean(dz), k2 = -k0*mean(dz*xhat))
+    Vec8 k0, k1, k2;  // MODE 1 with BN: dx = k0 * dz + k1 + k2 * xhat
     Vec8 s0, s1;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s0.v[i] = s1.v[i] = 0.f;
-    if (APPLY) {
+    for (int i = 0; i < 8; ++i) s0.v[i] = s1.v[i] = 0.f, k0.v[i] = 1.f, k1.v[i] = 0.f, k2.v[i] = 0.f;
+    if (MODE == 1 && BN) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            if (ss != nullptr) {
-                const float g = gamma != nullptr ? gamma[vec * 8 + i] : 1.f;
-                k0.v[i] = g * is.v[i];
-                k1.v[i] = -k0.v[i] * sums[vec * 8 + i] / (float)m;
-                k2.v[i] = -k0.v[i] * sums[c + vec * 8 + i] / (float)m;
-            } else {
-                k0.v[i] = 1.f, k1.v[i] = 0.f, k2.v[i] = 0.f;
-            }
+            const float g = gamma != nullptr ? gamma[vec * 8 + i] : 1.f;
+            k0.v[i] = g * is.v[i];
+            k1.v[i] = -k0.v[i] * sums[vec * 8 + i] / (float)m;
+            k2.v[i] = -k0.v[i] * sums[c + vec * 8 + i] / (float)m;
         }
     }
-    for (long long pix = (long long)blockIdx.x * ppb + threadIdx.x / cv; pix < m; pix += (long long)gridDim.x * ppb) {
+    const long long stride = (long long)gridDim.x * ppb;
+    for (long long pix = (long long)blockIdx.x * ppb + threadIdx.x / cv; pix < m; pix += stride) {
         const Vec8 v = load8(x + pix * ld + vec * 8);
         const Vec8 a = load8(g1 + pix * ldg1 + vec * 8);
         Vec8 b;
-        if (g2 != nullptr) b = load8(g2 + pix * ldg2 + vec * 8);
+        if (ACT2 >= 0) b = load8(g2 + pix * ldg2 + vec * 8);
         Vec8 o;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float z = fmaf(v.v[i], sc.v[i], sh.v[i]);
-            float dz = a.v[i] * act_grad(z, act1, slope);
-            if (g2 != nullptr) dz = fmaf(b.v[i], act_grad(z, act2, slope), dz);
-            const float xh = (v.v[i] - mu.v[i]) * is.v[i];
-            if (APPLY) {
-                o.v[i] = fmaf(k0.v[i], dz, fmaf(k2.v[i], xh, k1.v[i]));
+            const float z = BN ? fmaf(v.v[i], sc.v[i], sh.v[i]) : v.v[i];
+            float dz = a.v[i] * act_grad_t<ACT1>(z, slope);
+            if (ACT2 >= 0) dz = fmaf(b.v[i], act_grad_t<(ACT2 >= 0 ? ACT2 : 0)>(z, slope), dz);
+            if (BN) {
+                const float xh = (v.v[i] - mu.v[i]) * is.v[i];
+                if (MODE == 1)
+                    o.v[i] = fmaf(k0.v[i], dz, fmaf(k2.v[i], xh, k1.v[i]));
+                else
+                    s1.v[i] = fmaf(dz, xh, s1.v[i]);
             } else {
-                s0.v[i] += dz;
-                s1.v[i] = fmaf(dz, xh, s1.v[i]);
+                o.v[i] = dz;
             }
+            if (MODE != 1) s0.v[i] += dz;
         }
-        if (APPLY) store8(dx + pix * lddx + vec * 8, o);
+        if (MODE != 0) store8(dx + pix * lddx + vec * 8, o);
     }
-    if (!APPLY) block_reduce_2x8(s0, s1, cv, c, sums);
+    if (MODE != 1) block_reduce_2x8(s0, s1, cv, c, sums);
+}
+
+template <int MODE>
+static int bn_bwd_dispatch(int grid, cudaStream_t st, const __nv_bfloat16* x, long long m, int c, int ld, const float* ss,
+                           const __nv_bfloat16* g1, int ldg1, int act1, const __nv_bfloat16* g2, int ldg2, int act2,
+                           float slope, float* sums, const float* gamma, __nv_bfloat16* dx, int lddx) {
+#define PAI_BWD(A1, A2, BNF)                                                                                        \
+    bn_bwd_kernel<A1, A2, BNF, MODE><<<grid, kEwThreads, 0, st>>>(x, m, c, ld, ss, g1, ldg1, g2, ldg2, slope, sums, \
+                                                                   gamma, dx, lddx)
+#define PAI_BWD_A2(A1, BNF)                                            \
+    do {                                                               \
+        if (g2 == nullptr) PAI_BWD(A1, -1, BNF);                       \
+        else if (act2 == PAI_ACT_RELU) PAI_BWD(A1, PAI_ACT_RELU, BNF); \
+        else if (act2 == PAI_ACT_LEAKY) PAI_BWD(A1, PAI_ACT_LEAKY, BNF); \
+        else PAI_BWD(A1, PAI_ACT_NONE, BNF);                           \
+    } while (0)
+#define PAI_BWD_A1(BNF)                                                \
+    do {                                                               \
+        if (act1 == PAI_ACT_LEAKY) PAI_BWD_A2(PAI_ACT_LEAKY, BNF);     \
+        else if (act1 == PAI_ACT_RELU) PAI_BWD_A2(PAI_ACT_RELU, BNF);  \
+        else PAI_BWD_A2(PAI_ACT_NONE, BNF);                            \
+    } while (0)
+    if (ss != nullptr) {
+        if (MODE == 2) {
+            set_error("bn_bwd: the fused apply+reduce mode is for layers without BatchNorm");
+            return -2;
+        }
+        PAI_BWD_A1(true);
+    } else {
+        PAI_BWD_A1(false);
+    }
+#undef PAI_BWD_A1
+#undef PAI_BWD_A2
+#undef PAI_BWD
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 // per-channel column sum of a bf16 [m, c] matrix (bias gradients)
@@ -277,8 +330,23 @@ int pai_bn_apply_act(const void* x, long long m, int c, int ld, const float* sca
     PAI_REQUIRE(x && out1 && m > 0, "pai_bn_apply_act: null pointer / empty input");
     PAI_REQUIRE(ew_ok(c, x, ld) && ew_ok(c, out1, ld1) && (out2 == nullptr || ew_ok(c, out2, ld2)),
                 "pai_bn_apply_act: bad channel count / stride / alignment (c=%d)", c);
-    bn_apply_act_kernel<<<ew_grid(m, c), kEwThreads, 0, (cudaStream_t)stream>>>(
-        (const bf16*)x, m, c, ld, scale_shift, (bf16*)out1, ld1, act1, (bf16*)out2, ld2, act2, slope);
+    const int grid = ew_grid(m, c);
+    cudaStream_t st = (cudaStream_t)stream;
+#define PAI_APPLY(A1, A2) \
+    bn_apply_act_kernel<A1, A2><<<grid, kEwThreads, 0, st>>>((const bf16*)x, m, c, ld, scale_shift, (bf16*)out1, ld1, (bf16*)out2, ld2, slope)
+#define PAI_APPLY_A2(A1)                                               \
+    do {                                                               \
+        if (out2 == nullptr) PAI_APPLY(A1, -1);                        \
+        else if (act2 == PAI_ACT_RELU) PAI_APPLY(A1, PAI_ACT_RELU);    \
+        else if (act2 == PAI_ACT_LEAKY) PAI_APPLY(A1, PAI_ACT_LEAKY);  \
+        else PAI_APPLY(A1, PAI_ACT_NONE);                              \
+    } while (0)
+    PAI_REQUIRE(act1 != PAI_ACT_TANH && act2 != PAI_ACT_TANH, "pai_bn_apply_act: tanh is not a BatchNorm consumer");
+    if (act1 == PAI_ACT_LEAKY) PAI_APPLY_A2(PAI_ACT_LEAKY);
+    else if (act1 == PAI_ACT_RELU) PAI_APPLY_A2(PAI_ACT_RELU);
+    else PAI_APPLY_A2(PAI_ACT_NONE);
+#undef PAI_APPLY_A2
+#undef PAI_APPLY
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -290,11 +358,8 @@ int pai_bn_bwd_reduce(const void* x, long long m, int c, int ld, const float* sc
                 "pai_bn_bwd_reduce: bad channel count / stride / alignment (c=%d)", c);
     cudaStream_t st = (cudaStream_t)stream;
     PAI_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, st));
-    bn_bwd_kernel<false><<<ew_grid(m, c), kEwThreads, 0, st>>>((const bf16*)x, m, c, ld, scale_shift, (const bf16*)g1,
-                                                                ldg1, act1, (const bf16*)g2, ldg2, act2, slope, sums,
-                                                                nullptr, nullptr, 0);
-    PAI_CUDA_OK(cudaGetLastError());
-    return 0;
+    return bn_bwd_dispatch<0>(ew_grid(m, c), st, (const bf16*)x, m, c, ld, scale_shift, (const bf16*)g1, ldg1, act1,
+                              (const bf16*)g2, ldg2, act2, slope, sums, nullptr, nullptr, 0);
 }
 
 int pai_bn_bwd_apply(const void* x, long long m, int c, int ld, const float* scale_shift, const void* g1, int ldg1,
@@ -304,11 +369,20 @@ int pai_bn_bwd_apply(const void* x, long long m, int c, int ld, const float* sca
                 "pai_bn_bwd_apply: null pointer / empty input");
     PAI_REQUIRE(ew_ok(c, x, ld) && ew_ok(c, g1, ldg1) && (g2 == nullptr || ew_ok(c, g2, ldg2)) && ew_ok(c, dx, lddx),
                 "pai_bn_bwd_apply: bad channel count / stride / alignment (c=%d)", c);
-    bn_bwd_kernel<true><<<ew_grid(m, c), kEwThreads, 0, (cudaStream_t)stream>>>(
-        (const bf16*)x, m, c, ld, scale_shift, (const bf16*)g1, ldg1, act1, (const bf16*)g2, ldg2, act2, slope,
-        const_cast<float*>(sums), gamma, (bf16*)dx, lddx);
-    PAI_CUDA_OK(cudaGetLastError());
-    return 0;
+    return bn_bwd_dispatch<1>(ew_grid(m, c), (cudaStream_t)stream, (const bf16*)x, m, c, ld, scale_shift, (const bf16*)g1,
+                              ldg1, act1, (const bf16*)g2, ldg2, act2, slope, const_cast<float*>(sums), gamma, (bf16*)dx,
+                              lddx);
+}
+
+int pai_act_bwd(const void* x, long long m, int c, int ld, const void* g1, int ldg1, int act1, const void* g2, int ldg2,
+                int act2, float slope, float* sums, void* dx, int lddx, void* stream) {
+    PAI_REQUIRE(x && g1 && dx && sums && m > 0, "pai_act_bwd: null pointer / empty input");
+    PAI_REQUIRE(ew_ok(c, x, ld) && ew_ok(c, g1, ldg1) && (g2 == nullptr || ew_ok(c, g2, ldg2)) && ew_ok(c, dx, lddx),
+                "pai_act_bwd: bad channel count / stride / alignment (c=%d)", c);
+    cudaStream_t st = (cudaStream_t)stream;
+    PAI_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, st));
+    return bn_bwd_dispatch<2>(ew_grid(m, c), st, (const bf16*)x, m, c, ld, nullptr, (const bf16*)g1, ldg1, act1,
+                              (const bf16*)g2, ldg2, act2, slope, sums, nullptr, (bf16*)dx, lddx);
 }
 
 int pai_colsum(const void* x, long long m, int c, int ld, float* sums2c, void* stream) {

@@ -283,9 +283,8 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
     # ---- bottleneck encoder L-1: dec_in0 = relu(conv + bias)
     i = L - 1
     conv = spec.enc_convs[i]
-    sums = ops.bn_bwd_reduce(s.dec_in0, None, dcat, ACT_RELU)
     d_raw = _bf16(*s.dec_in0.shape, device=dev)
-    ops.bn_bwd_apply(s.dec_in0, None, dcat, ACT_RELU, None, ACT_NONE, sums, None, d_raw)
+    sums = ops.act_bwd(s.dec_in0, dcat, ACT_RELU, None, ACT_NONE, d_raw)
     dwc = ops.conv4x4_wgrad(s.a_in[i], d_raw, stride=2)                          # [16, co, ci]
     grads[(0, i)] = (dwc.permute(1, 2, 0).reshape(ch[i], ch[i - 1], 4, 4), sums[:ch[i]].clone())
     d_a = ops.convT4x4s2_fprop(d_raw, _dgrad_pack(conv.weight), ch[i - 1])
@@ -306,9 +305,8 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
         d_a = ops.convT4x4s2_fprop(d_raw, _dgrad_pack(conv.weight), ch[i - 1])
     # ---- encoder 0: a_in[1] = lrelu(e0) has the sign of e0, so it doubles as the activation mask
     c0 = ch[0]
-    sums = ops.bn_bwd_reduce(s.a_in[1], None, d_a, ACT_LEAKY, dskip[0], ACT_NONE, slope=SLOPE)
     d_raw = _bf16(*s.a_in[1].shape, device=dev)
-    ops.bn_bwd_apply(s.a_in[1], None, d_a, ACT_LEAKY, dskip[0], ACT_NONE, sums, None, d_raw, slope=SLOPE)
+    sums = ops.act_bwd(s.a_in[1], d_a, ACT_LEAKY, dskip[0], ACT_NONE, d_raw, slope=SLOPE)
     dw0 = ops.pointwise_wgrad(d_raw, s.xcol)                                     # [c0, 64]
     grads[(0, 0)] = (dw0[:, :16].reshape(c0, 1, 4, 4), sums[:c0].clone())
     out = []
@@ -402,9 +400,8 @@ def disc_backward(spec: DiscSpec, s: _Saved, g_logits: torch.Tensor, need_params
         conv = spec.convs[k]
         hk = s.hs[k]                                # lrelu output: same sign as the pre-activation
         ck = hk.shape[3]
-        sums = ops.bn_bwd_reduce(hk, None, dh, ACT_LEAKY, slope=SLOPE) if need_params else None
         d_pre = _bf16(*hk.shape, device=dev)
-        ops.bn_bwd_apply(hk, None, dh, ACT_LEAKY, None, ACT_NONE, sums, None, d_pre, slope=SLOPE)
+        sums = ops.act_bwd(hk, dh, ACT_LEAKY, None, ACT_NONE, d_pre, slope=SLOPE)
         if k > 0:
             if need_params:
                 dwc = ops.conv4x4_wgrad(s.hs[k - 1], d_pre, stride=2)

@@ -36,6 +36,8 @@ SIGNATURES = {
                           c_float, c_void_p, c_void_p],
     "pai_bn_bwd_apply": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int,
                          c_float, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "pai_act_bwd": [c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p,
+                    c_void_p, c_int, c_void_p],
     "pai_colsum": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p],
     "pai_smallc_conv_fprop": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                               c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p],

@@ -221,6 +221,19 @@ def bn_bwd_apply(x, ss, g1, act1, g2, act2, sums, gamma, dx, slope=0.2):
     return dx
 
 
+def act_bwd(x, g1, act1, g2, act2, dx, slope=0.2):
+    """Activation backward of a layer without BatchNorm, fused with the bias gradient:
+    ``dx = g1*act1'(x) + g2*act2'(x)``; returns ``sums`` with ``sums[:c] = sum over pixels of dx``."""
+    m, c, ld = _mat(x)
+    _, _, ldg1 = _mat(g1)
+    ldg2 = _mat(g2)[2] if g2 is not None else 0
+    _, _, lddx = _mat(dx)
+    sums = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+    lib.call("pai_act_bwd", _ptr(x), m, c, ld, _ptr(g1), ldg1, act1, _ptr(g2), ldg2, act2, float(slope), _ptr(sums),
+             _ptr(dx), lddx, _stream())
+    return sums
+
+
 def colsum(x):
     m, c, ld = _mat(x)
     sums = torch.empty(2 * c, dtype=torch.float32, device=x.device)
