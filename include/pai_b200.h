@@ -184,6 +184,53 @@ int pai_adam_multi(int count, float* const* params, const float* const* grads, f
                    float* const* exp_avg_sqs, const int* numels, float beta1, float beta2, float step_size,
                    float inv_bias_correction2_sqrt, float eps, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Layers of the Residual / Attention / Trans U-Net variants (models/res_unet.py, attention_unet.py,
+ * trans_unet.py).  Dense 3x3 and 1x1 convolutions run on the implicit-GEMM kernels:
+ *   pai_conv3x3_fprop   nn.Conv2d(cin, cout, 3, padding=1): y[n,oy,ox,co] = act(bias[co] + sum x[n,oy-1+ky,ox-1+kx,ci] *
+ *                       W[co,ci,ky,kx]); w_packed bf16 [cout_pad][9*cin], w_packed[co][(ky*3+kx)*cin+ci].  Its data
+ *                       gradient is the same routine on dL/dy with w_packed[ci][((2-ky)*3+(2-kx))*cout+co].
+ *   pai_conv3x3_wgrad   dw[ky*3+kx][co][ci] += sum gy[n,oy,ox,co] * x[n,oy-1+ky,ox-1+kx,ci]   (fp32, accumulated)
+ *   (1x1 convolutions are pai_pointwise_gemm / pai_pointwise_wgrad.)
+ * The rest are HBM-bound streams over NHWC bf16 tensors (c % 8 == 0); 1-channel tensors are fp32 planes:
+ *   pai_maxpool2_fwd/bwd      nn.MaxPool2d(2); the gradient goes to the first maximum of the window
+ *   pai_upsample2_fwd/bwd     nn.Upsample(scale_factor=2) (nearest); the gradient sums the 2x2 block
+ *   pai_add_act               out = act(a + b) (b nullable)                (residual add; its backward is pai_act_bwd)
+ *   pai_scale_rows_fwd/bwd    out[p,:] = act(x[p,:] * s[p]);  gx = g*act'*s,  gs[p] = sum_c g*act'*x   (x * attention)
+ *   pai_conv_plane_to_wide    out[p,c] = act(bias[c] + sum_t plane[p+off_t] * w[c][t]), k x k taps, off_t = (ky-pad, kx-pad),
+ *                             negated when flip (Conv2d(1,C,k) forward; data gradient of Conv2d(C,1,k))
+ *   pai_conv_wide_to_plane    out[p] = act(bias + sum_t sum_c x[p+off_t,c] * w[t][c])       (Conv2d(C,1,k) forward)
+ *   pai_conv_plane_wide_wgrad dw[c][t] += sum_p wide[p,c] * plane[p+off_t]                  (k = 1 or 3)
+ *   pai_gconv4_3x3_fprop      Conv2d(c, c, 3, padding=1, groups=c/4): w fp32 [c][9][4]
+ *   pai_gconv4_3x3_wgrad      dw[co][t][j] += sum_p gy[p,co] * x[p+off_t, 4*(co/4)+j]
+ */
+int pai_conv3x3_fprop(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
+                      int cout_pad, const float* bias, int act, float slope, void* y, int y_ld, int y_f32, int n_tile,
+                      float* splitk_ws, void* stream);
+int pai_conv3x3_wgrad(const void* x, int n, int h, int w, int cin, int x_ld, const void* gy, int cout, int gy_ld,
+                      float* dw, void* stream);
+int pai_maxpool2_fwd(const void* x, int n, int h, int w, int c, int ldx, void* y, int ldy, void* stream);
+int pai_maxpool2_bwd(const void* x, int n, int h, int w, int c, int ldx, const void* gy, int ldgy, void* gx, int ldgx,
+                     void* stream);
+int pai_upsample2_fwd(const void* x, int n, int h, int w, int c, int ldx, void* y, int ldy, void* stream);
+int pai_upsample2_bwd(const void* gy, int n, int h, int w, int c, int ldgy, void* gx, int ldgx, void* stream);
+int pai_add_act(const void* a, int lda, const void* b, int ldb, long long m, int c, int act, float slope, void* out,
+                int ldo, void* stream);
+int pai_scale_rows_fwd(const void* x, int ldx, const float* s, long long m, int c, int act, void* out, int ldo,
+                       void* stream);
+int pai_scale_rows_bwd(const void* x, int ldx, const float* s, const void* g, int ldg, long long m, int c, int act,
+                       void* gx, int ldgx, float* gs, void* stream);
+int pai_conv_plane_to_wide(const float* plane, int n, int h, int w, int k, int pad, int flip, const float* wt,
+                           const float* bias, int c, int act, float slope, void* out, int ldo, void* stream);
+int pai_conv_wide_to_plane(const void* x, int n, int h, int w, int c, int ldx, int k, int pad, const float* wt,
+                           const float* bias, int act, float* out, void* stream);
+int pai_conv_plane_wide_wgrad(const float* plane, const void* wide, int ldw, int n, int h, int w, int c, int k, int pad,
+                              int flip, float* dw, void* stream);
+int pai_gconv4_3x3_fprop(const void* x, int n, int h, int w, int c, int ldx, const float* wt, const float* bias, void* y,
+                         int ldy, void* stream);
+int pai_gconv4_3x3_wgrad(const void* x, int ldx, const void* gy, int ldg, int n, int h, int w, int c, float* dw,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

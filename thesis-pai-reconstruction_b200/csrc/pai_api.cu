@@ -291,7 +291,9 @@ static int wgrad_common(const void* u, int un, int uh, int uw, int cu, int u_ld,
                 p.tap_c[t] = 0, p.tap_w[t] = kx - 1, p.tap_p[t] = 0, p.tap_h[t] = ky - 1;
             }   // stride 0: the single tap stays at offset 0
         }
-    const int ntaps = stride == 0 ? 1 : 16;
+    if (stride == 3)   // 3x3, stride 1, padding 1
+        for (int t = 0; t < 9; ++t) p.tap_c[t] = 0, p.tap_w[t] = t % 3 - 1, p.tap_p[t] = 0, p.tap_h[t] = t / 3 - 1;
+    const int ntaps = stride == 0 ? 1 : (stride == 3 ? 9 : 16);
     p.kblocks = b.tiles_w * b.tiles_h * b.tiles_n;
     p.cs_blocks = cs / 64;
     const int nb_total = ntaps * p.cs_blocks;
@@ -314,10 +316,8 @@ int pai_conv4x4_wgrad(const void* x, int n, int h, int w, int cin, int x_ld, con
 int pai_pointwise_wgrad(const void* u, long long m, int cu, int u_ld, const void* s, int cs, int s_ld, float* dw,
                         int splitk, void* stream) {
     PAI_REQUIRE(m > 0 && m < (1LL << 31), "pai_pointwise_wgrad: bad row count");
-    // rows are independent: view them as an [n, 1, w] grid with w = 64-pixel boxes
-    const int w = 64;
-    PAI_REQUIRE(m % w == 0, "pai_pointwise_wgrad: row count must be a multiple of 64 (got %lld)", m);
-    return wgrad_common(u, (int)(m / w), 1, w, cu, u_ld, s, 1, w, cs, s_ld, 0, dw, splitk, (cudaStream_t)stream,
+    // rows are independent: one [1, 1, m] pixel row cut into 64-pixel boxes (a ragged tail is TMA zero fill)
+    return wgrad_common(u, 1, 1, (int)m, cu, u_ld, s, 1, (int)m, cs, s_ld, 0, dw, splitk, (cudaStream_t)stream,
                         "pai_pointwise_wgrad");
 }
 
@@ -328,8 +328,9 @@ int pai_pointwise_gemm(const void* x, long long m, int cin, int x_ld, const void
     PAI_REQUIRE(cin > 0 && cin % 64 == 0, "pai_pointwise_gemm: cin must be a multiple of 64 (got %d)", cin);
     PAI_REQUIRE(cout_pad % 16 == 0 && cout <= cout_pad, "pai_pointwise_gemm: bad cout %d / cout_pad %d", cout, cout_pad);
     PAI_REQUIRE(aligned16(x) && aligned16(w_packed) && x_ld % 8 == 0 && x_ld >= cin, "pai_pointwise_gemm: alignment");
-    PAI_REQUIRE(m > 0 && m % 128 == 0 && m / 128 < (1LL << 31), "pai_pointwise_gemm: rows must be a multiple of 128 (got %lld)", m);
-    const int wbox = 128, n = (int)(m / wbox);
+    PAI_REQUIRE(m > 0 && m < (1LL << 31), "pai_pointwise_gemm: bad row count %lld", m);
+    // one [1, 1, m] pixel row cut into 128-row tiles; a ragged last tile is TMA zero fill and is not stored
+    const int wbox = (int)m, n = 1;
     PixBox b = pick_box(wbox, 1, n, 128);
     if (n_tile <= 0) n_tile = auto_n_tile(cout_pad, (long long)b.tiles_w * b.tiles_h * b.tiles_n);
     PAI_REQUIRE(n_tile >= 16 && n_tile <= 256 && n_tile % 16 == 0 && cout_pad % n_tile == 0,
@@ -359,6 +360,53 @@ int pai_convT4x4s2_wgrad(const void* x, int n, int h, int w, int cin, int x_ld, 
                          float* dw, int splitk, void* stream) {
     return wgrad_common(x, n, h, w, cin, x_ld, gy, 2 * h, 2 * w, cout, gy_ld, 2, dw, splitk, (cudaStream_t)stream,
                         "pai_convT4x4s2_wgrad");
+}
+
+int pai_conv3x3_fprop(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
+                      int cout_pad, const float* bias, int act, float slope, void* y, int y_ld, int y_f32, int n_tile,
+                      float* splitk_ws, void* stream) {
+    PAI_REQUIRE(x && w_packed && y, "pai_conv3x3_fprop: null pointer");
+    PAI_REQUIRE(cin > 0 && cin % 64 == 0, "pai_conv3x3_fprop: cin must be a multiple of 64 (got %d)", cin);
+    PAI_REQUIRE(cout_pad % 16 == 0 && cout <= cout_pad, "pai_conv3x3_fprop: bad cout %d / cout_pad %d", cout, cout_pad);
+    PAI_REQUIRE(aligned16(x) && aligned16(w_packed) && x_ld % 8 == 0 && x_ld >= cin, "pai_conv3x3_fprop: alignment");
+    PixBox b = pick_box(w, h, n, 128);
+    if (n_tile <= 0) n_tile = auto_n_tile(cout_pad, (long long)b.tiles_w * b.tiles_h * b.tiles_n);
+    PAI_REQUIRE(n_tile >= 16 && n_tile <= 256 && n_tile % 16 == 0 && cout_pad % n_tile == 0,
+                "pai_conv3x3_fprop: bad n_tile %d for cout_pad %d", n_tile, cout_pad);
+    CUtensorMap tm_a, tm_b;
+    int rc = map_unit(&tm_a, x, n, h, w, cin, x_ld, b);
+    if (rc) return rc;
+    uint64_t bd[2] = {(uint64_t)9 * cin, (uint64_t)cout_pad};
+    uint64_t bs[1] = {(uint64_t)9 * cin * 2};
+    uint32_t bb[2] = {64, (uint32_t)n_tile};
+    rc = encode_tmap_bf16(&tm_b, w_packed, 2, bd, bs, bb);
+    if (rc) return rc;
+    IgemmFpropParams p;
+    memset(&p, 0, sizeof(p));
+    p.bw = b.bw, p.bh = b.bh, p.bn = b.bn, p.tiles_w = b.tiles_w, p.tiles_h = b.tiles_h;
+    p.gw = w, p.gh = h, p.gn = n;
+    p.n_tile = n_tile, p.cout = cout, p.kc_per_tap = cin / 64, p.ntaps = 9;
+    for (int t = 0; t < 9; ++t) p.tap_c[t] = 0, p.tap_w[t] = t % 3 - 1, p.tap_p[t] = 0, p.tap_h[t] = t / 3 - 1;
+    p.b_rows_per_phase = cout_pad;
+    const int m_tiles = b.tiles_w * b.tiles_h * b.tiles_n;
+    p.splitk = pick_splitk(splitk_ws, (long long)m_tiles * (cout_pad / n_tile), 9 * (cin / 64));
+    if (p.splitk > 1) {
+        p.out_sn = (long long)h * w * cout, p.out_sh = (long long)w * cout, p.out_sw = cout;
+        p.out_f32 = 1, p.accumulate = 1, p.out = splitk_ws;
+        int rc2 = launch_igemm_fprop(tm_a, tm_b, p, m_tiles, cout_pad / n_tile, 1, (cudaStream_t)stream);
+        if (rc2) return rc2;
+        return launch_splitk_finish(splitk_ws, (long long)n * h * w, cout, bias, act, slope, y, y_ld, y_f32,
+                                    (cudaStream_t)stream);
+    }
+    p.out_sn = (long long)h * w * y_ld, p.out_sh = (long long)w * y_ld, p.out_sw = y_ld;
+    p.bias = bias, p.act = act, p.slope = slope, p.out_f32 = y_f32, p.out = y;
+    return launch_igemm_fprop(tm_a, tm_b, p, m_tiles, cout_pad / n_tile, 1, (cudaStream_t)stream);
+}
+
+int pai_conv3x3_wgrad(const void* x, int n, int h, int w, int cin, int x_ld, const void* gy, int cout, int gy_ld,
+                      float* dw, void* stream) {
+    return wgrad_common(gy, n, h, w, cout, gy_ld, x, h, w, cin, x_ld, 3, dw, 0, (cudaStream_t)stream,
+                        "pai_conv3x3_wgrad");
 }
 
 }  // extern "C"

@@ -1,0 +1,341 @@
+"""Layer-level autograd nodes on the B200 kernels for the Residual / Attention / Trans U-Net variants
+(reference: models/res_unet.py, models/attention_unet.py, models/trans_unet.py).
+
+Activations travel between nodes as NHWC bf16 tensors ``[N, H, W, C]``; 1-channel tensors (network input
+and output, attention logits) are fp32 planes ``[N, H, W]``.  Parameters are the fp32 tensors of the
+drop-in ``nn.Module`` tree in the reference's layouts.  Every node's forward AND backward is a kernel of
+libpai_b200.so; there is no PyTorch-op implementation behind them.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .engine import BN_EPS, BN_MOMENTUM, _packs
+from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH  # noqa: F401
+
+
+def _need(flag_list, i):
+    return flag_list[i]
+
+
+# ------------------------------------------------------------------------------------------ convolutions
+class _Conv1x1(torch.autograd.Function):
+    """nn.Conv2d(cin, cout, 1) / nn.Linear on the tensor-core pointwise GEMM (cin, cout multiples of 64)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        cout = weight.shape[0]
+        wp = _packs.get("c1_f", weight, ops.pack_conv1x1_weight)
+        y = ops.pointwise_gemm(x, wp, cout, bias=None if bias is None else bias.detach())
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        cout, cin = weight.shape[0], weight.shape[1]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            wt = _packs.get("c1_d", weight, ops.pack_conv1x1_weight_t)
+            gx = ops.pointwise_gemm(gy, wt, cin)
+        if ctx.needs_input_grad[1]:
+            gw = ops.pointwise_wgrad(gy, x).view(weight.shape)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = ops.colsum(gy).clone()
+        return gx, gw, gb
+
+
+class _Conv3x3(torch.autograd.Function):
+    """nn.Conv2d(cin, cout, 3, padding=1) on the implicit-GEMM kernel (cin, cout multiples of 64)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        cout = weight.shape[0]
+        wp = _packs.get("c3_f", weight, ops.pack_conv3x3_weight)
+        y = ops.conv3x3_fprop(x, wp, cout, bias=None if bias is None else bias.detach())
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        cout, cin = weight.shape[0], weight.shape[1]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            wd = _packs.get("c3_d", weight, ops.pack_conv3x3_weight_dgrad)
+            gx = ops.conv3x3_fprop(gy, wd, cin)
+        if ctx.needs_input_grad[1]:
+            gw = ops.conv3x3_wgrad(x, gy).permute(1, 2, 0).reshape(cout, cin, 3, 3)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = ops.colsum(gy).clone()
+        return gx, gw, gb
+
+
+def _gw_fwd(w):      # [C, 4, 3, 3] -> fp32 [C, 9, 4]
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], 9, 4).contiguous()
+
+
+def _gw_bwd(w):      # data-gradient weights: taps flipped, (co, j) transposed inside each group of 4
+    c = w.shape[0]
+    g = w.view(c // 4, 4, 4, 3, 3).flip(3, 4).permute(0, 2, 1, 3, 4).reshape(c, 4, 3, 3)
+    return _gw_fwd(g)
+
+
+class _GroupedConv3x3(torch.autograd.Function):
+    """nn.Conv2d(c, c, 3, padding=1, groups=c/4) (ResNeXt cardinality 32 x bottleneck 4, res_unet.py:150-156)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        y = ops.gconv4_3x3_fprop(x, _packs.get("g4_f", weight, _gw_fwd), None if bias is None else bias.detach())
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = ops.gconv4_3x3_fprop(gy, _packs.get("g4_d", weight, _gw_bwd))
+        if ctx.needs_input_grad[1]:
+            gw = ops.gconv4_3x3_wgrad(x, gy).view(-1, 3, 3, 4).permute(0, 3, 1, 2).contiguous()
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = ops.colsum(gy).clone()
+        return gx, gw, gb
+
+
+class _PlaneToWide(torch.autograd.Function):
+    """nn.Conv2d(1, c, k, padding=k//2) on an fp32 plane (the network input: no data gradient)."""
+
+    @staticmethod
+    def forward(ctx, plane, weight, bias, act):
+        c, k = weight.shape[0], weight.shape[2]
+        y = ops.conv_plane_to_wide(plane, weight.detach().reshape(c, k * k), None if bias is None else bias.detach(), k,
+                                   k // 2, act)
+        ctx.save_for_backward(plane, y)
+        ctx.k, ctx.act, ctx.has_bias = k, act, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        plane, y = ctx.saved_tensors
+        gy = gy.contiguous()
+        if ctx.act != ACT_NONE:
+            g2 = torch.empty_like(gy)
+            ops.act_bwd(y, gy, ctx.act, None, ACT_NONE, g2)
+            gy = g2
+        c, k = gy.shape[3], ctx.k
+        gw = ops.conv_plane_wide_wgrad(plane, gy, k, k // 2).view(c, 1, k, k)
+        gb = ops.colsum(gy).clone() if ctx.has_bias else None
+        return None, gw, gb, None
+
+
+class _WideToPlane(torch.autograd.Function):
+    """nn.Conv2d(c, 1, k, padding=k//2) (+ Tanh) -> fp32 plane (network output, attention logits)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        c, k = weight.shape[1], weight.shape[2]
+        wt = weight.detach().reshape(c, k * k).t().contiguous()           # [taps, c]
+        y = ops.conv_wide_to_plane(x, wt, None if bias is None else bias.detach(), k, k // 2, act)
+        ctx.save_for_backward(x, weight, y)
+        ctx.k, ctx.act, ctx.has_bias = k, act, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, y = ctx.saved_tensors
+        c, k = weight.shape[1], ctx.k
+        g = gy.float().contiguous()
+        if ctx.act == ACT_TANH:
+            g = g * (1.0 - y * y)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = ops.conv_plane_to_wide(g, weight.detach().reshape(c, k * k), None, k, k // 2, flip=True)
+        if ctx.needs_input_grad[1]:
+            gw = ops.conv_plane_wide_wgrad(g, x, k, k // 2, flip=True).view(1, c, k, k)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g.sum().reshape(1)
+        return gx, gw, gb, None
+
+
+def conv2d(x, mod: nn.Conv2d):
+    """Dispatch of an ``nn.Conv2d`` parameter holder onto the kernels (NHWC bf16 in / out)."""
+    k, cin, cout, groups = mod.kernel_size[0], mod.in_channels, mod.out_channels, mod.groups
+    if mod.stride != (1, 1) or mod.padding != (k // 2, k // 2) or mod.dilation != (1, 1):
+        raise RuntimeError(f"pai_b200: unsupported convolution geometry {mod}")
+    if groups == 1 and cin % 64 == 0 and cout % 64 == 0:
+        if k == 1:
+            return _Conv1x1.apply(x, mod.weight, mod.bias)
+        if k == 3:
+            return _Conv3x3.apply(x, mod.weight, mod.bias)
+    if k == 3 and groups > 1 and cin == cout and cin // groups == 4:
+        return _GroupedConv3x3.apply(x, mod.weight, mod.bias)
+    raise RuntimeError(f"pai_b200: no B200 kernel for {mod} (channel counts must be multiples of 64, or the "
+                       "ResNeXt 4-channel groups); there is no fallback")
+
+
+def conv_in(plane, mod: nn.Conv2d, act=ACT_NONE):
+    if mod.in_channels != 1:
+        raise RuntimeError("pai_b200: the B200 path takes 1-channel (grayscale PAI) inputs; got "
+                           f"in_channels={mod.in_channels}. No fallback exists.")
+    return _PlaneToWide.apply(plane, mod.weight, mod.bias, act)
+
+
+def conv_out(x, mod: nn.Conv2d, act=ACT_NONE):
+    if mod.out_channels != 1:
+        raise RuntimeError("pai_b200: the B200 path produces 1-channel outputs; got "
+                           f"out_channels={mod.out_channels}. No fallback exists.")
+    return _WideToPlane.apply(x, mod.weight, mod.bias, act)
+
+
+# ------------------------------------------------------------------------------------------ BatchNorm (+activation)
+class _BatchNormAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, raw, weight, bias, mod, act):
+        training = mod.training or mod.running_mean is None
+        m, c, _ = ops._mat(raw)
+        sums = ops.bn_stats(raw) if training else None
+        ss = ops.bn_finalize(sums, m, c, weight.detach(), bias.detach(), mod.running_mean, mod.running_var,
+                             training=training, eps=mod.eps, momentum=mod.momentum if mod.momentum is not None else 0.1)
+        if training and mod.num_batches_tracked is not None:
+            mod.num_batches_tracked.add_(1)
+        out = torch.empty(*raw.shape, dtype=torch.bfloat16, device=raw.device)
+        ops.bn_apply_act(raw, ss, out, act)
+        ctx.save_for_backward(raw, ss, weight)
+        ctx.act, ctx.training = act, training
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        raw, ss, weight = ctx.saved_tensors
+        g = g.contiguous()
+        c = raw.shape[-1]
+        if not ctx.training:
+            raise RuntimeError("pai_b200: backward through eval-mode BatchNorm is not implemented")
+        sums = ops.bn_bwd_reduce(raw, ss, g, ctx.act)
+        d_raw = torch.empty(*raw.shape, dtype=torch.bfloat16, device=raw.device)
+        ops.bn_bwd_apply(raw, ss, g, ctx.act, None, ACT_NONE, sums, weight.detach(), d_raw)
+        return d_raw, sums[c:], sums[:c], None, None
+
+
+def batchnorm_act(raw, mod: nn.BatchNorm2d, act=ACT_NONE):
+    if abs(mod.eps - BN_EPS) > 0 and mod.eps <= 0:
+        raise RuntimeError("pai_b200: bad BatchNorm eps")
+    return _BatchNormAct.apply(raw, mod.weight, mod.bias, mod, act)
+
+
+# ------------------------------------------------------------------------------------------ elementwise / resampling
+class _AddAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, act):
+        out = ops.add_act(a, b, act)
+        ctx.act = act
+        if act != ACT_NONE:
+            ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.act != ACT_NONE:
+            (out,) = ctx.saved_tensors
+            g2 = torch.empty(*out.shape, dtype=torch.bfloat16, device=out.device)
+            ops.act_bwd(out, g.contiguous(), ctx.act, None, ACT_NONE, g2)
+            g = g2
+        return g, g, None
+
+
+class _Act(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, act):
+        out = ops.add_act(a, None, act)
+        ctx.act = act
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        g2 = torch.empty(*out.shape, dtype=torch.bfloat16, device=out.device)
+        ops.act_bwd(out, g.contiguous(), ctx.act, None, ACT_NONE, g2)
+        return g2, None
+
+
+class _MaxPool2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.maxpool2_fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return ops.maxpool2_bwd(x, g.contiguous())
+
+
+class _Upsample2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.upsample2_fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.upsample2_bwd(g.contiguous())
+
+
+class _ScaleRows(torch.autograd.Function):
+    """``x * s`` with a per-pixel fp32 factor (attention_unet.py:96)."""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        ctx.save_for_backward(x, s)
+        return ops.scale_rows_fwd(x, s)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, s = ctx.saved_tensors
+        gx, gs = ops.scale_rows_bwd(x, s, g.contiguous())
+        return gx, gs
+
+
+def add_act(a, b, act=ACT_NONE):
+    return _AddAct.apply(a, b, act)
+
+
+def activation(a, act):
+    return _Act.apply(a, act)
+
+
+def maxpool2(x):
+    return _MaxPool2.apply(x)
+
+
+def upsample2(x):
+    return _Upsample2.apply(x)
+
+
+def scale_rows(x, s):
+    return _ScaleRows.apply(x, s)
+
+
+def dropout2d(x, mod):
+    if isinstance(mod, nn.Identity) or not mod.training or mod.p == 0:
+        return x
+    raise RuntimeError("pai_b200: train-mode Dropout2d with p > 0 is not implemented on the B200 path "
+                       "(main.py's default --dropout is 0.0); no fallback exists")
+
+
+def to_plane(x: torch.Tensor) -> torch.Tensor:
+    """``[N, 1, H, W]`` network input -> fp32 plane ``[N, H, W]`` on the GPU (the reference's ``x.type(float32)``)."""
+    if not x.is_cuda:
+        raise RuntimeError("pai_b200: the B200 path needs CUDA tensors; there is no CPU fallback")
+    if x.dim() != 4 or x.shape[1] != 1:
+        raise RuntimeError(f"pai_b200: expected a [N, 1, H, W] input, got {tuple(x.shape)}")
+    return x.float().contiguous().view(x.shape[0], x.shape[2], x.shape[3])

@@ -48,6 +48,25 @@ SIGNATURES = {
                            c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
     "pai_pointwise_wgrad": [c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
     "pai_col2im4x4s2": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
+    "pai_conv3x3_fprop": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_float,
+                          c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
+    "pai_conv3x3_wgrad": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p],
+    "pai_maxpool2_fwd": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
+    "pai_maxpool2_bwd": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p],
+    "pai_upsample2_fwd": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
+    "pai_upsample2_bwd": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p],
+    "pai_add_act": [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_float, c_void_p, c_int, c_void_p],
+    "pai_scale_rows_fwd": [c_void_p, c_int, c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_void_p],
+    "pai_scale_rows_bwd": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_void_p,
+                           c_void_p],
+    "pai_conv_plane_to_wide": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int,
+                               c_float, c_void_p, c_int, c_void_p],
+    "pai_conv_wide_to_plane": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                               c_void_p, c_void_p],
+    "pai_conv_plane_wide_wgrad": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                                  c_void_p],
+    "pai_gconv4_3x3_fprop": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    "pai_gconv4_3x3_wgrad": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "pai_adam_pack_conv4x4": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float,
                               c_float, c_void_p, c_void_p, c_int, c_void_p],
     "pai_adam_multi": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float,

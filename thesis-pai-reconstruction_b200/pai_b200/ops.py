@@ -316,3 +316,154 @@ def col2im4x4s2(p, bias=None, act=ACT_NONE):
     out = torch.empty(n, 2 * h, 2 * w, dtype=torch.float32, device=p.device)
     lib.call("pai_col2im4x4s2", _ptr(p), p.stride(2), n, h, w, _ptr(bias), act, _ptr(out), _stream())
     return out
+
+
+# ------------------------------------------------------------------------------------------ Res / Attention / Trans U-Net layers
+def pack_conv1x1_weight(w: torch.Tensor) -> torch.Tensor:
+    """Conv2d weight ``[Cout, Cin, 1, 1]`` (or a Linear ``[out, in]``) -> bf16 ``[cout_pad, Cin]``."""
+    cout, cin = w.shape[0], w.shape[1]
+    out = torch.zeros(padded_cout(cout), cin, dtype=torch.bfloat16, device=w.device)
+    out[:cout].copy_(w.reshape(cout, cin))
+    return out
+
+
+def pack_conv1x1_weight_t(w: torch.Tensor) -> torch.Tensor:
+    """-> bf16 ``[cin_pad, Cout]``: the data-gradient operand of a 1x1 convolution / Linear."""
+    cout, cin = w.shape[0], w.shape[1]
+    out = torch.zeros(padded_cout(cin), cout, dtype=torch.bfloat16, device=w.device)
+    out[:cin].copy_(w.reshape(cout, cin).t())
+    return out
+
+
+def pack_conv3x3_weight(w: torch.Tensor) -> torch.Tensor:
+    """Conv2d weight ``[Cout, Cin, 3, 3]`` -> bf16 ``[cout_pad, 9*Cin]``, column ``(ky*3+kx)*Cin + ci``."""
+    cout, cin = w.shape[0], w.shape[1]
+    out = torch.zeros(padded_cout(cout), 9 * cin, dtype=torch.bfloat16, device=w.device)
+    out[:cout].view(cout, 3, 3, cin).copy_(w.permute(0, 2, 3, 1))
+    return out
+
+
+def pack_conv3x3_weight_dgrad(w: torch.Tensor) -> torch.Tensor:
+    """-> bf16 ``[cin_pad, 9*Cout]`` with the taps flipped: conv3x3(dL/dy, this) = dL/dx."""
+    cout, cin = w.shape[0], w.shape[1]
+    out = torch.zeros(padded_cout(cin), 9 * cout, dtype=torch.bfloat16, device=w.device)
+    out[:cin].view(cin, 3, 3, cout).copy_(w.flip(2, 3).permute(1, 2, 3, 0))
+    return out
+
+
+def conv3x3_fprop(x, w_packed, cout, bias=None, act=ACT_NONE, slope=0.2, out=None, out_f32=False):
+    n, h, w, cin, ld = _nhwc(x)
+    cp = w_packed.shape[0]
+    if out is None:
+        out = torch.empty(n, h, w, cout, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+    old = _nhwc(out)[4]
+    ws = _splitk_ws(n * h * w, cout, x.device)
+    _igemm_call("pai_conv3x3_fprop", 2.0 * n * h * w * cout * 9 * cin, _ptr(x), n, h, w, cin, ld, _ptr(w_packed), cout, cp,
+                _ptr(bias), act, float(slope), _ptr(out), old, int(out.dtype == torch.float32), 0, _ptr(ws), _stream())
+    return out
+
+
+def conv3x3_wgrad(x, gy):
+    """-> fp32 ``[9, Cout, Cin]``; ``.permute(1, 2, 0).reshape(Cout, Cin, 3, 3)`` is the reference layout."""
+    n, h, w, cin, ld = _nhwc(x)
+    _, _, _, cout, gld = _nhwc(gy)
+    dw = torch.zeros(9, cout, cin, dtype=torch.float32, device=x.device)
+    _igemm_call("pai_conv3x3_wgrad", 2.0 * n * h * w * cout * 9 * cin, _ptr(x), n, h, w, cin, ld, _ptr(gy), cout, gld,
+                _ptr(dw), _stream())
+    return dw
+
+
+def maxpool2_fwd(x):
+    n, h, w, c, ld = _nhwc(x)
+    y = torch.empty(n, h // 2, w // 2, c, dtype=torch.bfloat16, device=x.device)
+    lib.call("pai_maxpool2_fwd", _ptr(x), n, h, w, c, ld, _ptr(y), c, _stream())
+    return y
+
+
+def maxpool2_bwd(x, gy):
+    n, h, w, c, ld = _nhwc(x)
+    gx = torch.empty(n, h, w, c, dtype=torch.bfloat16, device=x.device)
+    lib.call("pai_maxpool2_bwd", _ptr(x), n, h, w, c, ld, _ptr(gy), _nhwc(gy)[4], _ptr(gx), c, _stream())
+    return gx
+
+
+def upsample2_fwd(x, out=None):
+    n, h, w, c, ld = _nhwc(x)
+    if out is None:
+        out = torch.empty(n, 2 * h, 2 * w, c, dtype=torch.bfloat16, device=x.device)
+    lib.call("pai_upsample2_fwd", _ptr(x), n, h, w, c, ld, _ptr(out), _nhwc(out)[4], _stream())
+    return out
+
+
+def upsample2_bwd(gy):
+    n, h2, w2, c, ld = _nhwc(gy)
+    gx = torch.empty(n, h2 // 2, w2 // 2, c, dtype=torch.bfloat16, device=gy.device)
+    lib.call("pai_upsample2_bwd", _ptr(gy), n, h2 // 2, w2 // 2, c, ld, _ptr(gx), c, _stream())
+    return gx
+
+
+def add_act(a, b, act=ACT_NONE, slope=0.2, out=None):
+    m, c, lda = _mat(a)
+    ldb = _mat(b)[2] if b is not None else 0
+    if out is None:
+        out = torch.empty(*a.shape, dtype=torch.bfloat16, device=a.device)
+    lib.call("pai_add_act", _ptr(a), lda, _ptr(b), ldb, m, c, act, float(slope), _ptr(out), _mat(out)[2], _stream())
+    return out
+
+
+def scale_rows_fwd(x, s, act=ACT_NONE, out=None):
+    m, c, ld = _mat(x)
+    if out is None:
+        out = torch.empty(*x.shape, dtype=torch.bfloat16, device=x.device)
+    lib.call("pai_scale_rows_fwd", _ptr(x), ld, _ptr(s), m, c, act, _ptr(out), _mat(out)[2], _stream())
+    return out
+
+
+def scale_rows_bwd(x, s, g, act=ACT_NONE):
+    m, c, ld = _mat(x)
+    gx = torch.empty(*x.shape, dtype=torch.bfloat16, device=x.device)
+    gs = torch.empty(s.shape, dtype=torch.float32, device=x.device)
+    lib.call("pai_scale_rows_bwd", _ptr(x), ld, _ptr(s), _ptr(g), _mat(g)[2], m, c, act, _ptr(gx), c, _ptr(gs), _stream())
+    return gx, gs
+
+
+def conv_plane_to_wide(plane, w, bias, k, pad, act=ACT_NONE, slope=0.2, flip=False, out=None):
+    """plane fp32 ``[n, h, w]``, w fp32 ``[c, k*k]`` -> NHWC bf16 ``[n, h, w, c]``."""
+    n, h, wd = plane.shape
+    c = w.shape[0]
+    if out is None:
+        out = torch.empty(n, h, wd, c, dtype=torch.bfloat16, device=plane.device)
+    lib.call("pai_conv_plane_to_wide", _ptr(plane), n, h, wd, k, pad, int(flip), _ptr(w), _ptr(bias), c, act, float(slope),
+             _ptr(out), _nhwc(out)[4], _stream())
+    return out
+
+
+def conv_wide_to_plane(x, w, bias, k, pad, act=ACT_NONE):
+    """NHWC bf16 ``[n, h, w, c]``, w fp32 ``[k*k, c]`` -> fp32 plane ``[n, h, w]``."""
+    n, h, wd, c, ld = _nhwc(x)
+    out = torch.empty(n, h, wd, dtype=torch.float32, device=x.device)
+    lib.call("pai_conv_wide_to_plane", _ptr(x), n, h, wd, c, ld, k, pad, _ptr(w), _ptr(bias), act, _ptr(out), _stream())
+    return out
+
+
+def conv_plane_wide_wgrad(plane, wide, k, pad, flip=False):
+    """-> fp32 ``[c, k*k]`` = sum over pixels of ``wide[p, c] * plane[p + off_t]``."""
+    n, h, wd, c, ld = _nhwc(wide)
+    dw = torch.zeros(c, k * k, dtype=torch.float32, device=wide.device)
+    lib.call("pai_conv_plane_wide_wgrad", _ptr(plane), _ptr(wide), ld, n, h, wd, c, k, pad, int(flip), _ptr(dw), _stream())
+    return dw
+
+
+def gconv4_3x3_fprop(x, w, bias=None):
+    """Grouped 3x3 conv, 4 channels per group: x NHWC bf16, w fp32 ``[c, 9, 4]``."""
+    n, h, wd, c, ld = _nhwc(x)
+    y = torch.empty(n, h, wd, c, dtype=torch.bfloat16, device=x.device)
+    lib.call("pai_gconv4_3x3_fprop", _ptr(x), n, h, wd, c, ld, _ptr(w), _ptr(bias), _ptr(y), c, _stream())
+    return y
+
+
+def gconv4_3x3_wgrad(x, gy):
+    n, h, wd, c, ld = _nhwc(x)
+    dw = torch.zeros(c, 9, 4, dtype=torch.float32, device=x.device)
+    lib.call("pai_gconv4_3x3_wgrad", _ptr(x), ld, _ptr(gy), _nhwc(gy)[4], n, h, wd, c, _ptr(dw), _stream())
+    return dw
