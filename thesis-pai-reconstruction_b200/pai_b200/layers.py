@@ -21,31 +21,62 @@ def _need(flag_list, i):
 
 
 # ------------------------------------------------------------------------------------------ convolutions
+def _pad64(c):
+    return 64 * ((c + 63) // 64)
+
+
+def _pack_c1_f_padded(w):    # rows padded to a multiple of 64 so the padded output can be a GEMM K dimension
+    cout, cin = w.shape[0], w.shape[1]
+    out = torch.zeros(_pad64(cout), cin, dtype=torch.bfloat16, device=w.device)
+    out[:cout].copy_(w.reshape(cout, cin))
+    return out
+
+
+def _pack_c1_d_padded(w):    # [cin, pad64(cout)]
+    cout, cin = w.shape[0], w.shape[1]
+    out = torch.zeros(ops.padded_cout(cin), _pad64(cout), dtype=torch.bfloat16, device=w.device)
+    out[:cin, :cout].copy_(w.reshape(cout, cin).t())
+    return out
+
+
 class _Conv1x1(torch.autograd.Function):
-    """nn.Conv2d(cin, cout, 1) / nn.Linear on the tensor-core pointwise GEMM (cin, cout multiples of 64)."""
+    """nn.Conv2d(cin, cout, 1) / nn.Linear on the tensor-core pointwise GEMM.  cin must be a multiple of 64; a
+    cout that is not (the 32-channel attention gate) is computed in a zero-padded 64-channel buffer."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
         cout = weight.shape[0]
-        wp = _packs.get("c1_f", weight, ops.pack_conv1x1_weight)
-        y = ops.pointwise_gemm(x, wp, cout, bias=None if bias is None else bias.detach())
+        cp = _pad64(cout)
+        wp = _packs.get("c1_f", weight, _pack_c1_f_padded)
+        b = None
+        if bias is not None:
+            b = bias.detach()
+            if cp != cout:
+                b = torch.cat([b, b.new_zeros(cp - cout)])
+        y = ops.pointwise_gemm(x, wp, cp, bias=b)
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        return y
+        return y if cp == cout else y[..., :cout]
 
     @staticmethod
     def backward(ctx, gy):
         x, weight = ctx.saved_tensors
-        gy = gy.contiguous()
         cout, cin = weight.shape[0], weight.shape[1]
+        cp = _pad64(cout)
+        if cp != cout:
+            full = torch.zeros(*gy.shape[:-1], cp, dtype=torch.bfloat16, device=gy.device)
+            full[..., :cout].copy_(gy)
+            gy = full
+        else:
+            gy = gy.contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            wt = _packs.get("c1_d", weight, ops.pack_conv1x1_weight_t)
+            wt = _packs.get("c1_d", weight, _pack_c1_d_padded)
             gx = ops.pointwise_gemm(gy, wt, cin)
         if ctx.needs_input_grad[1]:
-            gw = ops.pointwise_wgrad(gy, x).view(weight.shape)
+            gw = ops.pointwise_wgrad(gy, x)[:cout].reshape(weight.shape)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = ops.colsum(gy).clone()
+            gb = ops.colsum(gy)[:cout].clone()
         return gx, gw, gb
 
 
@@ -166,16 +197,149 @@ class _WideToPlane(torch.autograd.Function):
         return gx, gw, gb, None
 
 
+class _Conv4x4s2(torch.autograd.Function):
+    """nn.Conv2d(cin, cout, 4, 2, 1) (models/pix2pix.py:63-69) on the implicit-GEMM kernel; the packs share the
+    fused engine's cache tags, so FusedAdam rewrites them in the optimizer step."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        from . import engine
+        y = ops.conv4x4_fprop(x, engine._fprop_pack(weight), weight.shape[0], stride=2,
+                              bias=None if bias is None else bias.detach())
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        from . import engine
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        cout, cin = weight.shape[0], weight.shape[1]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = ops.convT4x4s2_fprop(gy, engine._dgrad_pack(weight), cin)
+        if ctx.needs_input_grad[1]:
+            gw = ops.conv4x4_wgrad(x, gy, stride=2).permute(1, 2, 0).reshape(cout, cin, 4, 4)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = ops.colsum(gy).clone()
+        return gx, gw, gb
+
+
+class _ConvT4x4s2(torch.autograd.Function):
+    """nn.ConvTranspose2d(cin, cout, 4, 2, 1) (models/pix2pix.py:99-105), 4 sub-pixel phases."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        from . import engine
+        y = ops.convT4x4s2_fprop(x, engine._fpropT_pack(weight), weight.shape[1],
+                                 bias=None if bias is None else bias.detach())
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        from . import engine
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        cin, cout = weight.shape[0], weight.shape[1]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = ops.conv4x4_fprop(gy, engine._dgradT_pack(weight), cin, stride=2)
+        if ctx.needs_input_grad[1]:
+            gw = ops.convT4x4s2_wgrad(x, gy).permute(1, 2, 0).reshape(cin, cout, 4, 4)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = ops.colsum(gy).clone()
+        return gx, gw, gb
+
+
+class _Conv4x4s2In(torch.autograd.Function):
+    """nn.Conv2d(1, c, 4, 2, 1) on the fp32 input plane: im2col of the plane + one pointwise GEMM."""
+
+    @staticmethod
+    def forward(ctx, plane, weight, bias):
+        from . import engine
+        n, h, w = plane.shape
+        xcol = ops.im2col4x4([plane], h // 2, w // 2, stride=2)
+        y = ops.pointwise_gemm(xcol, engine._thin_in_pack(weight), weight.shape[0],
+                               bias=None if bias is None else bias.detach())
+        ctx.save_for_backward(xcol)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (xcol,) = ctx.saved_tensors
+        gy = gy.contiguous()
+        c = gy.shape[-1]
+        gw = ops.pointwise_wgrad(gy, xcol)[:, :16].reshape(c, 1, 4, 4)
+        gb = ops.colsum(gy).clone() if ctx.has_bias else None
+        return None, gw, gb
+
+
+class _ConvT4x4s2Out(torch.autograd.Function):
+    """nn.ConvTranspose2d(c, 1, 4, 2, 1) + Tanh -> fp32 plane: 16 per-tap partial products per input pixel
+    (one GEMM over the wide input) + col2im with bias and Tanh."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        from . import engine
+        part = ops.pointwise_gemm(x, engine._thin_out_fprop_pack(weight), 16, out_f32=True)
+        y = ops.col2im4x4s2(part, None if bias is None else bias.detach(), ACT_TANH)
+        ctx.save_for_backward(x, weight, y)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import engine
+        x, weight, y = ctx.saved_tensors
+        n, h2, w2 = y.shape
+        g_pre = (g.float() * (1.0 - y * y)).contiguous()
+        cin = weight.shape[0]
+        gcol = ops.im2col4x4([g_pre], h2 // 2, w2 // 2, stride=2)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = ops.pointwise_gemm(gcol, engine._thin_out_dgrad_pack(weight), cin)
+        if ctx.needs_input_grad[1]:
+            gw = ops.pointwise_wgrad(x, gcol)[:, :16].reshape(cin, 1, 4, 4)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g_pre.sum().reshape(1)
+        return gx, gw, gb
+
+
+def conv4x4s2(x, mod: nn.Conv2d):
+    if x.dim() == 3:
+        if mod.in_channels != 1:
+            raise RuntimeError("pai_b200: the B200 path takes 1-channel (grayscale PAI) inputs; no fallback exists")
+        return _Conv4x4s2In.apply(x, mod.weight, mod.bias)
+    if mod.in_channels % 64 or mod.out_channels % 64:
+        raise RuntimeError(f"pai_b200: channel counts must be multiples of 64 ({mod})")
+    return _Conv4x4s2.apply(x, mod.weight, mod.bias)
+
+
+def convT4x4s2(x, mod: nn.ConvTranspose2d):
+    if mod.in_channels % 64 or mod.out_channels % 64:
+        raise RuntimeError(f"pai_b200: channel counts must be multiples of 64 ({mod})")
+    return _ConvT4x4s2.apply(x, mod.weight, mod.bias)
+
+
+def convT4x4s2_out_tanh(x, mod: nn.ConvTranspose2d):
+    if mod.out_channels != 1:
+        raise RuntimeError("pai_b200: the B200 path produces 1-channel outputs; no fallback exists")
+    return _ConvT4x4s2Out.apply(x, mod.weight, mod.bias)
+
+
 def conv2d(x, mod: nn.Conv2d):
     """Dispatch of an ``nn.Conv2d`` parameter holder onto the kernels (NHWC bf16 in / out)."""
     k, cin, cout, groups = mod.kernel_size[0], mod.in_channels, mod.out_channels, mod.groups
     if mod.stride != (1, 1) or mod.padding != (k // 2, k // 2) or mod.dilation != (1, 1):
         raise RuntimeError(f"pai_b200: unsupported convolution geometry {mod}")
-    if groups == 1 and cin % 64 == 0 and cout % 64 == 0:
-        if k == 1:
-            return _Conv1x1.apply(x, mod.weight, mod.bias)
-        if k == 3:
-            return _Conv3x3.apply(x, mod.weight, mod.bias)
+    if groups == 1 and cin % 64 == 0 and k == 1 and cout % 8 == 0:
+        return _Conv1x1.apply(x, mod.weight, mod.bias)
+    if groups == 1 and cin % 64 == 0 and cout % 64 == 0 and k == 3:
+        return _Conv3x3.apply(x, mod.weight, mod.bias)
     if k == 3 and groups > 1 and cin == cout and cin // groups == 4:
         return _GroupedConv3x3.apply(x, mod.weight, mod.bias)
     raise RuntimeError(f"pai_b200: no B200 kernel for {mod} (channel counts must be multiples of 64, or the "
