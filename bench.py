@@ -44,6 +44,18 @@ def synthetic_pairs(n, seed, device="cpu"):
     return x.to(device), target.to(device)
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -151,7 +163,7 @@ def run_reference_arm(args):
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -318,11 +330,17 @@ def run_ours(args):
                 "value": rate, "unit": "images/s", "cores": threads, "kind": "port",
                 "sample": f"3 GAN training steps of batch 8 (BASELINE.json configs[0]) after 1 warm-up, "
                           f"{sec:.2f} s/step, torch CPU fp32 with {threads} threads on {cores} cpus"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     dp.barrier()
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else a library prints there (NCCL's version banner under
+    # NCCL_DEBUG) goes to stderr; the line itself is written to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
