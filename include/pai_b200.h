@@ -231,6 +231,31 @@ int pai_gconv4_3x3_fprop(const void* x, int n, int h, int w, int c, int ldx, con
 int pai_gconv4_3x3_wgrad(const void* x, int ldx, const void* gy, int ldg, int n, int h, int w, int c, float* dw,
                          void* stream);
 
+int pai_subsample2(const void* x, int n, int h, int w, int c, int ldx, void* y, int ldy, int scatter, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ViT bottleneck of the Trans U-Net (models/trans_unet.py:120-175): nn.LayerNorm, and
+ * nn.TransformerEncoderLayer(d, 8 heads, dim_feedforward=2048, activation="gelu") (post-norm).  Linear layers are
+ * pai_pointwise_gemm / pai_pointwise_wgrad.  Tokens are rows of a dense [m, d] bf16 matrix.
+ *   pai_layernorm_fwd/bwd  y = (x - mean)/sqrt(var + eps) * gamma + beta over the last dimension; mean / rstd [m] fp32
+ *                          are saved for the backward, which also yields dgamma / dbeta (fp32 [d])
+ *   pai_gelu_fwd/bwd       exact (erf) GELU
+ *   pai_attn_fwd/bwd       multi-head self-attention core over the SEQUENCE axis of qkv [s*b, 3*heads*head_dim]
+ *                          (row = s_idx*b + b_idx; the reference's missing batch_first makes s = images of the batch,
+ *                          b = patches): probs [b*heads, s, s] fp32 = softmax(Q K^T / sqrt(head_dim)),
+ *                          out [s*b, heads*head_dim] = probs V; the backward needs an fp32 work buffer like probs.
+ *   pai_subsample2         y[n,a,b,:] = x[n,2a,2b,:] (scatter = 0) or its adjoint into a zeroed y (scatter = 1)
+ */
+int pai_layernorm_fwd(const void* x, long long m, int d, const float* gamma, const float* beta, float eps, void* y,
+                      float* mean, float* rstd, void* stream);
+int pai_layernorm_bwd(const void* x, const void* g, long long m, int d, const float* gamma, const float* mean,
+                      const float* rstd, void* dx, float* dgamma, float* dbeta, void* stream);
+int pai_gelu_fwd(const void* x, long long n, void* y, void* stream);
+int pai_gelu_bwd(const void* x, const void* g, long long n, void* dx, void* stream);
+int pai_attn_fwd(const void* qkv, int s, int b, int heads, int head_dim, float* probs, void* out, void* stream);
+int pai_attn_bwd(const void* qkv, const void* dout, int s, int b, int heads, int head_dim, const float* probs,
+                 float* ds_work, void* dqkv, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -148,6 +148,28 @@ upsample2_bwd_kernel(const __nv_bfloat16* __restrict__ gy, int n, int h, int w, 
     }
 }
 
+// stride-2 subsampling (the 1x1 stride-2 projection of the Trans U-Net encoder, trans_unet.py:208-216):
+// y[n,a,b,:] = x[n,2a,2b,:]; backward scatters into a zeroed tensor.
+__global__ void __launch_bounds__(kLyThreads)
+subsample2_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int c, int ldx, __nv_bfloat16* __restrict__ y,
+                  int ldy, int scatter) {
+    const int cv = c >> 3, oh = h >> 1, ow = w >> 1;
+    const long long total = (long long)n * oh * ow * cv;
+    for (long long i = (long long)blockIdx.x * kLyThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kLyThreads) {
+        const int vec = (int)(i % cv);
+        long long r = i / cv;
+        const int ox = (int)(r % ow);
+        r /= ow;
+        const int oy = (int)(r % oh);
+        const int b = (int)(r / oh);
+        const long long fine = (((long long)b * h + 2 * oy) * w + 2 * ox), coarse = (((long long)b * oh + oy) * ow + ox);
+        if (!scatter)   // x fine -> y coarse
+            *reinterpret_cast<uint4*>(y + coarse * ldy + vec * 8) = *reinterpret_cast<const uint4*>(x + fine * ldx + vec * 8);
+        else            // x coarse (gradient) -> y fine (pre-zeroed)
+            *reinterpret_cast<uint4*>(y + fine * ldy + vec * 8) = *reinterpret_cast<const uint4*>(x + coarse * ldx + vec * 8);
+    }
+}
+
 // out = act(a + b) (b nullable) over [m, c]
 __global__ void __launch_bounds__(kLyThreads)
 add_act_kernel(const __nv_bfloat16* __restrict__ a, int lda, const __nv_bfloat16* __restrict__ b, int ldb, long long m,
@@ -465,6 +487,14 @@ int pai_upsample2_bwd(const void* gy, int n, int h, int w, int c, int ldgy, void
     PAI_REQUIRE(v8_ok(c, gy, ldgy) && v8_ok(c, gx, ldgx), "pai_upsample2_bwd: bad channels / alignment");
     upsample2_bwd_kernel<<<ly_grid((long long)n * h * w * (c / 8)), kLyThreads, 0, (cudaStream_t)stream>>>(
         (const bf16*)gy, n, h, w, c, ldgy, (bf16*)gx, ldgx);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int pai_subsample2(const void* x, int n, int h, int w, int c, int ldx, void* y, int ldy, int scatter, void* stream) {
+    PAI_REQUIRE(x && y && n > 0 && h % 2 == 0 && w % 2 == 0, "pai_subsample2: null pointer or odd size");
+    PAI_REQUIRE(v8_ok(c, x, ldx) && v8_ok(c, y, ldy), "pai_subsample2: bad channels / alignment");
+    subsample2_kernel<<<ly_grid((long long)n * (h / 2) * (w / 2) * (c / 8)), kLyThreads, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, n, h, w, c, ldx, (bf16*)y, ldy, scatter);
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -181,7 +181,7 @@ int pai_adam_multi(int count, float* const* params, const float* const* grads, f
             if (t.n[i] > max_n) max_n = t.n[i];
         }
         int bx = (max_n + 255) / 256;
-        if (bx > 64) bx = 64;
+        if (bx > 148 * 8) bx = 148 * 8;
         adam_multi_kernel<<<dim3(bx, t.count), 256, 0, (cudaStream_t)stream>>>(t, hy);
         PAI_CUDA_OK(cudaGetLastError());
     }

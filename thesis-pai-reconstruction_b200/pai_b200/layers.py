@@ -362,17 +362,23 @@ def conv_out(x, mod: nn.Conv2d, act=ACT_NONE):
 
 # ------------------------------------------------------------------------------------------ BatchNorm (+activation)
 class _BatchNormAct(torch.autograd.Function):
+    """BatchNorm2d (+ activation) over the first ``c = num_features`` channels of ``raw``; a wider ``raw`` is a
+    zero-padded 64-channel carrier (Trans U-Net bottlenecks of 16 / 32 channels) whose tail stays zero."""
+
     @staticmethod
     def forward(ctx, raw, weight, bias, mod, act):
         training = mod.training or mod.running_mean is None
-        m, c, _ = ops._mat(raw)
-        sums = ops.bn_stats(raw) if training else None
+        c, cfull = weight.shape[0], raw.shape[-1]
+        rv = raw if c == cfull else raw[..., :c]
+        m = raw.numel() // cfull
+        sums = ops.bn_stats(rv) if training else None
         ss = ops.bn_finalize(sums, m, c, weight.detach(), bias.detach(), mod.running_mean, mod.running_var,
                              training=training, eps=mod.eps, momentum=mod.momentum if mod.momentum is not None else 0.1)
         if training and mod.num_batches_tracked is not None:
             mod.num_batches_tracked.add_(1)
-        out = torch.empty(*raw.shape, dtype=torch.bfloat16, device=raw.device)
-        ops.bn_apply_act(raw, ss, out, act)
+        alloc = torch.empty if c == cfull else torch.zeros
+        out = alloc(*raw.shape, dtype=torch.bfloat16, device=raw.device)
+        ops.bn_apply_act(rv, ss, out if c == cfull else out[..., :c], act)
         ctx.save_for_backward(raw, ss, weight)
         ctx.act, ctx.training = act, training
         return out
@@ -381,12 +387,14 @@ class _BatchNormAct(torch.autograd.Function):
     def backward(ctx, g):
         raw, ss, weight = ctx.saved_tensors
         g = g.contiguous()
-        c = raw.shape[-1]
+        c, cfull = weight.shape[0], raw.shape[-1]
         if not ctx.training:
             raise RuntimeError("pai_b200: backward through eval-mode BatchNorm is not implemented")
-        sums = ops.bn_bwd_reduce(raw, ss, g, ctx.act)
-        d_raw = torch.empty(*raw.shape, dtype=torch.bfloat16, device=raw.device)
-        ops.bn_bwd_apply(raw, ss, g, ctx.act, None, ACT_NONE, sums, weight.detach(), d_raw)
+        rv, gv = (raw, g) if c == cfull else (raw[..., :c], g[..., :c])
+        sums = ops.bn_bwd_reduce(rv, ss, gv, ctx.act)
+        alloc = torch.empty if c == cfull else torch.zeros
+        d_raw = alloc(*raw.shape, dtype=torch.bfloat16, device=raw.device)
+        ops.bn_bwd_apply(rv, ss, gv, ctx.act, None, ACT_NONE, sums, weight.detach(), d_raw if c == cfull else d_raw[..., :c])
         return d_raw, sums[c:], sums[:c], None, None
 
 
@@ -494,6 +502,172 @@ def dropout2d(x, mod):
         return x
     raise RuntimeError("pai_b200: train-mode Dropout2d with p > 0 is not implemented on the B200 path "
                        "(main.py's default --dropout is 0.0); no fallback exists")
+
+
+# ------------------------------------------------------------------------------------------ Trans U-Net pieces
+def _pack_p1_f(w, cin_p):
+    cout, cin = w.shape[0], w.shape[1]
+    out = torch.zeros(_pad64(cout), cin_p, dtype=torch.bfloat16, device=w.device)
+    out[:cout, :cin].copy_(w.reshape(cout, cin))
+    return out
+
+
+def _pack_p1_d(w, cin_p):
+    cout, cin = w.shape[0], w.shape[1]
+    out = torch.zeros(cin_p, _pad64(cout), dtype=torch.bfloat16, device=w.device)
+    out[:cin, :cout].copy_(w.reshape(cout, cin).t())
+    return out
+
+
+class _Conv1x1Padded(torch.autograd.Function):
+    """Bias-free 1x1 convolution between zero-padded 64-channel carriers: x ``[..., pad64(cin)]`` ->
+    ``[..., pad64(cout)]`` (trans_unet.py:188-205 bottleneck projections with 16 / 32 channels)."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        cin_p = x.shape[-1]
+        wp = _packs.get(f"p1_f{cin_p}", weight, lambda w: _pack_p1_f(w, cin_p))
+        y = ops.pointwise_gemm(x, wp, wp.shape[0])
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        cout, cin, cin_p = weight.shape[0], weight.shape[1], x.shape[-1]
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            wt = _packs.get(f"p1_d{cin_p}", weight, lambda w: _pack_p1_d(w, cin_p))
+            gx = ops.pointwise_gemm(gy, wt, cin_p)
+        if ctx.needs_input_grad[1]:
+            gw = ops.pointwise_wgrad(gy, x)[:cout, :cin].reshape(weight.shape)
+        return gx, gw
+
+
+def _w3_as_4x4(w, cin_p):
+    """[cout, cin, 3, 3] -> zero-padded [pad64(cout), cin_p, 4, 4]: a 3x3 stride-2 pad-1 convolution reads input
+    2*o - 1 + k, exactly taps 0..2 of the 4x4 stride-2 pad-1 convolution."""
+    cout, cin = w.shape[0], w.shape[1]
+    out = torch.zeros(_pad64(cout), cin_p, 4, 4, dtype=torch.float32, device=w.device)
+    out[:cout, :cin, :3, :3].copy_(w)
+    return out
+
+
+class _Conv3x3s2Padded(torch.autograd.Function):
+    """Bias-free nn.Conv2d(c, c, 3, stride=2, padding=1) between zero-padded 64-channel carriers, run on the 4x4
+    stride-2 implicit-GEMM kernels with a zero 4th kernel row / column (trans_unet.py:191-199)."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        cin_p = x.shape[-1]
+        wp = _packs.get(f"c3s2_f{cin_p}", weight, lambda w: ops.pack_conv_weight(_w3_as_4x4(w, cin_p)))
+        y = ops.conv4x4_fprop(x, wp, wp.shape[0], stride=2)
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        cout, cin, cin_p = weight.shape[0], weight.shape[1], x.shape[-1]
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            wd = _packs.get(f"c3s2_d{cin_p}", weight, lambda w: ops.pack_convT_weight(_w3_as_4x4(w, cin_p)))
+            gx = ops.convT4x4s2_fprop(gy, wd, cin_p)
+        if ctx.needs_input_grad[1]:
+            dw = ops.conv4x4_wgrad(x, gy, stride=2)                      # [16, cout_p, cin_p]
+            gw = dw.view(4, 4, dw.shape[1], dw.shape[2])[:3, :3, :cout, :cin].permute(2, 3, 0, 1).contiguous()
+        return gx, gw
+
+
+class _Subsample2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.subsample2(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.subsample2(g.contiguous(), scatter=True)
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        y, mean, rstd = ops.layernorm_fwd(x, weight.detach(), bias.detach(), eps)
+        ctx.save_for_backward(x, weight, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight, mean, rstd = ctx.saved_tensors
+        dx, dgamma, dbeta = ops.layernorm_bwd(x, g.contiguous(), weight.detach(), mean, rstd)
+        return dx, dgamma, dbeta, None
+
+
+class _Gelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.gelu_fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return ops.gelu_bwd(x, g.contiguous())
+
+
+class _Attention(torch.autograd.Function):
+    """softmax(Q K^T / sqrt(hd)) V per head over the sequence axis of ``qkv [S*B, 3E]``."""
+
+    @staticmethod
+    def forward(ctx, qkv, s, b, heads):
+        out, probs = ops.attn_fwd(qkv, s, b, heads)
+        ctx.save_for_backward(qkv, probs)
+        ctx.dims = (s, b, heads)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        qkv, probs = ctx.saved_tensors
+        s, b, heads = ctx.dims
+        return ops.attn_bwd(qkv, g.contiguous(), probs, s, b, heads), None, None, None
+
+
+def conv1x1_padded(x, mod: nn.Conv2d):
+    if mod.bias is not None or mod.kernel_size != (1, 1) or mod.groups != 1 or x.shape[-1] != _pad64(mod.in_channels):
+        raise RuntimeError(f"pai_b200: unexpected bottleneck projection {mod}")
+    return _Conv1x1Padded.apply(x, mod.weight)
+
+
+def conv3x3s2_padded(x, mod: nn.Conv2d):
+    if (mod.bias is not None or mod.kernel_size != (3, 3) or mod.stride != (2, 2) or mod.padding != (1, 1)
+            or mod.groups != 1 or x.shape[-1] != _pad64(mod.in_channels)):
+        raise RuntimeError(f"pai_b200: unexpected strided bottleneck convolution {mod}")
+    return _Conv3x3s2Padded.apply(x, mod.weight)
+
+
+def subsample2(x):
+    return _Subsample2.apply(x)
+
+
+def linear(x2d, weight, bias):
+    """nn.Linear on the tensor-core pointwise GEMM; x2d is a dense [m, in] bf16 matrix."""
+    if weight.shape[1] % 64 or weight.shape[0] % 8:
+        raise RuntimeError(f"pai_b200: Linear {tuple(weight.shape)} needs in % 64 == 0 and out % 8 == 0")
+    return _Conv1x1.apply(x2d, weight, bias)
+
+
+def layernorm(x2d, mod: nn.LayerNorm):
+    return _LayerNorm.apply(x2d, mod.weight, mod.bias, mod.eps)
+
+
+def gelu(x2d):
+    return _Gelu.apply(x2d)
+
+
+def attention(qkv2d, s, b, heads):
+    return _Attention.apply(qkv2d, s, b, heads)
 
 
 def to_plane(x: torch.Tensor) -> torch.Tensor:

@@ -467,3 +467,64 @@ def gconv4_3x3_wgrad(x, gy):
     dw = torch.zeros(c, 9, 4, dtype=torch.float32, device=x.device)
     lib.call("pai_gconv4_3x3_wgrad", _ptr(x), ld, _ptr(gy), _nhwc(gy)[4], n, h, wd, c, _ptr(dw), _stream())
     return dw
+
+
+# ------------------------------------------------------------------------------------------ Trans U-Net (ViT bottleneck)
+def subsample2(x, scatter=False):
+    n, h, w, c, ld = _nhwc(x)
+    if not scatter:
+        y = torch.empty(n, h // 2, w // 2, c, dtype=torch.bfloat16, device=x.device)
+        lib.call("pai_subsample2", _ptr(x), n, h, w, c, ld, _ptr(y), c, 0, _stream())
+    else:            # x is the coarse gradient [n, h, w, c]; result is the fine [n, 2h, 2w, c]
+        y = torch.zeros(n, 2 * h, 2 * w, c, dtype=torch.bfloat16, device=x.device)
+        lib.call("pai_subsample2", _ptr(x), n, 2 * h, 2 * w, c, ld, _ptr(y), c, 1, _stream())
+    return y
+
+
+def layernorm_fwd(x, gamma, beta, eps):
+    m, d = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(m, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(m, dtype=torch.float32, device=x.device)
+    lib.call("pai_layernorm_fwd", _ptr(x), m, d, _ptr(gamma), _ptr(beta), float(eps), _ptr(y), _ptr(mean), _ptr(rstd),
+             _stream())
+    return y, mean, rstd
+
+
+def layernorm_bwd(x, g, gamma, mean, rstd):
+    m, d = x.shape
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(d, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(d, dtype=torch.float32, device=x.device)
+    lib.call("pai_layernorm_bwd", _ptr(x), _ptr(g), m, d, _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(dgamma),
+             _ptr(dbeta), _stream(), kernels=2)
+    return dx, dgamma, dbeta
+
+
+def gelu_fwd(x):
+    y = torch.empty_like(x)
+    lib.call("pai_gelu_fwd", _ptr(x), x.numel(), _ptr(y), _stream())
+    return y
+
+
+def gelu_bwd(x, g):
+    dx = torch.empty_like(x)
+    lib.call("pai_gelu_bwd", _ptr(x), _ptr(g), x.numel(), _ptr(dx), _stream())
+    return dx
+
+
+def attn_fwd(qkv, s, b, heads):
+    e = qkv.shape[1] // 3
+    probs = torch.empty(b * heads, s, s, dtype=torch.float32, device=qkv.device)
+    out = torch.empty(s * b, e, dtype=torch.bfloat16, device=qkv.device)
+    lib.call("pai_attn_fwd", _ptr(qkv), s, b, heads, e // heads, _ptr(probs), _ptr(out), _stream())
+    return out, probs
+
+
+def attn_bwd(qkv, dout, probs, s, b, heads):
+    e = qkv.shape[1] // 3
+    work = torch.empty_like(probs)
+    dqkv = torch.empty_like(qkv)
+    lib.call("pai_attn_bwd", _ptr(qkv), _ptr(dout), s, b, heads, e // heads, _ptr(probs), _ptr(work), _ptr(dqkv), _stream(),
+             kernels=2)
+    return dqkv
