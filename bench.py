@@ -204,6 +204,49 @@ def ssim_sweep_roofline(device, peaks):
             "algorithmic_bytes_per_pair": 524288, "traffic": None}
 
 
+def variant_rates(device):
+    """BASELINE.json configs[2..3]: one training step (forward, loss, backward, FusedAdam) of the other U-Net families
+    through the same drop-in API, synthetic 1x256x256 pairs, device-timed images/s.  Reported next to the headline
+    metric; not part of `value`."""
+    from models.attention_unet import AttentionUnetGAN
+    from models.res_unet import ResUnetGAN
+    from models.trans_unet import TransUnetGAN
+    cases = {
+        "res_unet_next_ssim_b32": (lambda: ResUnetGAN(in_channels=1, out_channels=1, res_type="next", dropout=0.0,
+                                                      loss_type="ssim"), 32),
+        "attention_unet_ssim_b64": (lambda: AttentionUnetGAN(in_channels=1, out_channels=1, dropout=0.0,
+                                                             loss_type="ssim"), 64),
+        "trans_unet_ssim_b64": (lambda: TransUnetGAN(in_channels=1, out_channels=1, channel_mults=(1, 2, 2, 4, 4),
+                                                     patch_size=4, dropout=0.0, loss_type="ssim"), 64),
+    }
+    out = {}
+    for name, (ctor, batch) in cases.items():
+        try:
+            torch.manual_seed(0)
+            m = ctor().to(device).train()
+            x, t = synthetic_pairs(batch, seed=4242)
+            x, t = x.to(device), t.to(device)
+            for i in range(3):
+                m.training_step((x, t), i)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            steps = 5
+            e0.record()
+            for i in range(steps):
+                m.training_step((x, t), i)
+                m.logged.clear()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"images_per_s": batch / (ms * 1e-3), "ms_per_step": ms, "batch": batch,
+                         "params": sum(p.numel() for p in m.parameters())}
+            del m, x, t
+            torch.cuda.empty_cache()
+        except Exception as ex:  # pragma: no cover
+            out[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+    return out
+
+
 def run_ours(args):
     from pai_b200 import dp, lib, ops
     rank, local, world = dp.init_from_env()
@@ -324,6 +367,8 @@ def run_ours(args):
             line["ssim_roofline"] = ssim_sweep_roofline(dev, peaks)
         except Exception as ex:  # pragma: no cover
             line["ssim_roofline"] = {"error": str(ex)}
+        if world == 1 and not args.no_variants:
+            line["variants"] = variant_rates(dev)
         if world == 1 and not args.no_cpu_baseline:
             rate, sec, cores, threads = cpu_reference_step_rate(steps=3, warmup=1, batch=8)
             line["cpu_baseline"] = {
@@ -348,6 +393,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step (BASELINE.json: 64)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the Res / Attention / Trans U-Net step rates")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -119,12 +119,14 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tile = p.n_tile;
+    const bool fused = p.fused_phases != 0;
     const uint32_t a_bytes = 128 * 128;
     const uint32_t b_bytes = (uint32_t)n_tile * 128;
-    const uint32_t stage_bytes = a_bytes + b_bytes;
+    const uint32_t stage_bytes = a_bytes + (fused ? 4 : 1) * b_bytes;
     const int stages = p.stages;
-    const int num_kb = p.ntaps * p.kc_per_tap;
-    const uint32_t acc_cols = tmem_cols_for(n_tile);
+    const int num_kb = (fused ? 9 : p.ntaps) * p.kc_per_tap;
+    const int acc_n = fused ? 4 * n_tile : n_tile;          // accumulator columns per tile
+    const uint32_t acc_cols = tmem_cols_for(acc_n);
     const int total_tiles = p.n_tiles * p.m_tiles * p.phases * p.splitk;
 
     if (warp == 0 && lane == 0) {
@@ -149,7 +151,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     const uint32_t tmem_base = ps.tmem_base;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -163,16 +165,28 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 const int col0 = nt * n_tile;
                 const int kb_end = num_kb * (ks + 1) / p.splitk;
                 for (int kb = num_kb * ks / p.splitk; kb < kb_end; ++kb) {
-                    const int tap = kb / p.kc_per_tap;
+                    const int tap = kb / p.kc_per_tap;          // fused: box index 0..8
                     const int kc = kb - tap * p.kc_per_tap;
-                    const int ti = phase_idx * p.ntaps + tap;
                     mbar_wait(&ps.empty[stage], phase ^ 1);
                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
                     uint8_t* sb = sa + a_bytes;
-                    mbar_expect_tx(&ps.full[stage], stage_bytes);
-                    tma_load_5d(sa, &tm_a, &ps.full[stage], p.tap_c[ti] + kc * 64, w0 + p.tap_w[ti], p.tap_p[ti],
-                                h0 + p.tap_h[ti], n0);
-                    tma_load_2d(sb, &tm_b, &ps.full[stage], kb * 64, phase_idx * p.b_rows_per_phase + col0);
+                    if (fused) {
+                        int nu = 0;
+                        while (nu < 4 && p.box_users[tap][nu] >= 0) ++nu;
+                        mbar_expect_tx(&ps.full[stage], a_bytes + nu * b_bytes);
+                        tma_load_5d(sa, &tm_a, &ps.full[stage], kc * 64, w0 + p.box_w[tap], 0, h0 + p.box_h[tap], n0);
+                        for (int u = 0; u < nu; ++u) {
+                            const int pt = p.box_users[tap][u], ph = pt >> 2, tp = pt & 3;
+                            tma_load_2d(sb + u * b_bytes, &tm_b, &ps.full[stage], (tp * p.kc_per_tap + kc) * 64,
+                                        ph * p.b_rows_per_phase);
+                        }
+                    } else {
+                        const int ti = phase_idx * p.ntaps + tap;
+                        mbar_expect_tx(&ps.full[stage], stage_bytes);
+                        tma_load_5d(sa, &tm_a, &ps.full[stage], p.tap_c[ti] + kc * 64, w0 + p.tap_w[ti], p.tap_p[ti],
+                                    h0 + p.tap_h[ti], n0);
+                        tma_load_2d(sb, &tm_b, &ps.full[stage], kb * 64, phase_idx * p.b_rows_per_phase + col0);
+                    }
                     if (++stage == stages) {
                         stage = 0;
                         phase ^= 1;
@@ -181,7 +195,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(128, n_tile, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
@@ -194,15 +208,33 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 const uint32_t tmem_d = tmem_base + a * acc_cols;
                 const int ks = t - p.fd_splitk.quot(t) * p.splitk;
                 const int kb_begin = num_kb * ks / p.splitk, kb_end = num_kb * (ks + 1) / p.splitk;
+                uint32_t started = 0;      // fused: phases whose accumulator already holds a partial sum
                 for (int kb = kb_begin; kb < kb_end; ++kb) {
                     mbar_wait(&ps.full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
                     const uint32_t sb = sa + a_bytes;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        umma_bf16_ss(tmem_d, umma_desc_kmajor_sw128(sa + k * 32), umma_desc_kmajor_sw128(sb + k * 32),
-                                     idesc, (kb != kb_begin) || (k != 0));
+                    // descriptors: the 14-bit start-address field counts 16-byte units, so stepping K by 16
+                    // elements (32 B) or moving to the next B tile is a plain add on the base descriptor (the
+                    // single issuing thread is the bottleneck of the narrow-N layers: keep its chain short)
+                    const uint64_t da0 = umma_desc_kmajor_sw128(sa), db0 = umma_desc_kmajor_sw128(sb);
+                    if (fused) {
+                        const int box = kb / p.kc_per_tap;
+                        for (int u = 0; u < 4 && p.box_users[box][u] >= 0; ++u) {
+                            const int ph = p.box_users[box][u] >> 2;
+                            const uint64_t dbu = db0 + (uint64_t)u * (b_bytes >> 4);
+                            const uint32_t td = tmem_d + ph * n_tile;
+                            umma_bf16_ss(td, da0, dbu, idesc, (started >> ph) & 1);
+                            umma_bf16_acc(td, da0 + 2, dbu + 2, idesc);
+                            umma_bf16_acc(td, da0 + 4, dbu + 4, idesc);
+                            umma_bf16_acc(td, da0 + 6, dbu + 6, idesc);
+                            started |= 1u << ph;
+                        }
+                    } else {
+                        umma_bf16_ss(tmem_d, da0, db0, idesc, kb != kb_begin);
+                        umma_bf16_acc(tmem_d, da0 + 2, db0 + 2, idesc);
+                        umma_bf16_acc(tmem_d, da0 + 4, db0 + 4, idesc);
+                        umma_bf16_acc(tmem_d, da0 + 6, db0 + 6, idesc);
                     }
                     umma_commit(&ps.empty[stage]);
                     if (++stage == stages) {
@@ -246,12 +278,16 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             const bool all_vec = __all_sync(0xffffffffu, vec_ok || !row_ok);
             const bool fast = !p.out_f32 && all_vec && (n_tile & 63) == 0 && col0 + n_tile <= p.cout &&
                               (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+            // (the fused-phase mode is only launched when this holds: cout == n_tile == 64, bf16 output)
             if (fast) {
                 // ---- coalesced path: 64 channels of 32 rows are transposed through a swizzled smem tile so
                 // that 8 lanes write one full 128-byte row segment (4 rows per store instruction)
                 uint4* tile = stage_buf[warp - 4];
                 int item = 0;
-                for (int c = 0; c < n_tile; c += 64) {
+                for (int c = 0; c < acc_n; c += 64) {
+                    // fused phases: chunk c is phase c/64 of the same 64 output channels
+                    const long long coff = fused ? p.out_phase_off[c >> 6] : 0;
+                    const int oc = fused ? 0 : c;
                     for (int which = 0; which < n_out; ++which, ++item) {
                         if ((item & 1) != half) continue;
                         uint32_t v[64];
@@ -262,7 +298,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(which == 0 ? p.out : p.out2);
                         const int act = which == 0 ? p.act : p.act2;
                         const long long my_off = which == 0 ? off : off2;
-                        const float* bias_c = p.bias != nullptr ? p.bias + col0 + c : nullptr;
+                        const float* bias_c = p.bias != nullptr ? p.bias + col0 + oc : nullptr;
                         // activation / bias dispatch hoisted out of the 64-element loop
                         if (act == PAI_ACT_LEAKY)
                             bias_act_pack<PAI_ACT_LEAKY>(v, bias_c, p.slope, tile, lane);
@@ -279,7 +315,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                             const uint4 val = tile[row * 8 + (ch ^ (row & 7))];
                             const long long roff = __shfl_sync(0xffffffffu, my_off, row);
                             const int rok = __shfl_sync(0xffffffffu, (int)row_ok, row);
-                            if (rok) *reinterpret_cast<uint4*>(dst + roff + c + ch * 8) = val;
+                            if (rok) *reinterpret_cast<uint4*>(dst + roff + coff + oc + ch * 8) = val;
                         }
                         __syncwarp();
                     }
@@ -393,7 +429,7 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_consta
     const uint32_t tmem_base = ps.tmem_base;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (long long u = u_begin; u < u_end; ++u) {
@@ -423,7 +459,7 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(128, n_cols, 1, 1);
             int stage = 0;
             uint32_t phase = 0;
@@ -440,13 +476,14 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_consta
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
                     const uint32_t sb = sa + a_bytes;
-                    for (int a = 0; a < mb; ++a) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {  // 16 pixels (= 16 rows of 128 B) per MMA
-                            umma_bf16_ss(tmem_base + a * 256,
-                                         umma_desc_mnmajor_sw128(sa + a * 2 * blk_bytes + k * 2048, blk_bytes),
-                                         umma_desc_mnmajor_sw128(sb + k * 2048, blk_bytes), idesc, !(first && k == 0));
-                        }
+                    const uint64_t db0 = umma_desc_mnmajor_sw128(sb, blk_bytes);
+                    for (int a = 0; a < mb; ++a) {     // 16 pixels (= 16 rows of 128 B = 128 16-byte units) per MMA
+                        const uint64_t da0 = umma_desc_mnmajor_sw128(sa + a * 2 * blk_bytes, blk_bytes);
+                        const uint32_t td = tmem_base + a * 256;
+                        umma_bf16_ss(td, da0, db0, idesc, !first);
+                        umma_bf16_acc(td, da0 + 128, db0 + 128, idesc);
+                        umma_bf16_acc(td, da0 + 256, db0 + 256, idesc);
+                        umma_bf16_acc(td, da0 + 384, db0 + 384, idesc);
                     }
                     first = false;
                     umma_commit(&ps.empty[stage]);
@@ -517,7 +554,7 @@ static int pick_stages(size_t stage_bytes, size_t budget) {
 
 int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFpropParams p, int m_tiles,
                        int n_tiles, int phases, cudaStream_t stream) {
-    const size_t stage_bytes = 128 * 128 + (size_t)p.n_tile * 128;
+    const size_t stage_bytes = 128 * 128 + (size_t)(p.fused_phases ? 4 : 1) * p.n_tile * 128;
     p.stages = pick_stages(stage_bytes, 192 * 1024);
     p.m_tiles = m_tiles, p.n_tiles = n_tiles, p.phases = phases;
     const size_t smem = stage_bytes * p.stages + 1024;

@@ -2,6 +2,7 @@
 // tap tables for the implicit-GEMM kernels in igemm.cu.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <cudaTypedefs.h>
@@ -244,6 +245,26 @@ int pai_convT4x4s2_fprop(const void* x, int n, int h, int w, int cin, int x_ld, 
     p.out_sn = 4LL * h * w * ld, p.out_sh = 2 * wo * ld, p.out_sw = 2LL * ld;
     for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px) p.out_phase_off[py * 2 + px] = (py * wo + px) * ld;
+    // phase fusion for the 64-channel layers (dec6, the data gradients of enc1 / D1): the activation tile is the
+    // L2-bound operand there, and 9 boxes per channel block instead of 16 feed all four phases
+    const bool fuse = p.splitk == 1 && cout == 64 && cout_pad == 64 && n_tile == 64 && !y_f32 && y_ld % 8 == 0 &&
+                      aligned16(y) && (bias == nullptr || aligned16(bias)) && getenv("PAI_NO_PHASE_FUSION") == nullptr;
+    if (fuse) {
+        p.fused_phases = 1;
+        for (int bx = 0; bx < 9; ++bx) {
+            const int dy = bx / 3 - 1, dx = bx % 3 - 1;
+            p.box_h[bx] = dy, p.box_w[bx] = dx;
+            int nu = 0;
+            for (int py = 0; py < 2; ++py)
+                for (int ty = 0; ty < 2; ++ty)
+                    for (int px = 0; px < 2; ++px)
+                        for (int tx = 0; tx < 2; ++tx)
+                            if (kTd[py][ty] == dy && kTd[px][tx] == dx) p.box_users[bx][nu++] = (py * 2 + px) * 4 + ty * 2 + tx;
+            for (; nu < 4; ++nu) p.box_users[bx][nu] = -1;
+        }
+        p.bias = bias, p.act = act, p.slope = slope, p.out_f32 = 0, p.out = y;
+        return launch_igemm_fprop(tm_a, tm_b, p, m_tiles, 1, 1, (cudaStream_t)stream);
+    }
     if (p.splitk > 1) {
         p.out_f32 = 1, p.accumulate = 1, p.out = splitk_ws;
         int rc2 = launch_igemm_fprop(tm_a, tm_b, p, m_tiles, cout_pad / n_tile, 4, (cudaStream_t)stream);

@@ -37,6 +37,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a converged warp; the compiler then issues the single-thread uniform-datapath instructions (UTCHMMA,
+// UTMALDG, UTCBAR) directly instead of wrapping each in an elect-and-retry loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -119,6 +133,17 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, u
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Same with the accumulate flag fixed to 1 (no predicate set-up on the issuing thread).
+__device__ __forceinline__ void umma_bf16_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.eq.b32 p, 0, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc)
         : "memory");
 }
 // Arrives on `bar` once every previously issued tcgen05.mma of this thread has completed.
