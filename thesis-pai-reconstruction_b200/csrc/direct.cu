@@ -345,7 +345,10 @@ int pai_smallc_conv_wgrad(const void* a, int lda, int c, const float* plane0, co
     PAI_REQUIRE((long long)n * oh * ow < (1LL << 30), "pai_smallc_conv_wgrad: tensor too large");
     const int ppb = kDcThreads / (cv * 4);
     long long blocks = ((long long)n * oh * ow + ppb - 1) / ppb;
-    if (blocks > 148 * 6) blocks = 148 * 6;
+    // every block ends with (threads per pixel) * 32 * cin atomics: wide layers (c = 512: one pixel per block
+    // iteration) get one block per SM, narrow ones a few waves
+    const long long cap = ppb == 1 ? 148 : 148 * 6;
+    if (blocks > cap) blocks = cap;
     cudaStream_t st = (cudaStream_t)stream;
     smallc_wgrad_kernel<<<(int)blocks, kDcThreads, smem, st>>>((const __nv_bfloat16*)a, lda, plane0, plane1, g, dw);
     PAI_CUDA_OK(cudaGetLastError());
