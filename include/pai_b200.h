@@ -256,6 +256,25 @@ int pai_attn_fwd(const void* qkv, int s, int b, int heads, int head_dim, float* 
 int pai_attn_bwd(const void* qkv, const void* dout, int s, int b, int heads, int head_dim, const float* probs,
                  float* ds_work, void* dqkv, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * fp32 check path (north star: "1e-5 with the fp32 accumulate check path").  Slow, exact twins of the tensor-core
+ * layers on fp32 NCHW tensors in the reference's own layouts: one thread per output element, fp32 FMA accumulation,
+ * no bf16 rounding.  Forward only; used by tests through pai_b200.engine.check_path(), never by training / bench.
+ *   pai_check_conv2d_f32     nn.Conv2d (transposed = 0, weight [cout,cin,k,k]) or nn.ConvTranspose2d (transposed = 1,
+ *                            weight [cin,cout,k,k]) with square kernel k, stride, zero padding pad; pre_act is the
+ *                            activation the reference applies in front of the conv (models/pix2pix.py:62,98,
+ *                            models/wrapper.py:205), evaluated on load;  y [n,cout,ho,wo]
+ *   pai_check_batchnorm_f32  nn.BatchNorm2d over [n,c,hw]; training = batch statistics (+ running-stat update,
+ *                            unbiased variance), eval = running statistics
+ *   pai_check_act_f32        elementwise PAI_ACT_* (the final Tanh, models/pix2pix.py:195)
+ */
+int pai_check_conv2d_f32(const float* x, int n, int cin, int h, int w, const float* wt, int cout, int k, int stride,
+                         int pad, const float* bias, int pre_act, float slope, int transposed, float* y, void* stream);
+int pai_check_batchnorm_f32(const float* x, int n, int c, int hw, const float* gamma, const float* beta,
+                            float* running_mean, float* running_var, int training, float eps, float momentum, float* y,
+                            void* stream);
+int pai_check_act_f32(const float* x, long long count, int act, float slope, float* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,90 @@
+"""North-star clause "generator outputs within 1e-2 max-abs at bf16 (1e-5 with the fp32 accumulate check path)":
+the same drop-in modules, run through the exact fp32 kernels of csrc/check_f32.cu (``engine.check_path()``), against
+the fixtures of the UNMODIFIED reference (tests/golden/pix2pix_ref.npz, fp32 on CPU) and the CPU oracle port.
+
+Tolerance: 1e-5 max-abs on outputs in (-1, 1) / on PatchGAN logits, written below.  Train-mode BatchNorm divides by
+the standard deviation of as few as N*4 values (enc6) and amplifies fp32 rounding, so the train-mode bound is 1e-4
+max-abs with a 1e-5 mean-abs bound; the running statistics (0.1 x batch statistics of activations of order 1 whose
+means nearly cancel) must match to 1e-4 relative + 1e-5 absolute."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pix2pix_port as port
+
+pytestmark = pytest.mark.gpu
+
+
+def _build(seed=0):
+    from models.pix2pix import Pix2Pix
+    from models.utils import init_weights
+    from models.wrapper import Discriminator
+    torch.manual_seed(seed)
+    m = Pix2Pix(in_channels=1, out_channels=1, dropout=0.0, loss_type="gan")
+    m.discriminator = Discriminator(in_channels=1)
+    m.discriminator.apply(init_weights)
+    return m.cuda()
+
+
+@pytest.fixture(scope="module")
+def gz(golden_dir):
+    return np.load(os.path.join(golden_dir, "pix2pix_ref.npz"))
+
+
+def test_eval_forward_fp32_check_path_1e5(gz):
+    from pai_b200 import engine, lib
+    m = _build().eval()
+    x, target = port.synthetic_pairs(2, seed=1234)
+    before = lib.launches
+    with engine.check_path():
+        y = m(x.cuda())
+        logits = m.discriminator(x.cuda(), target.cuda())
+    assert lib.launches > before                       # ran on the library's kernels
+    assert y.shape == (2, 1, 256, 256) and y.dtype == torch.float32 and not y.requires_grad
+    d = np.abs(y.cpu()[:, :, ::4, ::4].numpy() - gz["gen_eval_sub"])
+    assert d.max() < 1e-5, d.max()
+    dl = np.abs(logits.cpu().numpy() - gz["disc_logits"])
+    assert dl.max() < 1e-5, dl.max()
+    # and the bf16 tensor-core path on the same weights stays within the north star's 1e-2 of the check path
+    with torch.no_grad():
+        yb = m(x.cuda())
+    assert float((yb - y).abs().max()) < 1e-2
+
+
+def test_train_forward_fp32_check_path(gz):
+    from pai_b200 import engine
+    m = _build().train()
+    sd0 = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    x, _ = port.synthetic_pairs(2, seed=1234)
+    with engine.check_path():
+        y = m(x.cuda())
+    d = np.abs(y.cpu()[:, :, ::4, ::4].numpy() - gz["gen_train_sub"])
+    assert d.max() < 1e-4 and d.mean() < 1e-5, (d.max(), d.mean())
+    # running statistics advanced exactly like the reference's BatchNorm (oracle port on the same weights)
+    tr = port.OracleTrainer(sd0, "gan")
+    with torch.no_grad():
+        port.unet_forward(tr.sd, x, training=True)
+    for k, v in m.state_dict().items():
+        if k.startswith("unet.") and (k.endswith("running_mean") or k.endswith("running_var")):
+            assert torch.allclose(v.cpu(), tr.sd[k], rtol=1e-4, atol=1e-5), k
+        if k.startswith("unet.") and k.endswith("num_batches_tracked"):
+            assert int(v) == int(tr.sd[k]) == 1
+
+
+@pytest.mark.parametrize("n", [1, 3])
+def test_check_path_against_oracle_port_other_seeds(n):
+    from pai_b200 import engine
+    m = _build(seed=5).eval()
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    x, target = port.synthetic_pairs(n, seed=70 + n)
+    tr = port.OracleTrainer(sd, "gan")
+    with torch.no_grad():
+        yo = port.unet_forward(tr.sd, x, training=False)
+        lo = port.disc_forward(tr.sd, x, target)
+    with engine.check_path():
+        y = m(x.cuda())
+        lg = m.discriminator(x.cuda(), target.cuda())
+    assert float((y.cpu() - yo).abs().max()) < 1e-5
+    assert float((lg.cpu() - lo).abs().max()) < 1e-5

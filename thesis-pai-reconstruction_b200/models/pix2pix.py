@@ -103,4 +103,6 @@ class Unet(nn.Module):
             raise RuntimeError("pai_b200: train-mode Dropout2d (dropout > 0) has no B200 kernel yet; the "
                                "benchmark configuration and main.py's default use dropout=0.0")
         spec = self._engine_spec()
+        if engine.check_path_enabled():
+            return engine.unet_forward_check(spec, x, self.training)
         return engine.UnetFunction.apply(spec, self.training, x, *spec.params())

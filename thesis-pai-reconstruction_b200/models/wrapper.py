@@ -165,4 +165,6 @@ class Discriminator(nn.Module):
 
     def forward(self, x, y):
         spec = self._engine_spec()
+        if engine.check_path_enabled():
+            return engine.disc_forward_check(spec, x, y)
         return engine.DiscFunction.apply(spec, x, y, *spec.params())

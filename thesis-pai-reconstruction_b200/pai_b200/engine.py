@@ -147,6 +147,75 @@ def _batchnorm(raw, bn: BNState, training: bool):
     return ss
 
 
+# ------------------------------------------------------------------------------------------ fp32 check path
+_check = False
+
+
+class check_path:
+    """``with engine.check_path(): y = model(x)`` runs the drop-in generator / PatchGAN forward on the exact fp32
+    kernels of csrc/check_f32.cu (fp32 NCHW tensors, fp32 FMA accumulation, no bf16 operands) instead of the
+    tcgen05 path -- the north star's "1e-5 with the fp32 accumulate check path".  Forward only (no autograd graph)."""
+
+    def __enter__(self):
+        global _check
+        self.prev, _check = _check, True
+        return self
+
+    def __exit__(self, *exc):
+        global _check
+        _check = self.prev
+        return False
+
+
+def check_path_enabled() -> bool:
+    return _check
+
+
+def _check_bn(v, bn, training):
+    if bn is None:
+        return v
+    y = ops.check_batchnorm(v, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, training,
+                            eps=BN_EPS, momentum=BN_MOMENTUM)
+    if training:
+        bn.num_batches_tracked.add_(1)
+    return y
+
+
+@torch.no_grad()
+def unet_forward_check(spec: "UnetSpec", x: torch.Tensor, training: bool) -> torch.Tensor:
+    """``Unet.forward`` (models/pix2pix.py:198-216) layer by layer on the fp32 check kernels."""
+    L = spec.levels
+    skips = []
+    v = x.contiguous().float()
+    for i in range(L):
+        conv = spec.enc_convs[i]
+        v = ops.check_conv2d(v, conv.weight.detach(), conv.bias.detach(), pre_act=ACT_NONE if i == 0 else ACT_LEAKY,
+                             slope=SLOPE)
+        v = _check_bn(v, spec.enc_bns[i], training)
+        skips.append(v)
+    for j in range(L):
+        conv = spec.dec_convs[j]
+        if j > 0:
+            v = torch.cat([v, skips[L - 1 - j]], dim=1)            # models/pix2pix.py:212
+        # every DecoderBlock starts with a ReLU; the last decoder is a bare ConvTranspose2d (:185-193)
+        v = ops.check_conv2d(v, conv.weight.detach(), conv.bias.detach(), pre_act=ACT_RELU if j < L - 1 else ACT_NONE,
+                             transposed=True)
+        v = _check_bn(v, spec.dec_bns[j], training)
+    return ops.check_act(v, ACT_TANH)
+
+
+@torch.no_grad()
+def disc_forward_check(spec: "DiscSpec", x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """``Discriminator.forward`` (models/wrapper.py:236-238): conv -> LeakyReLU blocks, bias-free stride-1 head."""
+    v = torch.cat([x.float(), y.float()], dim=1).contiguous()
+    K = len(spec.convs)
+    for k, conv in enumerate(spec.convs):
+        head = k == K - 1
+        v = ops.check_conv2d(v, conv.weight.detach(), None if conv.bias is None else conv.bias.detach(),
+                             stride=1 if head else 2, pad=1, pre_act=ACT_NONE if k == 0 else ACT_LEAKY, slope=SLOPE)
+    return v
+
+
 # ------------------------------------------------------------------------------------------ generator
 class UnetSpec:
     """Shapes + parameter holders of a reference-layout Unet (built by models/pix2pix.py:Unet)."""

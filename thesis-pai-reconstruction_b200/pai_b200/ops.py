@@ -528,3 +528,39 @@ def attn_bwd(qkv, dout, probs, s, b, heads):
     lib.call("pai_attn_bwd", _ptr(qkv), _ptr(dout), s, b, heads, e // heads, _ptr(probs), _ptr(work), _ptr(dqkv), _stream(),
              kernels=2)
     return dqkv
+
+
+# ------------------------------------------------------------------------------------------ fp32 check path
+def check_conv2d(x, w, bias=None, stride=2, pad=1, pre_act=ACT_NONE, slope=0.2, transposed=False):
+    """nn.Conv2d / nn.ConvTranspose2d on fp32 NCHW (csrc/check_f32.cu): exact-arithmetic twin of the igemm layers."""
+    assert x.dtype == torch.float32 and w.dtype == torch.float32 and x.is_cuda
+    x, w = x.contiguous(), w.contiguous()
+    n, cin, h, wd = x.shape
+    k = w.shape[2]
+    cout = w.shape[1] if transposed else w.shape[0]
+    assert w.shape[2] == w.shape[3] and (w.shape[0] if transposed else w.shape[1]) == cin
+    ho = (h - 1) * stride - 2 * pad + k if transposed else (h + 2 * pad - k) // stride + 1
+    wo = (wd - 1) * stride - 2 * pad + k if transposed else (wd + 2 * pad - k) // stride + 1
+    y = torch.empty(n, cout, ho, wo, dtype=torch.float32, device=x.device)
+    b = None if bias is None else bias.contiguous()
+    lib.call("pai_check_conv2d_f32", _ptr(x), n, cin, h, wd, _ptr(w), cout, k, stride, pad, _ptr(b), pre_act, slope,
+             1 if transposed else 0, _ptr(y), _stream())
+    return y
+
+
+def check_batchnorm(x, gamma, beta, running_mean, running_var, training, eps=1e-5, momentum=0.1):
+    assert x.dtype == torch.float32 and x.is_cuda
+    x = x.contiguous()
+    n, c = x.shape[0], x.shape[1]
+    hw = x.numel() // max(n * c, 1)
+    y = torch.empty_like(x)
+    lib.call("pai_check_batchnorm_f32", _ptr(x), n, c, hw, _ptr(gamma), _ptr(beta), _ptr(running_mean), _ptr(running_var),
+             1 if training else 0, eps, momentum, _ptr(y), _stream())
+    return y
+
+
+def check_act(x, act, slope=0.2):
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    lib.call("pai_check_act_f32", _ptr(x), x.numel(), act, slope, _ptr(y), _stream())
+    return y
