@@ -169,3 +169,47 @@ def test_full_size_properties():
     for d in (0, 7, 15):
         band = fm[:, 0, 16 * d + 5:16 * d + 11, 5:251].reshape(8, -1).mean(-1)
         assert float(band.mean()) == pytest.approx(float(rm["depth_ssim"][d, 0]), abs=1e-5)
+
+
+@pytest.mark.parametrize("dtype,denorm,h", [(torch.float32, False, 256), (torch.float32, True, 256),
+                                            (torch.bfloat16, False, 256), (torch.float32, False, 128)])
+def test_streaming_sweep_kernel_against_oracle(dtype, denorm, h):
+    """Large batches of 256-wide images take the persistent warp-specialised streaming kernel
+    (csrc/ssim.cu, namespace stream; n >= 592).  Checked against the torchmetrics restatement on images spread over
+    the CTAs' image sequences (first / second / last image of a CTA, last image overall) and against the
+    row-batched kernel (PAI_SSIM_NO_STREAM) on every image: per-image SSIM, 16 depth bands, squared error."""
+    m = _m()
+    n = 700
+    g = torch.Generator(device="cuda").manual_seed(11)
+    base = torch.rand(n, 1, h, 256, device="cuda", generator=g)
+    # smooth structure so that SSIM is not degenerate: average neighbouring rows
+    base = (base + base.roll(1, 2) + base.roll(1, 3)) / 3
+    pred = (base + 0.05 * torch.randn(n, 1, h, 256, device="cuda", generator=g)).clamp_(0, 1)
+    if denorm:
+        base, pred = 2 * base - 1, 2 * pred - 1
+    base, pred = base.to(dtype), pred.to(dtype)
+    bands = h == 256                      # depth bands need h / 16 > 10 rows
+    s1, e1, b1, _ = m._launch_fwd(pred, base, denorm, bands, False)
+    os.environ["PAI_SSIM_NO_STREAM"] = "1"
+    try:
+        s0, e0, b0, _ = m._launch_fwd(pred, base, denorm, bands, False)
+    finally:
+        del os.environ["PAI_SSIM_NO_STREAM"]
+    torch.cuda.synchronize()
+    win = (h - 10) * 246
+    assert float((s1 - s0).abs().max()) / win < 1e-6                  # same arithmetic, different summation order
+    if bands:
+        assert float((b1 - b0).abs().max()) / ((h // 16 - 10) * 246) < 1e-6
+    assert torch.allclose(e1, e0, rtol=1e-5, atol=1e-6)
+    idx = [0, 1, 147, 148, 149, 295, 296, 591, 592, n - 1]
+    pf, bf = pred[idx].float().cpu(), base[idx].float().cpu()
+    if denorm:
+        pf, bf = port.denormalize(pf), port.denormalize(bf)
+    want = tm.structural_similarity_index_measure(pf, bf, data_range=1.0, reduction="none")
+    assert float((s1[idx].cpu() / win - want).abs().max()) < TOL
+    want_sse = ((pf - bf) ** 2).flatten(1).sum(1)
+    assert torch.allclose(e1[idx].cpu(), want_sse, rtol=1e-4)
+    if bands:
+        want_depth = torch.stack([port.depth_ssim(pf[i:i + 1], bf[i:i + 1])[:, 0] for i in range(len(idx))])
+        got_depth = b1[idx].cpu() / (6 * 246)
+        assert float((got_depth - want_depth).abs().max()) < TOL

@@ -14,6 +14,7 @@
 //   stage C  vertical 11-tap Gaussian, lane <-> column, SSIM formula, warp-shuffle reductions
 // Only sigma_p^2 + sigma_t^2 enters SSIM, so 4 planes are filtered instead of torchmetrics' 5.
 #include <math.h>
+#include <stdlib.h>
 
 #include "pai_common.cuh"
 #include "pai_kernels.h"
@@ -599,6 +600,284 @@ static int launch(const void* pred, const void* target, int n, int h, int band_r
 
 }  // namespace rows
 
+
+// =============================================================================================
+// Streaming forward for large batches of 256-wide images (the report.py sweep, BASELINE.json configs[4]):
+// a persistent, warp-specialised CTA per SM walks whole images as ONE continuous stream of rows.
+//   * producer warp: cp.async.bulk of 8-row granules of pred / target into a 4-granule ring (mbarrier full / empty)
+//   * 8 V warps (thread <-> column): every input row is read from the ring ONCE, its products p^2+t^2, p t are
+//     formed once, and it is scattered into the 11 pending vertical-filter accumulators it contributes to
+//     (registers, 16-slot circular naming, 16-row unrolled loop) -- 22 FFMA2 per pixel, no re-reads, no window
+//     shifting; each completed row goes to a double-buffered smem batch of 8 rows; also the squared error
+//   * 8 H warps (thread <-> (row, run of 8 columns)): horizontal 11-tap filter of the batch, SSIM formula on pixel
+//     pairs, per-image / per-depth-band sums (warp shuffles + one global atomic per warp and sum)
+// V and H warps run concurrently on different batches, so the FMA pipe stays busy across the smem hand-over.
+// Accumulation order per output equals the row-batched kernel above (ascending tap index), results are bit-equal.
+// Interior windows only (rows / columns 5 .. dim-6): what the scalar metrics need.
+namespace stream {
+
+static constexpr int W = 256, GR = 8, NG = 4, NB = 3, VP = 9, VC = W + 10;
+static constexpr int NV = 256, NH = 256, NT = 32 + NV + NH;     // warp 0 producer, warps 1-8 V, warps 9-16 H
+
+using rows::bulk_g2s;
+using rows::mul2;
+using rows::ring_ld;
+using rows::sub2;
+
+// Blocking wait without clock reads: try_wait suspends the thread in hardware for up to the hinted time, so a waiting
+// warp costs (almost) no issue slots of the SM sub-partition it shares with the computing warps.  A pipeline bug still
+// traps instead of hanging the GPU (bounded number of wake-ups).
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (int spins = 0;; ++spins) {
+        uint32_t ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity), "r"(100000u)
+            : "memory");
+        if (ok) return;
+        if (spins > (1 << 22)) __trap();
+    }
+}
+
+template <typename T>
+static constexpr size_t smem_bytes() {
+    return (size_t)2 * NG * GR * W * sizeof(T) + (size_t)NB * VC * VP * sizeof(float4);
+}
+
+template <typename T, bool DENORM>
+__global__ void __launch_bounds__(NT, 1)
+ssim_fwd_stream_kernel(const T* __restrict__ pred, const T* __restrict__ target, int n, int h, int band_rows,
+                       float* __restrict__ ssim_sum, float* __restrict__ band_sum, float* __restrict__ sse,
+                       const Gauss gk) {
+    extern __shared__ __align__(128) uint8_t stream_smem[];
+    T* ring_p = reinterpret_cast<T*>(stream_smem);
+    T* ring_t = ring_p + NG * GR * W;
+    float4* vbuf = reinterpret_cast<float4*>(stream_smem + (size_t)2 * NG * GR * W * sizeof(T));
+    __shared__ uint64_t gfull[NG], gempty[NG], vfull[NB], vempty[NB];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_mine = (n - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // images blockIdx.x + i * gridDim.x
+    if (n_mine <= 0) return;
+    const int gran_per_img = h / GR;
+    const int total_gran = n_mine * gran_per_img;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < NG; ++i) {
+            mbar_init(&gfull[i], 1);
+            mbar_init(&gempty[i], NV / 32);
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            mbar_init(&vfull[i], NV / 32);
+            mbar_init(&vempty[i], NH / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // halo columns of the batches are never written in interior mode: keep them finite
+    for (int i = tid; i < NB * 10 * VP; i += NT) {
+        const int b = i / (10 * VP), r = i - b * 10 * VP, c = r / VP, o = r - c * VP;
+        vbuf[b * VC * VP + (c < 5 ? c : W + c) * VP + o] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+
+    float2 g[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) g[i] = make_float2(gk.g[i], gk.g[i]);
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer warp
+        if (lane == 0) {
+            const uint32_t bytes = (uint32_t)(GR * W * sizeof(T));
+            int img_i = 0, gi = 0;
+            for (int G = 0; G < total_gran; ++G) {
+                const int slot = G & (NG - 1);
+                mbar_wait_sleep(&gempty[slot], ((G / NG) & 1) ^ 1);     // fresh barrier: passes for the first NG
+                const size_t off = ((size_t)(blockIdx.x + (size_t)img_i * gridDim.x) * h + (size_t)gi * GR) * W;
+                mbar_expect_tx(&gfull[slot], 2 * bytes);
+                bulk_g2s(ring_p + slot * GR * W, pred + off, bytes, &gfull[slot]);
+                bulk_g2s(ring_t + slot * GR * W, target + off, bytes, &gfull[slot]);
+                if (++gi == gran_per_img) gi = 0, ++img_i;
+            }
+        }
+    } else if (warp <= NV / 32) {
+        // ------------------------------------------------------------------ V warps: thread <-> column
+        const int x = tid - 32;
+        float2 A[16], Q[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) A[i] = Q[i] = make_float2(0.f, 0.f);
+        float e_acc = 0.f;
+        int G = 0, vb = 0, vpar = 1, r16 = 0, img_i = 0;      // vpar: parity to wait on vempty[vb] (fresh: passes)
+        const int blocks_per_img = h / 16;
+        const int iters = n_mine * blocks_per_img;
+        float4* vcol = vbuf + (x + 5) * VP;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if ((j & 7) == 0) mbar_wait_sleep(&gfull[G & (NG - 1)], (G / NG) & 1);
+                const int s_in = ((G & (NG - 1)) * GR + (j & 7)) * W + x;
+                float p = ring_ld(ring_p + s_in), t = ring_ld(ring_t + s_in);
+                if (DENORM) {
+                    p = denorm(p);
+                    t = denorm(t);
+                }
+                const float2 a = make_float2(p, t);
+                const float2 q = make_float2(fmaf(p, p, t * t), p * t);
+                const float d = p - t;
+                e_acc = fmaf(d, d, e_acc);
+                // input row r contributes g[k] to output row r + 5 - k (k = 0 initialises, k = 10 completes)
+#pragma unroll
+                for (int k = 0; k < 11; ++k) {
+                    const int sl = (j + 5 - k) & 15;
+                    const float2 gw = g[k < 6 ? k : 10 - k];
+                    if (k == 0) {
+                        A[sl] = mul2(a, gw);
+                        Q[sl] = mul2(q, gw);
+                    } else {
+                        A[sl] = fma2(a, gw, A[sl]);
+                        Q[sl] = fma2(q, gw, Q[sl]);
+                    }
+                }
+                const int sl = (j - 5) & 15, ob = (j + 3) & 7;      // completed output row r - 5, its slot in the batch
+                if (it > 0 || j >= 5) {
+                    if (ob == 0) mbar_wait_sleep(&vempty[vb], vpar);
+                    vcol[ob] = make_float4(A[sl].x, A[sl].y, Q[sl].x, Q[sl].y);
+                    if (ob == 7) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&vfull[vb]);
+                        vcol += VC * VP;
+                        if (++vb == NB) vb = 0, vpar ^= 1, vcol -= NB * VC * VP;
+                    }
+                }
+                if ((j & 7) == 7) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&gempty[G & (NG - 1)]);
+                    ++G;
+                }
+            }
+            if (++r16 == blocks_per_img) {          // last row of an image: its squared error is complete
+                r16 = 0;
+                const float e = warp_sum(e_acc);
+                if (lane == 0) atomicAdd(sse + blockIdx.x + (size_t)img_i * gridDim.x, e);
+                e_acc = 0.f;
+                ++img_i;
+            }
+        }
+        // the stream's last batch holds rows h-8 .. h-6 of the last image only: hand it over as it is
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&vfull[vb]);
+    } else {
+        // ------------------------------------------------------------------ H warps: thread <-> (row, 8 columns)
+        const int ht = tid - 32 - NV;
+        const int hrow = ht & 7, run = ht >> 3;
+        const int total_batches = total_gran;       // 8 output rows per batch, h / 8 batches per image
+        float s_acc = 0.f, b_acc = 0.f;
+        int y0 = 0, br0 = 0, band = 0, img_i = 0, hb = 0, hpar = 0;
+        const float4* src = vbuf + (8 * run) * VP + hrow;
+        const float2 one_two = make_float2(1.f, 2.f), c1 = make_float2(1e-4f, 1e-4f), c2 = make_float2(9e-4f, 9e-4f);
+        for (int Bh = 0; Bh < total_batches; ++Bh) {
+            mbar_wait_sleep(&vfull[hb], hpar);
+            float2 a[GR + 10], q[GR + 10];
+#pragma unroll
+            for (int j = 0; j < GR + 10; ++j) {
+                const float4 v = src[j * VP];
+                a[j] = make_float2(v.x, v.y);
+                q[j] = make_float2(v.z, v.w);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&vempty[hb]);     // the batch now lives in registers
+            src += VC * VP;
+            if (++hb == NB) hb = 0, hpar ^= 1, src -= NB * VC * VP;
+            float2 ma[GR], mq[GR];
+            rows::filt11<GR>(a, g, ma);
+            rows::filt11<GR>(q, g, mq);
+            // SSIM on plane pairs: ma = (mu_p, mu_t), mq = (E[p^2 + t^2], E[p t]); u = (mu_p^2 + mu_t^2, mu_p mu_t);
+            // (b1, a1) = u * (1, 2) + c1, (b2, a2) = (mq - u) * (1, 2) + c2, (den, num) = (b1 b2, a1 a2) -- the same
+            // roundings as ssim_terms(), 8 FMA-pipe instructions per pixel and no register shuffling
+            float sv[GR];
+#pragma unroll
+            for (int o = 0; o < GR; ++o) {
+                const float2 sq = mul2(ma[o], ma[o]);
+                const float2 u = make_float2(sq.x + sq.y, ma[o].x * ma[o].y);
+                const float2 ba1 = fma2(u, one_two, c1);
+                const float2 ba2 = fma2(sub2(mq[o], u), one_two, c2);
+                const float2 dn = mul2(ba1, ba2);
+                float inv;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(dn.x));
+                sv[o] = dn.y * inv;
+            }
+            float part = 0.f;
+            if (run == 0) {
+#pragma unroll
+                for (int o = 5; o < GR; ++o) part += sv[o];
+            } else if (run == W / 8 - 1) {
+#pragma unroll
+                for (int o = 0; o < 3; ++o) part += sv[o];
+            } else {
+#pragma unroll
+                for (int o = 0; o < GR; ++o) part += sv[o];
+            }
+            const int y = y0 + hrow;
+            if (y >= 5 && y < h - 5) s_acc += part;
+            if (band_sum != nullptr) {
+                const int br = br0 + hrow;
+                if (br >= 5 && br < band_rows - 5) b_acc += part;
+            }
+            y0 += GR;
+            br0 += GR;
+            if (band_sum != nullptr && br0 == band_rows) {       // band complete (band_rows is a multiple of 8)
+                const float v = warp_sum(b_acc);
+                if (lane == 0) atomicAdd(band_sum + (blockIdx.x + (size_t)img_i * gridDim.x) * 16 + band, v);
+                b_acc = 0.f;
+                br0 = 0;
+                ++band;
+            }
+            if (y0 == h) {
+                const float v = warp_sum(s_acc);
+                if (lane == 0) atomicAdd(ssim_sum + blockIdx.x + (size_t)img_i * gridDim.x, v);
+                s_acc = 0.f;
+                y0 = 0;
+                band = 0;
+                br0 = 0;
+                ++img_i;
+            }
+        }
+    }
+}
+
+template <typename T, bool DENORM>
+static int launch(const void* pred, const void* target, int n, int h, int band_rows, float* ssim_sum, float* band_sum,
+                  float* sse, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        PAI_CUDA_OK(cudaFuncSetAttribute(ssim_fwd_stream_kernel<T, DENORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem_bytes<T>()));
+        attr = true;
+    }
+    int dev = 0, sms = 148;
+    PAI_CUDA_OK(cudaGetDevice(&dev));
+    PAI_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = n < sms ? n : sms;
+    ssim_fwd_stream_kernel<T, DENORM><<<grid, NT, smem_bytes<T>(), st>>>((const T*)pred, (const T*)target, n, h, band_rows,
+                                                                         ssim_sum, band_sum, sse, host_gauss());
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// whole images per CTA: worth it once every SM gets several images
+static bool eligible(int n, int h, int w, int band_rows, const void* full_map) {
+    return w == W && full_map == nullptr && h % 16 == 0 && h >= 32 && (band_rows == 0 || band_rows % GR == 0) &&
+           n >= 4 * 148;
+}
+
+}  // namespace stream
+
 template <typename T, bool DENORM>
 static int fwd_launch(const void* pred, const void* target, int n, int h, int w, int band_rows, float* ssim_sum,
                       float* band_sum, float* sse, float* full_map, cudaStream_t st) {
@@ -659,6 +938,16 @@ int pai_ssim_psnr_fwd(const void* pred, const void* target, int dtype, int n, in
     PAI_CUDA_OK(cudaMemsetAsync(ssim_sum, 0, sizeof(float) * n, st));
     PAI_CUDA_OK(cudaMemsetAsync(sse, 0, sizeof(float) * n, st));
     if (band_sum) PAI_CUDA_OK(cudaMemsetAsync(band_sum, 0, sizeof(float) * 16 * n, st));
+    const bool aligned16 = (reinterpret_cast<uintptr_t>(pred) & 15) == 0 && (reinterpret_cast<uintptr_t>(target) & 15) == 0;
+    // large batches of 256-wide images without the full map (the evaluation sweep): persistent streaming kernel
+    if (aligned16 && stream::eligible(n, h, w, band_rows, full_map) && !getenv("PAI_SSIM_NO_STREAM")) {
+        if (dtype == PAI_DTYPE_F32)
+            return denormalize ? stream::launch<float, true>(pred, target, n, h, band_rows, ssim_sum, band_sum, sse, st)
+                               : stream::launch<float, false>(pred, target, n, h, band_rows, ssim_sum, band_sum, sse, st);
+        return denormalize
+                   ? stream::launch<__nv_bfloat16, true>(pred, target, n, h, band_rows, ssim_sum, band_sum, sse, st)
+                   : stream::launch<__nv_bfloat16, false>(pred, target, n, h, band_rows, ssim_sum, band_sum, sse, st);
+    }
     // 256-wide images (every shape of the reference's pipeline) take the row-streaming kernel
     if (w == rows::W && (reinterpret_cast<uintptr_t>(pred) & 15) == 0 && (reinterpret_cast<uintptr_t>(target) & 15) == 0 &&
         (full_map == nullptr || (reinterpret_cast<uintptr_t>(full_map) & 15) == 0)) {
