@@ -29,6 +29,16 @@ def _worker(rank, world, port, q):
     n = dp.allreduce_gradients(net.parameters())
     dp.barrier()
     mx = dp.allreduce_max(float(rank), torch.device("cpu"))
+    # overlapped exchange used by the fused backward nodes: a large gradient is averaged while "backward" continues,
+    # and allreduce_gradients() afterwards must not average it a second time
+    big = torch.nn.Parameter(torch.zeros(1 << 18))
+    small = torch.nn.Parameter(torch.zeros(5))
+    big.grad = torch.full((1 << 18,), float(rank + 1))
+    small.grad = torch.full((5,), float(10 * (rank + 1)))
+    dp.allreduce_async(big.grad)
+    n2 = dp.allreduce_gradients([big, small])
+    assert float(big.grad[0]) == 1.5 and float(big.grad[-1]) == 1.5, big.grad[:3]
+    assert float(small.grad[0]) == 15.0 and n2 == 5
     q.put((rank, [t.numpy() for t in ref], [g.numpy() for g in local], [p.grad.numpy() for p in net.parameters()], n, mx))
     torch.distributed.destroy_process_group()
 

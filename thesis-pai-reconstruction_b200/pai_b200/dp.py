@@ -36,15 +36,50 @@ def world_size() -> int:
 
 _BIG = 1 << 18      # elements: gradients at least this large are reduced in place, one collective each
 
+_pending = []       # (work, tensor) of the all-reduces started while the backward pass is still running
+_done = set()       # data_ptr of the gradients those collectives already average
+
+
+def active() -> bool:
+    return _enabled and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def allreduce_async(t: torch.Tensor) -> None:
+    """Called by the fused backward nodes (pai_b200.engine) the moment a large weight gradient exists: starts its
+    in-place average over all ranks on NCCL's stream, so the exchange of layer k overlaps the dgrad / wgrad GEMMs of
+    layers k-1, k-2, ... (the bucketed overlap DDP would give main.py:123-135).  ``finish_async`` joins them."""
+    if not active() or t.numel() < _BIG or not t.is_contiguous():
+        return
+    nccl = dist.get_backend() == "nccl"
+    work = dist.all_reduce(t, op=dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM, async_op=True)
+    _pending.append((work, t))
+    _done.add(t.data_ptr())
+
+
+def finish_async() -> None:
+    """Makes the current stream wait for every collective started by ``allreduce_async``."""
+    if not _pending:
+        return
+    nccl = dist.get_backend() == "nccl"
+    world = dist.get_world_size()
+    for work, t in _pending:
+        work.wait()
+        if not nccl:
+            t.div_(world)
+    _pending.clear()
+
 
 def allreduce_gradients(params) -> int:
-    """In-place average of ``p.grad`` over all ranks.  Large gradients (the convolution weights) are averaged
+    """In-place average of ``p.grad`` over all ranks (gradients already averaged during the backward pass by
+    ``allreduce_async`` are skipped).  Large gradients (the convolution weights) are averaged
     in place by their own asynchronous all-reduce -- no flatten / copy-back passes over the 218 MB of generator
     gradients --, the many small ones (biases, BatchNorm affine) share one flat buffer per dtype.  Returns the
     number of elements exchanged (0 when not data-parallel)."""
     if not (_enabled and dist.is_initialized()) or dist.get_world_size() == 1:
         return 0
-    grads = [p.grad for p in params if p.grad is not None]
+    finish_async()
+    grads = [p.grad for p in params if p.grad is not None and p.grad.data_ptr() not in _done]
+    _done.clear()
     if not grads:
         return 0
     world = dist.get_world_size()

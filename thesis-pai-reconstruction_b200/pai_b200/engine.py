@@ -17,7 +17,7 @@ from typing import List, Optional
 
 import torch
 
-from . import ops
+from . import dp, ops
 from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH
 
 BN_EPS, BN_MOMENTUM, SLOPE = 1e-5, 0.1, 0.2
@@ -346,8 +346,9 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
         d_in = s.cat[j] if j > 0 else s.dec_in0
         cin = conv.weight.shape[0]
         dwt = ops.convT4x4s2_wgrad(d_in, d_raw)                                  # [16, cin, co]
-        grads[(1, j)] = (dwt.permute(1, 2, 0).reshape(cin, co, 4, 4), torch.zeros(co, device=dev),
-                         sums[co:], sums[:co])
+        gw = dwt.permute(1, 2, 0).reshape(cin, co, 4, 4)
+        dp.allreduce_async(gw)                    # data-parallel: the exchange overlaps the rest of the backward
+        grads[(1, j)] = (gw, torch.zeros(co, device=dev), sums[co:], sums[:co])
         dcat = ops.conv4x4_fprop(d_raw, _dgradT_pack(conv.weight), cin, stride=2)   # grad w.r.t. decoder input
     # ---- bottleneck encoder L-1: dec_in0 = relu(conv + bias)
     i = L - 1
@@ -355,7 +356,9 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
     d_raw = _bf16(*s.dec_in0.shape, device=dev)
     sums = ops.act_bwd(s.dec_in0, dcat, ACT_RELU, None, ACT_NONE, d_raw)
     dwc = ops.conv4x4_wgrad(s.a_in[i], d_raw, stride=2)                          # [16, co, ci]
-    grads[(0, i)] = (dwc.permute(1, 2, 0).reshape(ch[i], ch[i - 1], 4, 4), sums[:ch[i]].clone())
+    gw = dwc.permute(1, 2, 0).reshape(ch[i], ch[i - 1], 4, 4)
+    dp.allreduce_async(gw)
+    grads[(0, i)] = (gw, sums[:ch[i]].clone())
     d_a = ops.convT4x4s2_fprop(d_raw, _dgrad_pack(conv.weight), ch[i - 1])
     # ---- encoders L-2 .. 1
     for i in range(L - 2, 0, -1):
@@ -367,6 +370,7 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
                          d_raw, slope=SLOPE)
         dwc = ops.conv4x4_wgrad(s.a_in[i], d_raw, stride=2)
         gw = dwc.permute(1, 2, 0).reshape(ch[i], ch[i - 1], 4, 4)
+        dp.allreduce_async(gw)
         if bn is not None:
             grads[(0, i)] = (gw, torch.zeros(ch[i], device=dev), sums[ch[i]:], sums[:ch[i]])
         else:
@@ -383,6 +387,7 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
         out += list(grads[(0, i)])
     for j in range(L):
         out += list(grads[(1, j)])
+    dp.finish_async()
     return out
 
 
@@ -475,6 +480,7 @@ def disc_backward(spec: DiscSpec, s: _Saved, g_logits: torch.Tensor, need_params
             if need_params:
                 dwc = ops.conv4x4_wgrad(s.hs[k - 1], d_pre, stride=2)
                 grads[2 * k] = dwc.permute(1, 2, 0).reshape(ck, s.hs[k - 1].shape[3], 4, 4)
+                dp.allreduce_async(grads[2 * k])
                 grads[2 * k + 1] = sums[:ck].clone()
             dh = ops.convT4x4s2_fprop(d_pre, _dgrad_pack(conv.weight), s.hs[k - 1].shape[3])
         else:
@@ -487,6 +493,7 @@ def disc_backward(spec: DiscSpec, s: _Saved, g_logits: torch.Tensor, need_params
                 h, w = s.px.shape[1], s.px.shape[2]
                 part = ops.pointwise_gemm(d_pre, _thin_in_dgrad_pack(conv.weight, 1), 16, out_f32=True)
                 gy = ops.col2im4x4s2(part).view(n, 1, h, w)
+    dp.finish_async()
     return grads, gy
 
 
