@@ -176,13 +176,18 @@ int pai_col2im4x4s2(const float* p, int ldp, int n, int h, int w, const float* b
  *                          be NULL; pack2 has b_pad rows per phase; padding rows are left untouched)
  *   pai_adam_multi         the same update for `count` small dense tensors in one launch (host arrays of
  *                          device pointers)
+ *   pai_adam_prepare       device-side step counter for CUDA-graph capture of the training step: ++*step and
+ *                          dyn[0..1] = {lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t)} (double arithmetic).  When the
+ *                          `dyn` argument of the two update functions is non-NULL they read these two scalars from
+ *                          the device instead of their step_size / inv_bias_correction2_sqrt arguments.
  */
 int pai_adam_pack_conv4x4(float* w, const float* grad, float* exp_avg, float* exp_avg_sq, int a, int b, float beta1,
                           float beta2, float step_size, float inv_bias_correction2_sqrt, float eps, void* pack1,
-                          void* pack2, int b_pad, void* stream);
+                          void* pack2, int b_pad, const float* dyn, void* stream);
 int pai_adam_multi(int count, float* const* params, const float* const* grads, float* const* exp_avgs,
                    float* const* exp_avg_sqs, const int* numels, float beta1, float beta2, float step_size,
-                   float inv_bias_correction2_sqrt, float eps, void* stream);
+                   float inv_bias_correction2_sqrt, float eps, const float* dyn, void* stream);
+int pai_adam_prepare(int* step, float lr, float beta1, float beta2, float* dyn, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Layers of the Residual / Attention / Trans U-Net variants (models/res_unet.py, attention_unet.py,

@@ -21,6 +21,25 @@ struct AdamHyper {
     float one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_sqrt, eps;
 };
 
+// Bias-correction scalars kept on the device so that a captured CUDA graph of the training step stays valid from one
+// replay to the next: ++*step; dyn = {lr / (1 - b1^t), 1 / sqrt(1 - b2^t)} in double like torch's host code.
+__global__ void adam_prepare_kernel(int* step, float lr, float beta1, float beta2, float* dyn) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const int t = *step + 1;
+        *step = t;
+        dyn[0] = (float)((double)lr / (1.0 - pow((double)beta1, (double)t)));
+        dyn[1] = (float)(1.0 / sqrt(1.0 - pow((double)beta2, (double)t)));
+    }
+}
+
+__device__ __forceinline__ AdamHyper adam_dyn(AdamHyper h, const float* __restrict__ dyn) {
+    if (dyn != nullptr) {
+        h.step_size = __ldg(dyn);
+        h.inv_bc2_sqrt = __ldg(dyn + 1);
+    }
+    return h;
+}
+
 __device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, const AdamHyper& h) {
     m = fmaf(g - m, h.one_minus_b1, m);
     v = fmaf(v, h.b2, h.one_minus_b2 * g * g);
@@ -33,9 +52,10 @@ static constexpr int kTA = 32, kTB = 32, kPackThreads = 256;
 // grid (ceil(B/32), ceil(A/32)); smem: s1[16][32 a][32 b] and s2[16][32 b][32 a] bf16 (2 x 32 KB)
 __global__ void __launch_bounds__(kPackThreads)
 adam_pack_conv4x4_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
-                         float* __restrict__ v, int A, int B, AdamHyper hy, __nv_bfloat16* __restrict__ p1,
-                         __nv_bfloat16* __restrict__ p2, int b_pad) {
+                         float* __restrict__ v, int A, int B, AdamHyper hy0, const float* __restrict__ dyn,
+                         __nv_bfloat16* __restrict__ p1, __nv_bfloat16* __restrict__ p2, int b_pad) {
     extern __shared__ __nv_bfloat16 pk_smem[];
+    const AdamHyper hy = adam_dyn(hy0, dyn);
     __nv_bfloat16* s1 = pk_smem;                       // [tap][a][b]
     __nv_bfloat16* s2 = pk_smem + 16 * kTA * kTB;      // [tap][b][a]
     const int a0 = blockIdx.y * kTA, b0 = blockIdx.x * kTB;
@@ -118,7 +138,8 @@ struct AdamTable {
 };
 
 __global__ void __launch_bounds__(256)
-adam_multi_kernel(const __grid_constant__ AdamTable t, AdamHyper hy) {
+adam_multi_kernel(const __grid_constant__ AdamTable t, AdamHyper hy0, const float* __restrict__ dyn) {
+    const AdamHyper hy = adam_dyn(hy0, dyn);
     for (int k = blockIdx.y; k < t.count; k += gridDim.y) {
         float* p = t.p[k];
         const float* g = t.g[k];
@@ -141,7 +162,7 @@ extern "C" {
 
 int pai_adam_pack_conv4x4(float* w, const float* grad, float* exp_avg, float* exp_avg_sq, int a, int b, float beta1,
                           float beta2, float step_size, float inv_bias_correction2_sqrt, float eps, void* pack1,
-                          void* pack2, int b_pad, void* stream) {
+                          void* pack2, int b_pad, const float* dyn, void* stream) {
     PAI_REQUIRE(w != nullptr && a > 0 && b > 0, "pai_adam_pack_conv4x4: null weight / empty shape");
     PAI_REQUIRE(grad == nullptr || (exp_avg != nullptr && exp_avg_sq != nullptr),
                 "pai_adam_pack_conv4x4: optimizer state missing");
@@ -159,14 +180,21 @@ int pai_adam_pack_conv4x4(float* w, const float* grad, float* exp_avg, float* ex
     AdamHyper hy = {1.f - beta1, beta2, 1.f - beta2, step_size, inv_bias_correction2_sqrt, eps};
     dim3 grid((b + kTB - 1) / kTB, (a + kTA - 1) / kTA);
     adam_pack_conv4x4_kernel<<<grid, kPackThreads, smem, (cudaStream_t)stream>>>(
-        w, grad, exp_avg, exp_avg_sq, a, b, hy, (__nv_bfloat16*)pack1, (__nv_bfloat16*)pack2, b_pad);
+        w, grad, exp_avg, exp_avg_sq, a, b, hy, dyn, (__nv_bfloat16*)pack1, (__nv_bfloat16*)pack2, b_pad);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pai_adam_prepare(int* step, float lr, float beta1, float beta2, float* dyn, void* stream) {
+    PAI_REQUIRE(step != nullptr && dyn != nullptr, "pai_adam_prepare: null pointer");
+    adam_prepare_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step, lr, beta1, beta2, dyn);
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 int pai_adam_multi(int count, float* const* params, const float* const* grads, float* const* exp_avgs,
                    float* const* exp_avg_sqs, const int* numels, float beta1, float beta2, float step_size,
-                   float inv_bias_correction2_sqrt, float eps, void* stream) {
+                   float inv_bias_correction2_sqrt, float eps, const float* dyn, void* stream) {
     PAI_REQUIRE(count >= 0 && (count == 0 || (params && grads && exp_avgs && exp_avg_sqs && numels)),
                 "pai_adam_multi: null table");
     AdamHyper hy = {1.f - beta1, beta2, 1.f - beta2, step_size, inv_bias_correction2_sqrt, eps};
@@ -182,7 +210,7 @@ int pai_adam_multi(int count, float* const* params, const float* const* grads, f
         }
         int bx = (max_n + 255) / 256;
         if (bx > 148 * 8) bx = 148 * 8;
-        adam_multi_kernel<<<dim3(bx, t.count), 256, 0, (cudaStream_t)stream>>>(t, hy);
+        adam_multi_kernel<<<dim3(bx, t.count), 256, 0, (cudaStream_t)stream>>>(t, hy, dyn);
         PAI_CUDA_OK(cudaGetLastError());
     }
     return 0;

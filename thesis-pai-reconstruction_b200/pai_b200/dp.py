@@ -21,6 +21,9 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and not dist.is_initialized():
+        # collectives captured inside the training-step CUDA graph (pai_b200.graph): the NCCL watchdog must not query
+        # events of a capturing stream
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
@@ -47,8 +50,12 @@ def active() -> bool:
 def allreduce_async(t: torch.Tensor) -> None:
     """Called by the fused backward nodes (pai_b200.engine) the moment a large weight gradient exists: starts its
     in-place average over all ranks on NCCL's stream, so the exchange of layer k overlaps the dgrad / wgrad GEMMs of
-    layers k-1, k-2, ... (the bucketed overlap DDP would give main.py:123-135).  ``finish_async`` joins them."""
-    if not active() or t.numel() < _BIG or not t.is_contiguous():
+    layers k-1, k-2, ... (the bucketed overlap DDP would give main.py:123-135).  ``finish_async`` joins them.
+
+    OFF unless PAI_DP_OVERLAP=1: measured on 2 B200s the overlap buys nothing (11.78 ms/step either way) -- the
+    implicit-GEMM kernels are persistent with one statically scheduled CTA per SM, so every SM an NCCL CTA occupies
+    delays its igemm CTA by the collective's duration.  It needs a dynamic (CLC) tile scheduler to pay off."""
+    if not active() or t.numel() < _BIG or not t.is_contiguous() or os.environ.get("PAI_DP_OVERLAP", "0") != "1":
         return
     nccl = dist.get_backend() == "nccl"
     work = dist.all_reduce(t, op=dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM, async_op=True)
@@ -84,14 +91,26 @@ def allreduce_gradients(params) -> int:
         return 0
     world = dist.get_world_size()
     avg = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else None
-    total, works = 0, []
-    small = []
-    for g in grads:
-        if g.numel() >= _BIG and g.is_contiguous():
-            works.append((dist.all_reduce(g, op=avg if avg is not None else dist.ReduceOp.SUM, async_op=True), g))
-            total += g.numel()
+    total = 0
+    big = [g for g in grads if g.numel() >= _BIG and g.is_contiguous()]
+    small = [g for g in grads if not (g.numel() >= _BIG and g.is_contiguous())]
+    # the large gradients (convolution weights, 229 MB for generator + PatchGAN) are averaged in place by ONE grouped
+    # NCCL launch (ncclGroupStart/End around the per-tensor all-reduces) -- no flatten / copy-back passes and no
+    # per-tensor launch latency
+    if big:
+        op = avg if avg is not None else dist.ReduceOp.SUM
+        if avg is not None and hasattr(dist, "_coalescing_manager"):
+            with dist._coalescing_manager(device=big[0].device, async_ops=False):
+                for g in big:
+                    dist.all_reduce(g, op=op)
         else:
-            small.append(g)
+            works = [dist.all_reduce(g, op=op, async_op=True) for g in big]
+            for w in works:
+                w.wait()
+            if avg is None:
+                for g in big:
+                    g.div_(world)
+        total += sum(g.numel() for g in big)
     for dtype in {g.dtype for g in small}:
         group = [g for g in small if g.dtype == dtype]
         flat = torch.cat([g.reshape(-1) for g in group])
@@ -103,10 +122,6 @@ def allreduce_gradients(params) -> int:
             g.copy_(flat[off:off + n].view_as(g))
             off += n
         total += flat.numel()
-    for work, g in works:
-        work.wait()
-        if avg is None:
-            g.div_(world)
     return total
 
 

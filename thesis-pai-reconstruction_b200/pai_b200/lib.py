@@ -76,14 +76,15 @@ SIGNATURES = {
     "pai_attn_fwd": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "pai_attn_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "pai_adam_pack_conv4x4": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float,
-                              c_float, c_void_p, c_void_p, c_int, c_void_p],
+                              c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    "pai_adam_prepare": [c_void_p, c_float, c_float, c_float, c_void_p, c_void_p],
     "pai_check_conv2d_f32": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                              c_float, c_int, c_void_p, c_void_p],
     "pai_check_batchnorm_f32": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
                                 c_float, c_void_p, c_void_p],
     "pai_check_act_f32": [c_void_p, c_ll, c_int, c_float, c_void_p, c_void_p],
     "pai_adam_multi": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float,
-                       c_float, c_void_p],
+                       c_float, c_void_p, c_void_p],
 }
 RESTYPES = {"pai_ssim_bwd_workspace_bytes": (ctypes.c_longlong, [c_int, c_int, c_int])}
 

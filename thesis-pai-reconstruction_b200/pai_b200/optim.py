@@ -27,10 +27,78 @@ def _ptr(t):
 
 
 class FusedAdam(torch.optim.Adam):
+    """``torch.optim.Adam`` stepped by csrc/optim.cu.
+
+    When every parameter of a group receives a gradient at every step (always true for the reference's two
+    optimizers) the step count ``t`` of the group lives ON THE DEVICE (``pai_adam_prepare`` increments it and derives
+    the two bias-correction scalars), so ``step()`` issues no host-dependent kernel argument and the whole training
+    step can be captured in a CUDA graph (pai_b200.graph).  ``state_dict()`` / ``load_state_dict()`` translate between
+    that counter and torch's per-parameter ``state[p]["step"]`` tensors, so checkpoints are interchangeable."""
+
     def _plain(self, group) -> bool:
         return not (group.get("amsgrad") or group.get("weight_decay") or group.get("maximize")
                     or group.get("capturable") or group.get("differentiable")
                     or isinstance(group["lr"], torch.Tensor))
+
+    # ---- device-side step counter ---------------------------------------------------------------------------
+    def _dev_state(self, gi: int, device):
+        store = self.__dict__.setdefault("_pai_dev", {})
+        ent = store.get(gi)
+        if ent is None or ent["step"].device != device:
+            ent = {"step": torch.zeros(1, dtype=torch.int32, device=device),
+                   "dyn": torch.zeros(2, dtype=torch.float32, device=device), "uniform": None}
+            store[gi] = ent
+        return ent
+
+    def _sync_host_steps(self):
+        """Writes the device counters into torch's per-parameter ``step`` tensors."""
+        for gi, ent in self.__dict__.get("_pai_dev", {}).items():
+            if not ent["uniform"]:
+                continue
+            t = float(int(ent["step"].item()))
+            for p in self.param_groups[gi]["params"]:
+                st = self.state.get(p)
+                if st:
+                    st["step"] = torch.tensor(t, dtype=torch.float32)
+
+    def state_dict(self):
+        self._sync_host_steps()
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self.__dict__.pop("_pai_dev", None)          # re-derived from the loaded per-parameter steps at the next step
+
+    def _init_state(self, p):
+        st = self.state[p]
+        if len(st) == 0:
+            st["step"] = torch.tensor(0.0, dtype=torch.float32)
+            st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+        return st
+
+    def _launch(self, items, beta1, beta2, step_size, inv_bc2, eps, dyn, stream):
+        small = []
+        for p, g, st in items:
+            packs = engine.fused_pack_targets(p)
+            if packs is None:
+                p.__dict__.pop("_pai_packs", None)      # thin-layer packs are rebuilt lazily
+                small.append((p, g, st))
+                continue
+            p1, p2, b_pad = packs
+            lib.call("pai_adam_pack_conv4x4", _ptr(p), _ptr(g), _ptr(st["exp_avg"]), _ptr(st["exp_avg_sq"]),
+                     p.shape[0], p.shape[1], beta1, beta2, step_size, inv_bc2, eps, _ptr(p1), _ptr(p2),
+                     b_pad, _ptr(dyn), stream)
+            engine.restamp_packs(p)
+        if small:
+            n = len(small)
+            arr = ctypes.c_void_p * n
+            lib.call("pai_adam_multi", n,
+                     arr(*[p.data_ptr() for p, _, _ in small]), arr(*[g.data_ptr() for _, g, _ in small]),
+                     arr(*[s["exp_avg"].data_ptr() for _, _, s in small]),
+                     arr(*[s["exp_avg_sq"].data_ptr() for _, _, s in small]),
+                     (ctypes.c_int * n)(*[p.numel() for p, _, _ in small]),
+                     beta1, beta2, step_size, inv_bc2, eps, _ptr(dyn), stream, kernels=(n + 47) // 48)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -45,11 +113,14 @@ class FusedAdam(torch.optim.Adam):
             with torch.enable_grad():
                 loss = closure()
         stream = ops._stream()
-        for group in groups:
+        for gi, group in enumerate(groups):
             beta1, beta2 = group["betas"]
             lr, eps = float(group["lr"]), float(group["eps"])
-            by_step = {}
-            for p in group["params"]:
+            params = group["params"]
+            if not params:
+                continue
+            items = []
+            for p in params:
                 g = p.grad
                 if g is None:
                     continue
@@ -57,36 +128,27 @@ class FusedAdam(torch.optim.Adam):
                     raise RuntimeError("Adam does not support sparse gradients, please consider SparseAdam instead")
                 if not g.is_contiguous():
                     g = g.contiguous()
-                st = self.state[p]
-                if len(st) == 0:
-                    st["step"] = torch.tensor(0.0, dtype=torch.float32)
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                items.append((p, g, self._init_state(p)))
+            ent = self._dev_state(gi, params[0].device)
+            if ent["uniform"] is None:
+                # first step of this group (or after load_state_dict): adopt the device counter when all parameters
+                # share one step count and all of them are being stepped
+                steps = {float(st["step"]) for _, _, st in items}
+                ent["uniform"] = len(items) == len(params) and len(steps) == 1
+                if ent["uniform"]:
+                    ent["step"].fill_(int(steps.pop()))
+            if ent["uniform"] and len(items) != len(params):
+                self._sync_host_steps()                  # a parameter skipped this step: per-parameter counts from now on
+                ent["uniform"] = False
+            if ent["uniform"]:
+                lib.call("pai_adam_prepare", _ptr(ent["step"]), lr, beta1, beta2, _ptr(ent["dyn"]), stream)
+                self._launch(items, beta1, beta2, 0.0, 0.0, eps, ent["dyn"], stream)
+                continue
+            by_step = {}
+            for p, g, st in items:
                 st["step"] += 1
-                t = int(st["step"].item()) if st["step"].device.type == "cpu" else int(st["step"])
-                by_step.setdefault(t, []).append((p, g, st))
-            for t, items in by_step.items():
-                step_size = lr / (1.0 - beta1 ** t)
-                inv_bc2 = 1.0 / math.sqrt(1.0 - beta2 ** t)
-                small = []
-                for p, g, st in items:
-                    packs = engine.fused_pack_targets(p)
-                    if packs is None:
-                        p.__dict__.pop("_pai_packs", None)      # thin-layer packs are rebuilt lazily
-                        small.append((p, g, st))
-                        continue
-                    p1, p2, b_pad = packs
-                    lib.call("pai_adam_pack_conv4x4", _ptr(p), _ptr(g), _ptr(st["exp_avg"]), _ptr(st["exp_avg_sq"]),
-                             p.shape[0], p.shape[1], beta1, beta2, step_size, inv_bc2, eps, _ptr(p1), _ptr(p2),
-                             b_pad, stream)
-                    engine.restamp_packs(p)
-                if small:
-                    n = len(small)
-                    arr = ctypes.c_void_p * n
-                    lib.call("pai_adam_multi", n,
-                             arr(*[p.data_ptr() for p, _, _ in small]), arr(*[g.data_ptr() for _, g, _ in small]),
-                             arr(*[s["exp_avg"].data_ptr() for _, _, s in small]),
-                             arr(*[s["exp_avg_sq"].data_ptr() for _, _, s in small]),
-                             (ctypes.c_int * n)(*[p.numel() for p, _, _ in small]),
-                             beta1, beta2, step_size, inv_bc2, eps, stream, kernels=(n + 47) // 48)
+                by_step.setdefault(int(st["step"].item()), []).append((p, g, st))
+            for t, sub in by_step.items():
+                self._launch(sub, beta1, beta2, lr / (1.0 - beta1 ** t), 1.0 / math.sqrt(1.0 - beta2 ** t), eps, None,
+                             stream)
         return loss
