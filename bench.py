@@ -178,12 +178,16 @@ def build_model():
     return m
 
 
-def ssim_sweep_roofline(device, peaks):
+def ssim_sweep_roofline(device, peaks, rank=0, world=1):
     """BASELINE.json's second metric: the SSIM/PSNR/RMSE (+16 depth bands) metric kernel over the report.py
-    sweep (10 000 synthetic 256^2 fp32 pairs, 5.24 GB >> L2), algorithmic 524 288 B per pair."""
-    from pai_b200 import metrics
-    n = 10000
-    g = torch.Generator(device=device).manual_seed(7)
+    sweep (10 000 synthetic 256^2 fp32 pairs, 5.24 GB >> L2), algorithmic 524 288 B per pair.  With N GPUs the pairs
+    are sharded contiguously (no collective on the data path); `sweep_pairs_per_s` is the whole-job rate of the
+    public call metrics.report_metrics(distributed=True), all-gather of the per-image vectors included."""
+    from pai_b200 import dp, metrics
+    total = 10000
+    lo, hi = metrics.shard_bounds(total, rank, world)
+    n = hi - lo
+    g = torch.Generator(device=device).manual_seed(7 + rank)
     base = torch.rand(n, 1, IMG, IMG, device=device, generator=g)
     pred = (base + 0.05 * torch.randn(n, 1, IMG, IMG, device=device, generator=g)).clamp_(0, 1)
     for _ in range(3):
@@ -198,10 +202,25 @@ def ssim_sweep_roofline(device, peaks):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     gbs = n * 524288 / (ms * 1e-3) / 1e9
+    # the public sweep call (per-image SSIM / PSNR / MSE, depth bands, global RMSE; sharded when world > 1)
+    metrics.report_metrics(pred, base, distributed=world > 1)
+    dp.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        r = metrics.report_metrics(pred, base, distributed=world > 1)
+    e1.record()
+    torch.cuda.synchronize()
+    sweep_ms = dp.allreduce_max(e0.elapsed_time(e1) / 3, device)
     del base, pred
-    return {"kernel": "ssim_fwd_rows_kernel<float> (row-streaming, FFMA2 separable passes)", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
+    # traffic: ncu --set full capture of this kernel (profiles/r1_ssim_stream_summary.txt): dram__bytes_read.sum
+    # 1.049 GB for 2000 pairs = 524 680 B / pair, writes negligible -> scaled to this launch
+    return {"kernel": "ssim_fwd_stream_kernel<float> (persistent, warp-specialised: TMA producer / vertical scatter / "
+                      "horizontal filter warps, FFMA2)", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "pairs": n, "ms_per_sweep": ms, "pairs_per_s": n / (ms * 1e-3),
-            "algorithmic_bytes_per_pair": 524288, "traffic": None}
+            "algorithmic_bytes_per_pair": 524288, "traffic": n * 524680,
+            "limit": "FMA pipe (59 FMA-pipe instructions / pixel): 0.39 of HBM peak at most, see profiles/",
+            "sweep_pairs_per_s": total / (sweep_ms * 1e-3), "sweep_ms": sweep_ms, "sweep_ssim_mean": float(r["ssim_mean"])}
 
 
 def variant_rates(device):
@@ -362,7 +381,10 @@ def run_ours(args):
     roofline = {
         "kernel": "igemm_fprop_kernel + igemm_wgrad_kernel (tcgen05 implicit GEMM: conv/convT fprop, dgrad, wgrad)",
         "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-        "peak_kind": f"{peak_kind} bf16_tflops_sustained (kernels timed inside a long step)", "traffic": None,
+        "peak_kind": f"{peak_kind} bf16_tflops_sustained (kernels timed inside a long step)",
+        # DRAM read+write bytes per launch, averaged over the 96 launches of one step: ncu capture in
+        # profiles/r1_igemm_step_traffic.txt (9.998 GB per step)
+        "traffic": 104.1e6,
         "launches_per_step": sum(v[2] for v in kern.values()) / prof_steps,
         "algorithmic_gflop_per_step": tot_f / prof_steps / 1e9,
         "share_of_step": (tot_t / prof_steps) / (ms_step * 1e-3),
@@ -407,11 +429,14 @@ def run_ours(args):
         "roofline": roofline,
     }
 
+    resident.clear()
+    torch.cuda.empty_cache()
+    try:
+        sweep = ssim_sweep_roofline(dev, peaks, rank, world)
+    except Exception as ex:  # pragma: no cover
+        sweep = {"error": f"{type(ex).__name__}: {ex}"[:300]}
     if rank == 0:
-        try:
-            line["ssim_roofline"] = ssim_sweep_roofline(dev, peaks)
-        except Exception as ex:  # pragma: no cover
-            line["ssim_roofline"] = {"error": str(ex)}
+        line["ssim_roofline"] = sweep
         if world == 1 and not args.no_variants:
             line["variants"] = variant_rates(dev)
         if world == 1 and not args.no_cpu_baseline:

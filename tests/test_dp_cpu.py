@@ -76,3 +76,49 @@ def test_single_process_is_a_no_op():
     g = lin.weight.grad.clone()
     assert dp.allreduce_gradients(lin.parameters()) == 0 and torch.equal(g, lin.weight.grad)
     assert dp.world_size() == 1
+
+
+def _sweep_worker(rank, world, port, q):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from pai_b200 import dp, metrics
+    dp.init_from_env(backend="gloo")
+    g = torch.Generator().manual_seed(5)
+    n = 11                                              # ragged: shards of 6 and 5 pairs
+    ssim_all, sse_all, bands_all = torch.rand(n, generator=g), torch.rand(n, generator=g) * 50, torch.rand(n, 16, generator=g)
+    lo, hi = metrics.shard_bounds(n, rank, world)
+    s, e, b = metrics.gather_stats(ssim_all[lo:hi], sse_all[lo:hi], bands_all[lo:hi])
+    got = metrics.finalize_report(s, e, b, 65536)
+    want = metrics.finalize_report(ssim_all, sse_all, bands_all, 65536)
+    ok = all(torch.equal(got[k], want[k]) for k in ("ssim", "psnr", "mse", "ssim_mean", "psnr_mean", "rmse", "depth_ssim"))
+    s2, e2, b2 = metrics.gather_stats(ssim_all[lo:hi], sse_all[lo:hi], None)       # sweep without depth bands
+    ok = ok and b2 is None and torch.equal(s2, ssim_all) and torch.equal(e2, sse_all)
+    q.put((rank, ok, (lo, hi)))
+    torch.distributed.destroy_process_group()
+
+
+def test_sharded_evaluation_sweep_world2():
+    """SURVEY.md 8(e), evaluation sweep: contiguous shards of the pairs per rank, all-gather of the per-image
+    vectors, then exactly the single-process reductions (mean / unbiased std over images, global RMSE)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sweep_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert out[0][1] and out[1][1]
+    assert out[0][2] == (0, 6) and out[1][2] == (6, 11)
+
+
+def test_shard_bounds_cover_everything():
+    from pai_b200 import metrics
+    for n in (0, 1, 7, 10000):
+        for world in (1, 2, 3, 8):
+            cuts = [metrics.shard_bounds(n, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+            assert max(hi - lo for lo, hi in cuts) - min(hi - lo for lo, hi in cuts) <= 1

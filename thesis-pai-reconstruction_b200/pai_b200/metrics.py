@@ -138,17 +138,12 @@ def train_metrics(pred: torch.Tensor, target: torch.Tensor, denormalize: bool = 
 
 
 @torch.no_grad()
-def report_metrics(preds: torch.Tensor, targets: torch.Tensor, chunk: int = 4096, want_maps: bool = False,
-                   want_depth: bool = True):
-    """report.py:72-104,144-146,188-217 in one pass per pair.
-
-    Returns a dict with per-image ``ssim``/``psnr``/``mse`` ``[N]``, ``depth_ssim`` ``[16, 2]`` (mean and
-    unbiased std over images per depth band), ``ssim_mean``, ``psnr_mean``, global ``rmse`` and optionally
-    the full SSIM maps.  ``preds``/``targets`` may live on the host; they are streamed to the GPU in
-    ``chunk``-sized slices."""
+def per_image_stats(preds: torch.Tensor, targets: torch.Tensor, chunk: int = 4096, want_maps: bool = False,
+                    want_depth: bool = True):
+    """One pass of the metric kernel per pair -> per-image sufficient statistics on the GPU:
+    ``ssim [N]``, ``sse [N]`` (squared error over C*H*W), ``bands [N, 16]`` (depth-band SSIMs, or None), ``maps``."""
     _check(preds, targets)
     n, c, h, w = preds.shape
-    out_dev = preds.device
     ssims, sses, bands, maps = [], [], [], []
     for p, t in zip(preds.split(chunk), targets.split(chunk)):
         p, t = _canon(_to_device(p)), _canon(_to_device(t))
@@ -160,22 +155,82 @@ def report_metrics(preds: torch.Tensor, targets: torch.Tensor, chunk: int = 4096
         if want_depth:
             bands.append(bd.view(m, c, 16).sum(1) / (c * (h // 16 - 10) * (w - 10)))
         if want_maps:
-            maps.append(fm.to(out_dev))
-    ssim_i, sse_i = torch.cat(ssims), torch.cat(sses)
-    per = c * h * w
+            maps.append(fm)
+    dev = ssims[0].device if ssims else torch.device("cuda")
+    cat = lambda xs, shape: torch.cat(xs) if xs else torch.zeros(shape, device=dev)      # noqa: E731
+    return (cat(ssims, (0,)), cat(sses, (0,)), cat(bands, (0, 16)) if want_depth else None,
+            torch.cat(maps) if (want_maps and maps) else None)
+
+
+def finalize_report(ssim_i: torch.Tensor, sse_i: torch.Tensor, bands, per: int):
+    """The reductions report.py applies to the per-image values (report.py:88-96,144-146,213-214): per-image PSNR /
+    MSE, their means, the global RMSE from the summed squared error, depth-band mean and unbiased std over images.
+    ``per`` = C*H*W elements per image.  Plain tensor arithmetic on [N]-vectors (runs on any device)."""
+    n = ssim_i.shape[0]
     mse_i = sse_i / per
     psnr_i = _psnr_from_sse(sse_i, per)
     res = {
-        "ssim": ssim_i.to(out_dev),
-        "psnr": psnr_i.to(out_dev),
-        "mse": mse_i.to(out_dev),
-        "ssim_mean": ssim_i.mean().to(out_dev),
-        "psnr_mean": psnr_i.mean().to(out_dev),
-        "rmse": torch.sqrt(sse_i.double().sum() / (n * per)).float().to(out_dev),
-        "ssim_maps": torch.cat(maps) if want_maps else None,
+        "ssim": ssim_i, "psnr": psnr_i, "mse": mse_i,
+        "ssim_mean": ssim_i.mean(), "psnr_mean": psnr_i.mean(),
+        "rmse": torch.sqrt(sse_i.double().sum() / (n * per)).float(),
         "depth_ssim": None,
     }
-    if want_depth:
-        bd = torch.cat(bands)                       # [N, 16]
-        res["depth_ssim"] = torch.stack([bd.mean(0), bd.std(0)], dim=1).to(out_dev)
+    if bands is not None:
+        res["depth_ssim"] = torch.stack([bands.mean(0), bands.std(0)], dim=1)          # [16, 2]
+    return res
+
+
+def gather_stats(ssim_i, sse_i, bands):
+    """Data-parallel evaluation sweep: every rank evaluated a contiguous shard of the pairs; the
+    per-image vectors (19 floats per image) are all-gathered in rank order so every rank can apply
+    ``finalize_report`` to the full set exactly as the single-process sweep does.  No collective touches the images.
+    Shards may have different lengths.  Without an initialised process group this is the identity."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return ssim_i, sse_i, bands
+    world = dist.get_world_size()
+    cols = [ssim_i.reshape(-1, 1).float(), sse_i.reshape(-1, 1).float()]
+    if bands is not None:
+        cols.append(bands.float())
+    local = torch.cat(cols, dim=1).contiguous()                       # [n_local, 2 (+16)]
+    count = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    counts = [torch.zeros_like(count) for _ in range(world)]
+    dist.all_gather(counts, count)
+    counts = [int(c.item()) for c in counts]
+    width, most = local.shape[1], max(counts)
+    padded = torch.zeros(most, width, dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded)
+    full = torch.cat([p[:k] for p, k in zip(parts, counts)])
+    return full[:, 0].contiguous(), full[:, 1].contiguous(), (full[:, 2:].contiguous() if bands is not None else None)
+
+
+def shard_bounds(n: int, rank: int, world: int):
+    """Contiguous shard [lo, hi) of ``n`` pairs for ``rank`` (the first ``n % world`` ranks get one extra pair)."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+@torch.no_grad()
+def report_metrics(preds: torch.Tensor, targets: torch.Tensor, chunk: int = 4096, want_maps: bool = False,
+                   want_depth: bool = True, distributed: bool = False):
+    """report.py:72-104,144-146,188-217 in one pass per pair.
+
+    Returns a dict with per-image ``ssim``/``psnr``/``mse`` ``[N]``, ``depth_ssim`` ``[16, 2]`` (mean and
+    unbiased std over images per depth band), ``ssim_mean``, ``psnr_mean``, global ``rmse`` and optionally
+    the full SSIM maps.  ``preds``/``targets`` may live on the host; they are streamed to the GPU in
+    ``chunk``-sized slices.
+
+    ``distributed=True``: ``preds``/``targets`` are this rank's shard (``shard_bounds``); the per-image vectors are
+    all-gathered and every rank returns the metrics of the WHOLE sweep (``ssim_maps`` stays local)."""
+    n, c, h, w = preds.shape
+    out_dev = preds.device
+    ssim_i, sse_i, bands, maps = per_image_stats(preds, targets, chunk, want_maps, want_depth)
+    if distributed:
+        ssim_i, sse_i, bands = gather_stats(ssim_i, sse_i, bands)
+    res = finalize_report(ssim_i, sse_i, bands, c * h * w)
+    res = {k: (v.to(out_dev) if isinstance(v, torch.Tensor) else v) for k, v in res.items()}
+    res["ssim_maps"] = maps.to(out_dev) if maps is not None else None
     return res
