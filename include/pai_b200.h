@@ -188,6 +188,9 @@ int pai_adam_multi(int count, float* const* params, const float* const* grads, f
                    float* const* exp_avg_sqs, const int* numels, float beta1, float beta2, float step_size,
                    float inv_bias_correction2_sqrt, float eps, const float* dyn, void* stream);
 int pai_adam_prepare(int* step, float lr, float beta1, float beta2, float* dyn, void* stream);
+/* Weight gradient from the wgrad kernels' accumulation layout dw[16][ab] (tap-major, ab = A*B) to the parameter layout
+ * grad[ab][16] (= [A, B, 4, 4], models/pix2pix.py:63,99); zero_src != 0 also zeroes dw for the next accumulation. */
+int pai_wgrad_finish(float* dw_tap_major, long long ab, float* grad, int zero_src, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Layers of the Residual / Attention / Trans U-Net variants (models/res_unet.py, attention_unet.py,

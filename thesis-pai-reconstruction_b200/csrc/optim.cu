@@ -126,6 +126,26 @@ adam_pack_conv4x4_kernel(float* __restrict__ w, const float* __restrict__ g, flo
     }
 }
 
+// ---- weight gradient: GEMM layout -> parameter layout ----------------------------------------------------------
+// The stream-K wgrad kernels accumulate into a zeroed tap-major fp32 buffer dw[16][ab] (ab = A*B weight pairs).  This
+// pass writes the gradient in the reference's parameter layout grad[ab][16] (= [A, B, 4, 4]): reads coalesced per tap,
+// one 64-byte store per (a, b).  zero_src re-zeroes dw for a persistent accumulation buffer; measured slower overall
+// than a fresh fill right before the wgrad kernel, because the fill leaves the lines in L2 for the red.adds.
+__global__ void __launch_bounds__(256)
+wgrad_finish_kernel(float* __restrict__ dw, long long ab, float* __restrict__ grad, int zero_src) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ab; i += (long long)gridDim.x * blockDim.x) {
+        float v[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            v[t] = dw[t * ab + i];
+            if (zero_src) dw[t * ab + i] = 0.f;
+        }
+        float4* o = reinterpret_cast<float4*>(grad + i * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+}
+
 // ---- multi-tensor Adam for the small parameters --------------------------------------------------
 static constexpr int kMaxTensors = 48;
 struct AdamTable {
@@ -181,6 +201,16 @@ int pai_adam_pack_conv4x4(float* w, const float* grad, float* exp_avg, float* ex
     dim3 grid((b + kTB - 1) / kTB, (a + kTA - 1) / kTA);
     adam_pack_conv4x4_kernel<<<grid, kPackThreads, smem, (cudaStream_t)stream>>>(
         w, grad, exp_avg, exp_avg_sq, a, b, hy, dyn, (__nv_bfloat16*)pack1, (__nv_bfloat16*)pack2, b_pad);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pai_wgrad_finish(float* dw_tap_major, long long ab, float* grad, int zero_src, void* stream) {
+    PAI_REQUIRE(dw_tap_major && grad && ab > 0, "pai_wgrad_finish: null pointer / empty shape");
+    PAI_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0, "pai_wgrad_finish: grad must be 16 B aligned");
+    long long blocks = (ab + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    wgrad_finish_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(dw_tap_major, ab, grad, zero_src);
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -136,14 +136,18 @@ class BNState:
     num_batches_tracked = property(lambda self: self.mod.num_batches_tracked)
 
 
-def _batchnorm(raw, bn: BNState, training: bool):
-    """-> scale_shift [4C] of BN over the pixels of ``raw``; updates running stats when training."""
+def _batchnorm(raw, bn: BNState, training: bool, counters=None):
+    """-> scale_shift [4C] of BN over the pixels of ``raw``; updates running stats when training.  The
+    ``num_batches_tracked`` increments of a whole forward are collected in ``counters`` (one foreach launch)."""
     m, c, _ = ops._mat(raw)
     sums = ops.bn_stats(raw) if training else None
     ss = ops.bn_finalize(sums, m, c, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
                          training=training, eps=BN_EPS, momentum=BN_MOMENTUM)
     if training:
-        bn.num_batches_tracked.add_(1)
+        if counters is None:
+            bn.num_batches_tracked.add_(1)
+        else:
+            counters.append(bn.num_batches_tracked)
     return ss
 
 
@@ -261,6 +265,7 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
     hs = [h >> (i + 1) for i in range(L)]
     ws = [w >> (i + 1) for i in range(L)]
     s = _Saved()
+    counters = []
     # decoder j (>=1) reads cat[j]: [N, hs[L-1-j], ws[L-1-j], 2*C] with C = ch[L-1-j]
     cat = [None] + [_bf16(n, hs[L - 1 - j], ws[L - 1 - j], 2 * ch[L - 1 - j], device=dev) for j in range(1, L)]
     a_in = [None] * (L + 1)                    # a_in[i]: activated input of encoder i (i >= 1)
@@ -281,7 +286,7 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
         if i < L - 1:
             raw = ops.conv4x4_fprop(a_in[i], _fprop_pack(conv.weight), ch[i], stride=2, bias=conv.bias.detach())
             if bn is not None:
-                ss = _batchnorm(raw, bn, training)
+                ss = _batchnorm(raw, bn, training, counters)
             else:
                 ss = None
             a_in[i + 1] = _bf16(n, hs[i], ws[i], ch[i], device=dev)
@@ -298,7 +303,7 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
         conv, bn = spec.dec_convs[j], spec.dec_bns[j]
         co = spec.dec_out[j]
         raw = ops.convT4x4s2_fprop(d_in, _fpropT_pack(conv.weight), co, bias=conv.bias.detach())
-        ss = _batchnorm(raw, bn, training)
+        ss = _batchnorm(raw, bn, training, counters)
         ops.bn_apply_act(raw, ss, cat[j + 1][..., :co], ACT_RELU if j + 1 < L - 1 else ACT_NONE)
         raw_d[j], ss_d[j] = raw, ss
         d_in = cat[j + 1]
@@ -307,6 +312,8 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
     # read once) + col2im with bias and Tanh
     part = ops.pointwise_gemm(d_in, _thin_out_fprop_pack(last.weight), 16, out_f32=True)
     y = ops.col2im4x4s2(part, last.bias.detach(), ACT_TANH).view(n, 1, h, w)
+    if counters:
+        torch._foreach_add_(counters, 1)
     if not save:
         return y, None
     s.xcol = xcol
@@ -345,8 +352,7 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
         ops.bn_bwd_apply(raw, ss, g1, act_out, None, ACT_NONE, sums, bn.weight.detach(), d_raw)
         d_in = s.cat[j] if j > 0 else s.dec_in0
         cin = conv.weight.shape[0]
-        dwt = ops.convT4x4s2_wgrad(d_in, d_raw)                                  # [16, cin, co]
-        gw = dwt.permute(1, 2, 0).reshape(cin, co, 4, 4)
+        gw = ops.wgrad_finish(ops.convT4x4s2_wgrad(d_in, d_raw))   # [cin, co, 4, 4]
         dp.allreduce_async(gw)                    # data-parallel: the exchange overlaps the rest of the backward
         grads[(1, j)] = (gw, torch.zeros(co, device=dev), sums[co:], sums[:co])
         dcat = ops.conv4x4_fprop(d_raw, _dgradT_pack(conv.weight), cin, stride=2)   # grad w.r.t. decoder input
@@ -355,8 +361,7 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
     conv = spec.enc_convs[i]
     d_raw = _bf16(*s.dec_in0.shape, device=dev)
     sums = ops.act_bwd(s.dec_in0, dcat, ACT_RELU, None, ACT_NONE, d_raw)
-    dwc = ops.conv4x4_wgrad(s.a_in[i], d_raw, stride=2)                          # [16, co, ci]
-    gw = dwc.permute(1, 2, 0).reshape(ch[i], ch[i - 1], 4, 4)
+    gw = ops.wgrad_finish(ops.conv4x4_wgrad(s.a_in[i], d_raw, stride=2))
     dp.allreduce_async(gw)
     grads[(0, i)] = (gw, sums[:ch[i]].clone())
     d_a = ops.convT4x4s2_fprop(d_raw, _dgrad_pack(conv.weight), ch[i - 1])
@@ -368,8 +373,7 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
         d_raw = _bf16(*raw.shape, device=dev)
         ops.bn_bwd_apply(raw, ss, d_a, ACT_LEAKY, dskip[i], ACT_RELU, sums, None if bn is None else bn.weight.detach(),
                          d_raw, slope=SLOPE)
-        dwc = ops.conv4x4_wgrad(s.a_in[i], d_raw, stride=2)
-        gw = dwc.permute(1, 2, 0).reshape(ch[i], ch[i - 1], 4, 4)
+        gw = ops.wgrad_finish(ops.conv4x4_wgrad(s.a_in[i], d_raw, stride=2))
         dp.allreduce_async(gw)
         if bn is not None:
             grads[(0, i)] = (gw, torch.zeros(ch[i], device=dev), sums[ch[i]:], sums[:ch[i]])
@@ -478,8 +482,7 @@ def disc_backward(spec: DiscSpec, s: _Saved, g_logits: torch.Tensor, need_params
         sums = ops.act_bwd(hk, dh, ACT_LEAKY, None, ACT_NONE, d_pre, slope=SLOPE)
         if k > 0:
             if need_params:
-                dwc = ops.conv4x4_wgrad(s.hs[k - 1], d_pre, stride=2)
-                grads[2 * k] = dwc.permute(1, 2, 0).reshape(ck, s.hs[k - 1].shape[3], 4, 4)
+                grads[2 * k] = ops.wgrad_finish(ops.conv4x4_wgrad(s.hs[k - 1], d_pre, stride=2))
                 dp.allreduce_async(grads[2 * k])
                 grads[2 * k + 1] = sums[:ck].clone()
             dh = ops.convT4x4s2_fprop(d_pre, _dgrad_pack(conv.weight), s.hs[k - 1].shape[3])

@@ -163,6 +163,15 @@ def convT4x4s2_wgrad(x, gy, dw=None, splitk=0):
     return dw
 
 
+def wgrad_finish(dw: torch.Tensor) -> torch.Tensor:
+    """tap-major ``[16, A, B]`` (the wgrad kernels' accumulation layout) -> new ``[A, B, 4, 4]`` gradient in the
+    parameter layout, one coalesced pass (instead of a generic strided ``permute().reshape()`` copy)."""
+    _, a, b = dw.shape
+    grad = torch.empty(a, b, 4, 4, dtype=torch.float32, device=dw.device)
+    lib.call("pai_wgrad_finish", _ptr(dw), a * b, _ptr(grad), 0, _stream())
+    return grad
+
+
 # ------------------------------------------------------------------------------------------ BatchNorm / activations
 def _mat(t: torch.Tensor):
     """NHWC (or [m, c]) view -> (m, c, ld)."""
