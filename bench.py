@@ -239,6 +239,17 @@ def variant_rates(device):
                                                      patch_size=4, dropout=0.0, loss_type="ssim"), 64),
     }
     out = {}
+
+    def timed(m, x, t, steps=5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            m.training_step((x, t), i)
+            m.logged.clear()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
     for name, (ctor, batch) in cases.items():
         try:
             torch.manual_seed(0)
@@ -248,17 +259,21 @@ def variant_rates(device):
             for i in range(3):
                 m.training_step((x, t), i)
             torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            steps = 5
-            e0.record()
-            for i in range(steps):
-                m.training_step((x, t), i)
+            m.logged.clear()
+            eager_ms = timed(m, x, t)
+            ms, launch = eager_ms, "eager"
+            try:                                    # the same opt-in as the headline: whole step as one CUDA graph
+                m.enable_step_graph(warmup=1)
+                for i in range(3):
+                    m.training_step((x, t), i)
+                torch.cuda.synchronize()
                 m.logged.clear()
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1) / steps
-            out[name] = {"images_per_s": batch / (ms * 1e-3), "ms_per_step": ms, "batch": batch,
-                         "params": sum(p.numel() for p in m.parameters())}
+                ms, launch = timed(m, x, t), "cuda graph"
+            except Exception as ex:  # pragma: no cover
+                m.disable_step_graph()
+                launch = f"eager (graph capture failed: {type(ex).__name__}: {ex})"[:200]
+            out[name] = {"images_per_s": batch / (ms * 1e-3), "ms_per_step": ms, "eager_ms_per_step": eager_ms,
+                         "launch": launch, "batch": batch, "params": sum(p.numel() for p in m.parameters())}
             del m, x, t
             torch.cuda.empty_cache()
         except Exception as ex:  # pragma: no cover

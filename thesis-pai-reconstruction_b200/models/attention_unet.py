@@ -59,8 +59,9 @@ class AttentionBlock(nn.Module):
         self.relu = nn.ReLU()
 
     def forward(self, x, signal):
-        h_in = L.batchnorm_act(L.conv2d(x, self.input_gate[0]), self.input_gate[1], L.ACT_NONE)
-        h_sig = L.batchnorm_act(L.conv2d(signal, self.signal_gate[0]), self.signal_gate[1], L.ACT_NONE)
+        h_in = L.batchnorm_act(L.conv2d(x, self.input_gate[0], before_train_bn=self.input_gate[1].training), self.input_gate[1], L.ACT_NONE)
+        h_sig = L.batchnorm_act(L.conv2d(signal, self.signal_gate[0], before_train_bn=self.signal_gate[1].training), self.signal_gate[1],
+                                 L.ACT_NONE)
         h = L.add_act(h_sig, h_in, L.ACT_RELU)
         logit = L.conv_out(h, self.attention[0])                       # fp32 plane [N, h, w]
         bn = self.attention[1]

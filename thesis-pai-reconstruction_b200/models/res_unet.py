@@ -41,7 +41,7 @@ class ResUnetGAN(UnetWrapper):
 
 def _cba(x, conv, bn, act):
     """Conv2d -> BatchNorm2d -> activation."""
-    return L.batchnorm_act(L.conv2d(x, conv), bn, act)
+    return L.batchnorm_act(L.conv2d(x, conv, before_train_bn=bn.training), bn, act)
 
 
 class _SkipMixin:

@@ -91,8 +91,8 @@ class DecoderBlock(nn.Module):
 
     def forward(self, x):
         d = self.decode
-        h = L.batchnorm_act(L.conv2d(x, d[0]), d[1], L.ACT_RELU)
-        h = L.batchnorm_act(L.conv2d(h, d[3]), d[4], L.ACT_RELU)
+        h = L.batchnorm_act(L.conv2d(x, d[0], before_train_bn=d[1].training), d[1], L.ACT_RELU)
+        h = L.batchnorm_act(L.conv2d(h, d[3], before_train_bn=d[4].training), d[4], L.ACT_RELU)
         return L.upsample2(h)
 
 
