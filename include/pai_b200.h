@@ -228,6 +228,11 @@ int pai_scale_rows_fwd(const void* x, int ldx, const float* s, long long m, int 
                        void* stream);
 int pai_scale_rows_bwd(const void* x, int ldx, const float* s, const void* g, int ldg, long long m, int c, int act,
                        void* gx, int ldgx, float* gs, void* stream);
+/* nn.Dropout2d (models/pix2pix.py:107, models/attention_unet.py, models/res_unet.py): out[n, p, :] = x[n, p, :] * mask[n, :]
+ * with mask [n, c] fp32 = 0 or 1/(1 - p) drawn by the caller; in place when out == x; the backward is the same call on
+ * the gradient. */
+int pai_scale_channels(const void* x, int ldx, const float* mask, int n, long long hw, int c, void* out, int ldo,
+                       void* stream);
 int pai_conv_plane_to_wide(const float* plane, int n, int h, int w, int k, int pad, int flip, const float* wt,
                            const float* bias, int c, int act, float slope, void* out, int ldo, void* stream);
 int pai_conv_wide_to_plane(const void* x, int n, int h, int w, int c, int ldx, int k, int pad, const float* wt,

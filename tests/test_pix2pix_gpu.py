@@ -160,9 +160,76 @@ def test_unsupported_configurations_fail_loudly():
     m3 = Pix2Pix(in_channels=3, out_channels=3, dropout=0.0, loss_type="mse").cuda()
     with pytest.raises(RuntimeError):
         m3(torch.zeros(1, 3, 256, 256, device="cuda"))
-    md = Pix2Pix(in_channels=1, out_channels=1, dropout=0.5, loss_type="mse").cuda().train()
-    with pytest.raises(RuntimeError):
-        md(torch.zeros(1, 1, 256, 256, device="cuda"))
+
+
+def test_train_mode_dropout2d_matches_reference_arithmetic(monkeypatch):
+    """The reference's default constructor has ``dropout=0.5``: Dropout2d after the BatchNorm of decoders 0-2
+    (models/pix2pix.py:107,176-183).  With the SAME (sample, channel) masks the fused engine must reproduce the
+    reference arithmetic (restated here on the oracle port's layer functions): forward 3e-2 max-abs at bf16 like the
+    other train-mode checks, weight-gradient norms within 12 %.  RNG streams themselves cannot match (CPU vs device)."""
+    import torch.nn.functional as F
+    from models.pix2pix import Pix2Pix
+    from pai_b200 import ops
+    torch.manual_seed(2)
+    m = Pix2Pix(in_channels=1, out_channels=1, dropout=0.5, loss_type="mse").cuda().train()
+    assert [b.dropout for b in list(m.unet.decoders)[:-1]] == [0.5, 0.5, 0.5, 0, 0, 0, 0]
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    n = 3
+    x, target = port.synthetic_pairs(n, seed=31)
+    g = torch.Generator().manual_seed(9)
+    masks = [torch.bernoulli(torch.full((n, 512), 0.5), generator=g) * 2.0 for _ in range(3)]
+    calls = []
+
+    def fixed_mask(nn_, c, p, device):
+        assert (nn_, c, p) == (n, 512, 0.5)
+        calls.append(len(calls))
+        return masks[len(calls) - 1].to(device).contiguous()
+
+    monkeypatch.setattr(ops, "dropout2d_mask", fixed_mask)
+    y = m(x.cuda())
+    assert len(calls) == 3
+    loss = F.mse_loss(y, target.cuda())
+    loss.backward()
+
+    # reference arithmetic with the same masks (oracle/pix2pix_port.py layer by layer + Dropout2d)
+    ref = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in sd.items()}
+    h, feats = x, []
+    for i in range(8):
+        if i == 0:
+            h = F.conv2d(h, ref["unet.encoders.0.weight"], ref["unet.encoders.0.bias"], 2, 1)
+        else:
+            pfx = f"unet.encoders.{i}.encode"
+            h = F.conv2d(F.leaky_relu(h, 0.2), ref[pfx + ".1.weight"], ref[pfx + ".1.bias"], 2, 1)
+            if pfx + ".2.weight" in ref:
+                h = port._bn(ref, pfx + ".2", h, True)
+        feats.append(h)
+    feats.pop()
+    for j in range(8):
+        if j:
+            h = torch.cat([h, feats.pop()], 1)
+        if j < 7:
+            pfx = f"unet.decoders.{j}.decode"
+            h = F.conv_transpose2d(F.relu(h), ref[pfx + ".1.weight"], ref[pfx + ".1.bias"], 2, 1)
+            h = port._bn(ref, pfx + ".2", h, True)
+            if j < 3:
+                h = h * masks[j][:, :, None, None]
+        else:
+            h = F.conv_transpose2d(h, ref["unet.decoders.7.weight"], ref["unet.decoders.7.bias"], 2, 1)
+    yo = torch.tanh(h)
+    F.mse_loss(yo, target).backward()
+    d = (y.detach().cpu() - yo.detach()).abs()
+    assert d.max().item() < 4e-2 and d.mean().item() < 6e-3, (d.max().item(), d.mean().item())
+    named = dict(m.named_parameters())
+    for k in ("unet.decoders.0.decode.1.weight", "unet.decoders.2.decode.1.weight", "unet.decoders.5.decode.1.weight",
+              "unet.encoders.2.encode.1.weight", "unet.encoders.7.encode.1.weight"):
+        got, want = float(named[k].grad.norm()), float(ref[k].grad.norm())
+        assert got == pytest.approx(want, rel=0.12), (k, got, want)
+    # eval mode: Dropout2d is the identity
+    m.eval()
+    with torch.no_grad():
+        y1, y2 = m(x.cuda()), m(x.cuda())
+    # (split-K layers accumulate with atomics: equal up to summation order)
+    assert torch.allclose(y1, y2, atol=1e-4) and len(calls) == 3
 
 
 @pytest.mark.parametrize("loss_type", ["gan", "ssim+psnr"])

@@ -208,6 +208,23 @@ scale_rows_fwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float*
         st8(out + pix * ldo + vec * 8, v);
     }
 }
+// nn.Dropout2d on NHWC: out[n, p, c] = x[n, p, c] * mask[n, c]  (mask = 0 or 1 / (1 - p_drop) per (sample, channel));
+// the backward is the same multiplication applied to the gradient.
+__global__ void __launch_bounds__(kLyThreads)
+scale_channels_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ mask, long long m,
+                      long long hw, int c, __nv_bfloat16* __restrict__ out, int ldo) {
+    const int cv = c >> 3;
+    const long long total = m * cv;
+    for (long long i = (long long)blockIdx.x * kLyThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kLyThreads) {
+        const int vec = (int)(i % cv);
+        const long long pix = i / cv;
+        V8 v = ld8(x + pix * ldx + vec * 8);
+        const float* mk = mask + (pix / hw) * c + vec * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v.v[k] *= mk[k];
+        st8(out + pix * ldo + vec * 8, v);
+    }
+}
 // one warp per pixel: lanes stride over the channel vectors, shuffle-reduce the dot product
 __global__ void __launch_bounds__(kLyThreads)
 scale_rows_bwd_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const float* __restrict__ s,
@@ -513,6 +530,15 @@ int pai_scale_rows_fwd(const void* x, int ldx, const float* s, long long m, int 
     PAI_REQUIRE(v8_ok(c, x, ldx) && v8_ok(c, out, ldo), "pai_scale_rows_fwd: bad channels / alignment");
     scale_rows_fwd_kernel<<<ly_grid(m * (c / 8)), kLyThreads, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, s, m, c, act,
                                                                                         (bf16*)out, ldo);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int pai_scale_channels(const void* x, int ldx, const float* mask, int n, long long hw, int c, void* out, int ldo,
+                       void* stream) {
+    PAI_REQUIRE(x && mask && out && n > 0 && hw > 0, "pai_scale_channels: null pointer / empty input");
+    PAI_REQUIRE(v8_ok(c, x, ldx) && v8_ok(c, out, ldo), "pai_scale_channels: bad channels / alignment");
+    scale_channels_kernel<<<ly_grid((long long)n * hw * (c / 8)), kLyThreads, 0, (cudaStream_t)stream>>>(
+        (const bf16*)x, ldx, mask, (long long)n * hw, hw, c, (bf16*)out, ldo);
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }

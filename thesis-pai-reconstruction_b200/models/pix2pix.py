@@ -95,13 +95,11 @@ class Unet(nn.Module):
             blocks = list(self.decoders)
             dec_convs = [b.decode[1] for b in blocks[:-1]] + [blocks[-1]]
             dec_bns = [b.decode[2] for b in blocks[:-1]] + [None]
-            self._spec = engine.UnetSpec(enc_convs, enc_bns, dec_convs, dec_bns)
+            dec_dropout = [float(getattr(b, "dropout", 0) or 0) for b in blocks]
+            self._spec = engine.UnetSpec(enc_convs, enc_bns, dec_convs, dec_bns, dec_dropout)
         return self._spec
 
     def forward(self, x):
-        if self.training and any(getattr(b, "dropout", 0) > 0 for b in self.decoders):
-            raise RuntimeError("pai_b200: train-mode Dropout2d (dropout > 0) has no B200 kernel yet; the "
-                               "benchmark configuration and main.py's default use dropout=0.0")
         spec = self._engine_spec()
         if engine.check_path_enabled():
             return engine.unet_forward_check(spec, x, self.training)

@@ -188,6 +188,8 @@ def _check_bn(v, bn, training):
 @torch.no_grad()
 def unet_forward_check(spec: "UnetSpec", x: torch.Tensor, training: bool) -> torch.Tensor:
     """``Unet.forward`` (models/pix2pix.py:198-216) layer by layer on the fp32 check kernels."""
+    if training and any(p > 0 for p in spec.dec_dropout):
+        raise RuntimeError("pai_b200: the fp32 check path has no Dropout2d (it is a deterministic forward check)")
     L = spec.levels
     skips = []
     v = x.contiguous().float()
@@ -224,7 +226,9 @@ def disc_forward_check(spec: "DiscSpec", x: torch.Tensor, y: torch.Tensor) -> to
 class UnetSpec:
     """Shapes + parameter holders of a reference-layout Unet (built by models/pix2pix.py:Unet)."""
 
-    def __init__(self, enc_convs, enc_bns, dec_convs, dec_bns):
+    def __init__(self, enc_convs, enc_bns, dec_convs, dec_bns, dec_dropout=None):
+        # dec_dropout[j]: Dropout2d probability after decoder j's BatchNorm (models/pix2pix.py:107,176-183)
+        self.dec_dropout = list(dec_dropout) if dec_dropout is not None else [0.0] * len(dec_convs)
         self.enc_convs, self.enc_bns = enc_convs, [None if b is None else BNState(b) for b in enc_bns]
         self.dec_convs, self.dec_bns = dec_convs, [None if b is None else BNState(b) for b in dec_bns]
         self.levels = len(enc_convs)
@@ -298,13 +302,20 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
                                         act=ACT_RELU)
     # ---- decoders 0..L-2 (BN), L-1 (Tanh)
     raw_d, ss_d = [None] * L, [None] * L
+    drop_masks = [None] * L
     d_in = dec_in0
     for j in range(L - 1):
         conv, bn = spec.dec_convs[j], spec.dec_bns[j]
         co = spec.dec_out[j]
         raw = ops.convT4x4s2_fprop(d_in, _fpropT_pack(conv.weight), co, bias=conv.bias.detach())
         ss = _batchnorm(raw, bn, training, counters)
-        ops.bn_apply_act(raw, ss, cat[j + 1][..., :co], ACT_RELU if j + 1 < L - 1 else ACT_NONE)
+        slot = cat[j + 1][..., :co]
+        ops.bn_apply_act(raw, ss, slot, ACT_RELU if j + 1 < L - 1 else ACT_NONE)
+        if training and spec.dec_dropout[j] > 0:
+            # Dropout2d sits between the BatchNorm and the next block's ReLU; the mask is non-negative, so it commutes
+            # with the ReLU already applied: relu(mask * z) == mask * relu(z)
+            drop_masks[j] = ops.dropout2d_mask(n, co, spec.dec_dropout[j], dev)
+            ops.scale_channels(slot, drop_masks[j], out=slot)
         raw_d[j], ss_d[j] = raw, ss
         d_in = cat[j + 1]
     last = spec.dec_convs[L - 1]
@@ -317,6 +328,7 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
     if not save:
         return y, None
     s.xcol = xcol
+    s.drop_masks = drop_masks
     s.plane, s.cat, s.a_in, s.raw_e, s.ss_e, s.raw_d, s.ss_d, s.dec_in0, s.y = plane, cat, a_in, raw_e, ss_e, raw_d, ss_d, dec_in0, y
     return y, s
 
@@ -345,6 +357,8 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
         enc_i = L - 2 - j                       # encoder whose skip sits in cat[j+1]
         dskip[enc_i] = dcat[..., co:]
         g1 = dcat[..., :co]
+        if s.drop_masks[j] is not None:
+            ops.scale_channels(g1, s.drop_masks[j], out=g1)          # Dropout2d backward, in place on the fresh dgrad
         raw, ss = s.raw_d[j], s.ss_d[j]
         act_out = ACT_RELU if j + 1 < L - 1 else ACT_NONE     # consumer of this decoder's output
         sums = ops.bn_bwd_reduce(raw, ss, g1, act_out)

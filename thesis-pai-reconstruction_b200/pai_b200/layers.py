@@ -568,11 +568,26 @@ def scale_rows(x, s):
     return _ScaleRows.apply(x, s)
 
 
+class _Dropout2d(torch.autograd.Function):
+    """nn.Dropout2d in training mode: whole channels of a sample are zeroed with probability p, the rest scaled by
+    1 / (1 - p); the mask is drawn with torch's device generator (the reference's CPU stream cannot be reproduced)."""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        mask = ops.dropout2d_mask(x.shape[0], x.shape[3], p, x.device)
+        ctx.save_for_backward(mask)
+        return ops.scale_channels(x, mask)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (mask,) = ctx.saved_tensors
+        return ops.scale_channels(gy.contiguous(), mask), None
+
+
 def dropout2d(x, mod):
     if isinstance(mod, nn.Identity) or not mod.training or mod.p == 0:
         return x
-    raise RuntimeError("pai_b200: train-mode Dropout2d with p > 0 is not implemented on the B200 path "
-                       "(main.py's default --dropout is 0.0); no fallback exists")
+    return _Dropout2d.apply(x, float(mod.p))
 
 
 # ------------------------------------------------------------------------------------------ Trans U-Net pieces

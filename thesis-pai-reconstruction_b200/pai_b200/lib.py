@@ -77,6 +77,7 @@ SIGNATURES = {
     "pai_attn_bwd": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "pai_adam_pack_conv4x4": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float,
                               c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    "pai_scale_channels": [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_void_p, c_int, c_void_p],
     "pai_wgrad_finish": [c_void_p, c_ll, c_void_p, c_int, c_void_p],
     "pai_adam_prepare": [c_void_p, c_float, c_float, c_float, c_void_p, c_void_p],
     "pai_check_conv2d_f32": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,

@@ -163,6 +163,22 @@ def convT4x4s2_wgrad(x, gy, dw=None, splitk=0):
     return dw
 
 
+def dropout2d_mask(n: int, c: int, p: float, device) -> torch.Tensor:
+    """fp32 ``[n, c]`` Dropout2d mask: 0 with probability ``p``, else ``1 / (1 - p)`` (torch's device generator)."""
+    keep = torch.bernoulli(torch.full((n, c), 1.0 - p, dtype=torch.float32, device=device))
+    return keep.mul_(1.0 / (1.0 - p))
+
+
+def scale_channels(x, mask, out=None):
+    """``out[n, h, w, :] = x[n, h, w, :] * mask[n, :]`` (Dropout2d forward, and its backward on the gradient)."""
+    n, h, w, c, ld = _nhwc(x)
+    assert mask.shape == (n, c) and mask.dtype == torch.float32 and mask.is_contiguous()
+    if out is None:
+        out = torch.empty(n, h, w, c, dtype=torch.bfloat16, device=x.device)
+    lib.call("pai_scale_channels", _ptr(x), ld, _ptr(mask), n, h * w, c, _ptr(out), _nhwc(out)[4], _stream())
+    return out
+
+
 def wgrad_finish(dw: torch.Tensor) -> torch.Tensor:
     """tap-major ``[16, A, B]`` (the wgrad kernels' accumulation layout) -> new ``[A, B, 4, 4]`` gradient in the
     parameter layout, one coalesced pass (instead of a generic strided ``permute().reshape()`` copy)."""
