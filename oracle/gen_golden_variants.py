@@ -27,6 +27,7 @@ CASES = {
     "res_next": ("models.res_unet", "ResUnetGAN", dict(res_type="next", channel_mults=(1, 2, 4, 8, 8, 8)), 2, 256, "ssim"),
     "res_18_small": ("models.res_unet", "ResUnetGAN", dict(res_type="18", channel_mults=(1, 2, 4, 8)), 4, 64, "ssim+psnr"),
     "res_v2_small": ("models.res_unet", "ResUnetGAN", dict(res_type="v2", channel_mults=(1, 2, 4, 8)), 4, 64, "mse"),
+    "res_50_small": ("models.res_unet", "ResUnetGAN", dict(res_type="50", channel_mults=(1, 2, 4, 8)), 4, 64, "ssim+psnr"),
     "attention": ("models.attention_unet", "AttentionUnetGAN", dict(), 2, 256, "ssim"),
     "trans_small": ("models.trans_unet", "TransUnetGAN", dict(channel_mults=(1, 2, 2), patch_size=4), 2, 256, "ssim"),
 }

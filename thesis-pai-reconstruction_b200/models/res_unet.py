@@ -39,9 +39,9 @@ class ResUnetGAN(UnetWrapper):
         self.save_hyperparameters()
 
 
-def _cba(x, conv, bn, act):
-    """Conv2d -> BatchNorm2d -> activation."""
-    return L.batchnorm_act(L.conv2d(x, conv, before_train_bn=bn.training), bn, act)
+def _cba(x, conv, bn, act, padded=False):
+    """Conv2d -> BatchNorm2d -> activation (``padded``: bottleneck channels in zero-padded 64-channel carriers)."""
+    return L.batchnorm_act(L.conv2d(x, conv, before_train_bn=bn.training, padded=padded), bn, act)
 
 
 class _SkipMixin:
@@ -106,9 +106,10 @@ class ResidualBlock50(nn.Module, _SkipMixin):
 
     def forward(self, x):
         b = self.conv_block
-        h = _cba(x, b[0], b[1], L.ACT_RELU)
-        h = _cba(h, b[3], b[4], L.ACT_RELU)
-        h = _cba(h, b[6], b[7], L.ACT_NONE)
+        pad = b[0].out_channels % 64 != 0           # 16 / 32-channel bottlenecks of the first levels
+        h = _cba(x, b[0], b[1], L.ACT_RELU, padded=pad)
+        h = _cba(h, b[3], b[4], L.ACT_RELU, padded=pad)
+        h = _cba(h, b[6], b[7], L.ACT_NONE, padded=pad)
         return L.add_act(h, self._skip(x), L.ACT_RELU)
 
 

@@ -399,12 +399,18 @@ class _NoBias:
         return getattr(self.mod, name)
 
 
-def conv2d(x, mod: nn.Conv2d, before_train_bn: bool = False):
+def conv2d(x, mod: nn.Conv2d, before_train_bn: bool = False, padded: bool = False):
     """Dispatch of an ``nn.Conv2d`` parameter holder onto the kernels (NHWC bf16 in / out).  ``before_train_bn``: the
-    output feeds a BatchNorm2d in training mode, whose backward makes the bias gradient exactly zero."""
+    output feeds a BatchNorm2d in training mode, whose backward makes the bias gradient exactly zero.  ``padded``:
+    channel counts that are not multiples of 64 travel in zero-padded 64-channel carriers (input and output)."""
     if before_train_bn and mod.bias is not None and mod.bias.requires_grad:
-        return _ZeroGradFor.apply(conv2d(x, _NoBias(mod)), mod.bias)
+        return _ZeroGradFor.apply(conv2d(x, _NoBias(mod), padded=padded), mod.bias)
     k, cin, cout, groups = mod.kernel_size[0], mod.in_channels, mod.out_channels, mod.groups
+    if padded and groups == 1 and k in (1, 3) and x.shape[-1] == _pad64(cin) and (cin % 64 or cout % 64):
+        if mod.stride != (1, 1) or mod.padding != (k // 2, k // 2) or mod.dilation != (1, 1):
+            raise RuntimeError(f"pai_b200: unsupported convolution geometry {mod}")
+        # ResNet-50 style bottlenecks of 16 / 32 channels (res_unet.py:84-95)
+        return _ConvPadded.apply(x, mod.weight, mod.bias)
     if mod.stride != (1, 1) or mod.padding != (k // 2, k // 2) or mod.dilation != (1, 1):
         raise RuntimeError(f"pai_b200: unsupported convolution geometry {mod}")
     if groups == 1 and cin % 64 == 0 and k == 1 and cout % 8 == 0:
@@ -629,6 +635,63 @@ class _Conv1x1Padded(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gw = ops.pointwise_wgrad(gy, x)[:cout, :cin].reshape(weight.shape)
         return gx, gw
+
+
+def _pad_w(w, cin_p):
+    """[cout, cin, k, k] -> zero-padded fp32 [pad64(cout), cin_p, k, k]."""
+    cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+    out = torch.zeros(_pad64(cout), cin_p, k, k, dtype=torch.float32, device=w.device)
+    out[:cout, :cin].copy_(w)
+    return out
+
+
+def _pad_b(b, cout_p):
+    out = torch.zeros(cout_p, dtype=torch.float32, device=b.device)
+    out[:b.shape[0]].copy_(b)
+    return out
+
+
+class _ConvPadded(torch.autograd.Function):
+    """nn.Conv2d(cin, cout, k in {1, 3}, padding=k//2) with bias between zero-padded 64-channel carriers:
+    x ``[..., pad64(cin)]`` -> ``[..., pad64(cout)]``, padded output channels stay exactly zero (zero weights, zero
+    bias).  The GEMMs run on the padded shapes (pointwise / 3x3 implicit GEMM); gradients are sliced back."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        k, cin_p = weight.shape[2], x.shape[-1]
+        cout_p = _pad64(weight.shape[0])
+        bp = None if bias is None else _packs.get("cp_b", bias, lambda b: _pad_b(b, cout_p))
+        if k == 1:
+            wp = _packs.get(f"p1_f{cin_p}", weight, lambda w: _pack_p1_f(w, cin_p))
+            y = ops.pointwise_gemm(x, wp, cout_p, bias=bp)
+        else:
+            wp = _packs.get(f"cp3_f{cin_p}", weight, lambda w: ops.pack_conv3x3_weight(_pad_w(w, cin_p)))
+            y = ops.conv3x3_fprop(x, wp, cout_p, bias=bp)
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy = gy.contiguous()
+        cout, cin, k, cin_p = weight.shape[0], weight.shape[1], weight.shape[2], x.shape[-1]
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            if k == 1:
+                wt = _packs.get(f"p1_d{cin_p}", weight, lambda w: _pack_p1_d(w, cin_p))
+                gx = ops.pointwise_gemm(gy, wt, cin_p)
+            else:
+                wd = _packs.get(f"cp3_d{cin_p}", weight, lambda w: ops.pack_conv3x3_weight_dgrad(_pad_w(w, cin_p)))
+                gx = ops.conv3x3_fprop(gy, wd, cin_p)
+        if ctx.needs_input_grad[1]:
+            if k == 1:
+                gw = ops.pointwise_wgrad(gy, x)[:cout, :cin].reshape(weight.shape)
+            else:
+                gw = ops.conv3x3_wgrad(x, gy)[:, :cout, :cin].permute(1, 2, 0).reshape(cout, cin, 3, 3)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = ops.colsum(gy)[:cout].clone()
+        return gx, gw, gb
 
 
 def _w3_as_4x4(w, cin_p):
