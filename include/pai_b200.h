@@ -148,8 +148,11 @@ int pai_smallc_conv_wgrad(const void* a, int lda, int c, const float* plane0, co
 /* ---------------------------------------------------------------------------------------------
  * Degenerate layers as tensor-core GEMMs.  A convolution whose input (enc0, D0) or output (dec7, D0's
  * data gradient) is 1-2 channels wide becomes  im2col / col2im of the thin side  +  a pointwise GEMM:
- *   pai_im2col4x4      col[n,oy,ox, t*cin+j] = plane_j[n, s*oy+dy_t, s*ox+dx_t] (bf16, 64 channels, zero padded)
+ *   pai_im2col4x4      col[n,oy,ox, t*cin+j] = plane_j[n, s*oy+dy_t, s*ox+dx_t] (bf16 rows of 64 channels; only the first
+ *                      16*cin are written -- consumers pass k_valid = 16*cin / ignore the other wgrad columns)
  *   pai_pointwise_gemm y[r, co] = act(bias[co] + sum_ci x[r, ci] * w_packed[co][ci])  (1x1 conv over m rows;
+ *                      k_valid > 0 (cin == 64 only): just the first k_valid columns of x hold data (pai_im2col4x4
+ *                      output), the rest is never read by the tensor core and may be uninitialised;
  *                      optional second bf16 output y2 with its own activation; m % 128 == 0)
  *   pai_pointwise_wgrad dw[cu][cs] += sum_r u[r, cu] * s[r, cs]                         (m % 64 == 0)
  *   pai_col2im4x4s2    out[n,2a+py,2b+px] = act(bias + sum of the 4 (tap, neighbour) partial products of
@@ -159,7 +162,7 @@ int pai_im2col4x4(const float* plane0, const float* plane1, int cin, int n, int 
                   int flip, void* col, void* stream);
 int pai_pointwise_gemm(const void* x, long long m, int cin, int x_ld, const void* w_packed, int cout, int cout_pad,
                        const float* bias, int act, float slope, void* y, int y_ld, int y_f32, void* y2, int y2_ld,
-                       int act2, int n_tile, void* stream);
+                       int act2, int n_tile, int k_valid, void* stream);
 int pai_pointwise_wgrad(const void* u, long long m, int cu, int u_ld, const void* s, int cs, int s_ld, float* dw,
                         int splitk, void* stream);
 int pai_col2im4x4s2(const float* p, int ldp, int n, int h, int w, const float* bias, int act, float* out,

@@ -149,7 +149,8 @@ def test_thin_conv_as_im2col_plus_pointwise_gemm():
         wp = torch.zeros(c, 64, dtype=torch.bfloat16, device="cuda")
         wp[:, :16 * cin] = wt.permute(0, 2, 3, 1).reshape(c, -1)
         o2 = torch.zeros(n, h // 2, w // 2, 2 * c, dtype=torch.bfloat16, device="cuda")
-        o1 = ops.pointwise_gemm(col, wp, c, bias=bias, act=ops.ACT_LEAKY, out2=o2[..., c:], act2=ops.ACT_NONE)
+        o1 = ops.pointwise_gemm(col, wp, c, bias=bias, act=ops.ACT_LEAKY, out2=o2[..., c:], act2=ops.ACT_NONE,
+                                k_valid=16 * cin)        # im2col leaves the padding columns unwritten
         xin = torch.stack(planes, 1).bfloat16().float()
         ref = F.conv2d(xin, wt.bfloat16().float(), bias, stride=2, padding=1)
         tol = 1e-2 * max(1.0, ref.abs().max().item())
@@ -182,7 +183,7 @@ def test_thin_convT_as_pointwise_gemm_plus_col2im():
     gcol = ops.im2col4x4([g], h, w, stride=2)
     wd = torch.zeros(cin, 64, dtype=torch.bfloat16, device="cuda")
     wd[:, :16] = wt[:, 0].reshape(cin, 16)
-    dx = ops.pointwise_gemm(gcol, wd, cin)
+    dx = ops.pointwise_gemm(gcol, wd, cin, k_valid=16)
     refdx = xr.grad.permute(0, 2, 3, 1)
     assert (dx.float() - refdx).abs().max().item() < 2e-2 * max(1.0, refdx.abs().max().item())
     dw = ops.pointwise_wgrad(x, gcol)[:, :16].reshape(cin, 1, 4, 4)

@@ -232,9 +232,9 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         }
                     } else {
                         umma_bf16_ss(tmem_d, da0, db0, idesc, kb != kb_begin);
-                        umma_bf16_acc(tmem_d, da0 + 2, db0 + 2, idesc);
-                        umma_bf16_acc(tmem_d, da0 + 4, db0 + 4, idesc);
-                        umma_bf16_acc(tmem_d, da0 + 6, db0 + 6, idesc);
+                        if (p.kmma > 1) umma_bf16_acc(tmem_d, da0 + 2, db0 + 2, idesc);
+                        if (p.kmma > 2) umma_bf16_acc(tmem_d, da0 + 4, db0 + 4, idesc);
+                        if (p.kmma > 3) umma_bf16_acc(tmem_d, da0 + 6, db0 + 6, idesc);
                     }
                     umma_commit(&ps.empty[stage]);
                     if (++stage == stages) {
@@ -557,6 +557,7 @@ int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFp
     const size_t stage_bytes = 128 * 128 + (size_t)(p.fused_phases ? 4 : 1) * p.n_tile * 128;
     p.stages = pick_stages(stage_bytes, 192 * 1024);
     p.m_tiles = m_tiles, p.n_tiles = n_tiles, p.phases = phases;
+    if (p.kmma <= 0 || p.kmma > 4) p.kmma = 4;
     const size_t smem = stage_bytes * p.stages + 1024;
     static bool attr_done = false;
     static int num_sms = 148;

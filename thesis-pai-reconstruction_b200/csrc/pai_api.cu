@@ -344,8 +344,10 @@ int pai_pointwise_wgrad(const void* u, long long m, int cu, int u_ld, const void
 
 int pai_pointwise_gemm(const void* x, long long m, int cin, int x_ld, const void* w_packed, int cout, int cout_pad,
                        const float* bias, int act, float slope, void* y, int y_ld, int y_f32, void* y2, int y2_ld,
-                       int act2, int n_tile, void* stream) {
+                       int act2, int n_tile, int k_valid, void* stream) {
     PAI_REQUIRE(x && w_packed && y, "pai_pointwise_gemm: null pointer");
+    PAI_REQUIRE(k_valid == 0 || (cin == 64 && k_valid > 0 && k_valid <= 64 && k_valid % 16 == 0),
+                "pai_pointwise_gemm: k_valid (%d) needs cin == 64 and a multiple of 16", k_valid);
     PAI_REQUIRE(cin > 0 && cin % 64 == 0, "pai_pointwise_gemm: cin must be a multiple of 64 (got %d)", cin);
     PAI_REQUIRE(cout_pad % 16 == 0 && cout <= cout_pad, "pai_pointwise_gemm: bad cout %d / cout_pad %d", cout, cout_pad);
     PAI_REQUIRE(aligned16(x) && aligned16(w_packed) && x_ld % 8 == 0 && x_ld >= cin, "pai_pointwise_gemm: alignment");
@@ -373,6 +375,7 @@ int pai_pointwise_gemm(const void* x, long long m, int cin, int x_ld, const void
     p.out_sn = (long long)wbox * y_ld, p.out_sh = 0, p.out_sw = y_ld;
     p.out2_sn = (long long)wbox * y2_ld, p.out2_sh = 0, p.out2_sw = y2_ld;
     p.bias = bias, p.act = act, p.slope = slope, p.out_f32 = y_f32, p.out = y, p.out2 = y2, p.act2 = act2;
+    p.kmma = k_valid > 0 ? k_valid / 16 : 4;
     return launch_igemm_fprop(tm_a, tm_b, p, b.tiles_w * b.tiles_h * b.tiles_n, cout_pad / n_tile, 1,
                               (cudaStream_t)stream);
 }

@@ -59,6 +59,8 @@ struct IgemmFpropParams {
     int fused_phases;
     int box_w[9], box_h[9];            // box coordinate offsets
     int box_users[9][4];               // phase * 4 + tap of every MMA fed by the box, -1 terminated
+    int kmma;                  // MMA k-steps (16 channels each) issued per 64-channel K block: 4, or fewer when only the
+                               // first 16 * kmma columns of the (single) K block hold data (thin im2col operands)
     int splitk;                // K slices per output tile (>1: partial sums are accumulated into fp32 `out`)
     int accumulate;            // generic fp32 path adds into `out` (red.add) instead of storing
 };

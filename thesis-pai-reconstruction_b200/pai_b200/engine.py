@@ -283,7 +283,7 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
     # enc0 (1 input channel) = im2col of the plane + one tensor-core GEMM with two fused outputs
     xcol = ops.im2col4x4([plane], hs[0], ws[0], stride=2)
     ops.pointwise_gemm(xcol, _thin_in_pack(conv0.weight), c0, bias=conv0.bias.detach(), act=ACT_LEAKY, slope=SLOPE,
-                       out=a_in[1], out2=cat[L - 1][..., c0:], act2=ACT_NONE)
+                       out=a_in[1], out2=cat[L - 1][..., c0:], act2=ACT_NONE, k_valid=16)
     # ---- encoders 1..L-1
     for i in range(1, L):
         conv, bn = spec.enc_convs[i], spec.enc_bns[i]
@@ -348,7 +348,7 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
     gcol = ops.im2col4x4([g_pre], h // 2, w // 2, stride=2)                      # [N, h/2, w/2, 64], 16 taps of g
     dw = ops.pointwise_wgrad(s.cat[L - 1], gcol)                                 # [cin, 64]
     grads[(1, L - 1)] = (dw[:, :16].reshape(cin_last, 1, 4, 4), g_pre.sum().reshape(1))
-    dcat = ops.pointwise_gemm(gcol, _thin_out_dgrad_pack(last.weight), cin_last)
+    dcat = ops.pointwise_gemm(gcol, _thin_out_dgrad_pack(last.weight), cin_last, k_valid=16)
     # ---- decoders L-2 .. 0
     dskip = [None] * L                          # dskip[i]: grad w.r.t. relu(skip_i) (second half of dcat)
     for j in range(L - 2, -1, -1):
@@ -455,7 +455,7 @@ def disc_forward(spec: DiscSpec, x: torch.Tensor, y: torch.Tensor, save: bool):
     c0 = spec.convs[0]
     xycol = ops.im2col4x4([px, py], h // 2, w // 2, stride=2)                    # cat([x, y]) never materialised
     hcur = ops.pointwise_gemm(xycol, _thin_in_pack(c0.weight), spec.ch[0], bias=c0.bias.detach(), act=ACT_LEAKY,
-                              slope=SLOPE)
+                              slope=SLOPE, k_valid=32)
     hs = [hcur]
     for k in range(1, len(spec.convs) - 1):
         c = spec.convs[k]

@@ -303,7 +303,7 @@ class _Conv4x4s2In(torch.autograd.Function):
         n, h, w = plane.shape
         xcol = ops.im2col4x4([plane], h // 2, w // 2, stride=2)
         y = ops.pointwise_gemm(xcol, engine._thin_in_pack(weight), weight.shape[0],
-                               bias=None if bias is None else bias.detach())
+                               bias=None if bias is None else bias.detach(), k_valid=16)
         ctx.save_for_backward(xcol)
         ctx.has_bias = bias is not None
         return y
@@ -341,7 +341,7 @@ class _ConvT4x4s2Out(torch.autograd.Function):
         gcol = ops.im2col4x4([g_pre], h2 // 2, w2 // 2, stride=2)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = ops.pointwise_gemm(gcol, engine._thin_out_dgrad_pack(weight), cin)
+            gx = ops.pointwise_gemm(gcol, engine._thin_out_dgrad_pack(weight), cin, k_valid=16)
         if ctx.needs_input_grad[1]:
             gw = ops.pointwise_wgrad(x, gcol)[:, :16].reshape(cin, 1, 4, 4)
         if ctx.has_bias and ctx.needs_input_grad[2]:

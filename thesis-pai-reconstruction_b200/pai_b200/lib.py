@@ -45,7 +45,7 @@ SIGNATURES = {
                               c_int, c_int, c_void_p, c_void_p],
     "pai_im2col4x4": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "pai_pointwise_gemm": [c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_float, c_void_p,
-                           c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
+                           c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "pai_pointwise_wgrad": [c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
     "pai_col2im4x4s2": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
     "pai_conv3x3_fprop": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_float,

@@ -294,7 +294,9 @@ def smallc_conv_wgrad(a, planes, stride=2, flip=False):
 
 # ------------------------------------------------------------------------------------------ thin layers as GEMMs
 def im2col4x4(planes, oh, ow, stride=2, flip=False):
-    """1|2 fp32 planes ``[n, ih, iw]`` -> bf16 ``[n, oh, ow, 64]`` (channel = tap*cin + j, zero padded)."""
+    """1|2 fp32 planes ``[n, ih, iw]`` -> bf16 ``[n, oh, ow, 64]`` (channel = tap*cin + j).  Only the first
+    ``16 * len(planes)`` channels are written: pass ``k_valid=16 * len(planes)`` to ``pointwise_gemm`` and ignore the
+    other columns of a ``pointwise_wgrad`` result."""
     p0 = planes[0]
     p1 = planes[1] if len(planes) > 1 else None
     n, ih, iw = p0.shape
@@ -305,8 +307,9 @@ def im2col4x4(planes, oh, ow, stride=2, flip=False):
 
 
 def pointwise_gemm(x, w_packed, cout, bias=None, act=ACT_NONE, slope=0.2, out=None, out_f32=False, out2=None,
-                   act2=ACT_NONE, n_tile=0):
-    """1x1 convolution: ``y[..., co] = act(bias + x[..., :] @ w_packed[co, :])`` over all pixels of an NHWC tensor."""
+                   act2=ACT_NONE, n_tile=0, k_valid=0):
+    """1x1 convolution: ``y[..., co] = act(bias + x[..., :] @ w_packed[co, :])`` over all pixels of an NHWC tensor.
+    ``k_valid``: only the first ``k_valid`` of the 64 input columns hold data (``im2col4x4`` output)."""
     m, cin, ld = _mat(x)
     cp = w_packed.shape[0]
     if out is None:
@@ -319,7 +322,7 @@ def pointwise_gemm(x, w_packed, cout, bias=None, act=ACT_NONE, slope=0.2, out=No
         assert (m2, c2) == (m, cout)
     _igemm_call("pai_pointwise_gemm", 2.0 * m * cin * cout, _ptr(x), m, cin, ld, _ptr(w_packed), cout, cp, _ptr(bias),
                 act, float(slope), _ptr(out), old, int(out.dtype == torch.float32), _ptr(out2), old2, act2, n_tile,
-                _stream())
+                k_valid, _stream())
     return out
 
 
