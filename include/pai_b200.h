@@ -63,6 +63,17 @@ int pai_conv4x4_fprop(const void* x, int n, int h, int w, int cin, int x_ld, con
 int pai_convT4x4s2_fprop(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
                          int cout_pad, const float* bias, int act, float slope, void* y, int y_ld, int y_f32,
                          int n_tile, float* splitk_ws, void* stream);
+/* BatchNorm statistics from the GEMM epilogue ("BN fused into the epilogue" of the north star): the convolution writes
+ * its raw bf16 output (+bias, no activation) AND every CTA adds the per-channel sum / sum of squares of the values it
+ * stores to its own row of bn_partials [bn_rows >= #SMs][2*cout] (fp32, zeroed by the caller) -- the separate
+ * statistics pass over the output (pai_bn_stats) disappears.  Needs cout %% 64 == 0 and a layer large enough not to be
+ * split along K (more than 74 * 128 output pixels); otherwise an error is returned and nothing is launched. */
+int pai_conv4x4_fprop_bnstats(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
+                              int cout_pad, int stride, const float* bias, void* y, int y_ld, int n_tile,
+                              float* bn_partials, int bn_rows, void* stream);
+int pai_convT4x4s2_fprop_bnstats(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
+                                 int cout_pad, const float* bias, void* y, int y_ld, int n_tile, float* bn_partials,
+                                 int bn_rows, void* stream);
 
 /* Weight gradients (autograd of the two modules above).
  * pai_conv4x4_wgrad:   dw[ky*4+kx][co][ci] += sum_{n,oh,ow} gy[n,oh,ow,co] * x[n,stride*oh-1+ky,stride*ow-1+kx,ci]
@@ -118,6 +129,11 @@ int pai_bn_stats(const void* x, long long m, int c, int ld, float* sums, void* s
 int pai_bn_finalize(const float* sums, long long m, int c, const float* gamma, const float* beta, float eps,
                     float momentum, int training, float* running_mean, float* running_var, float* scale_shift,
                     void* stream);
+/* The same from `nparts` rows of partial sums [nparts][2*c] (summed first): the per-CTA rows written by
+ * pai_conv4x4_fprop_bnstats / pai_convT4x4s2_fprop_bnstats. */
+int pai_bn_finalize_partials(const float* sums, int nparts, long long m, int c, const float* gamma, const float* beta,
+                             float eps, float momentum, int training, float* running_mean, float* running_var,
+                             float* scale_shift, void* stream);
 int pai_bn_apply_act(const void* x, long long m, int c, int ld, const float* scale_shift, void* out1, int ld1,
                      int act1, void* out2, int ld2, int act2, float slope, void* stream);
 int pai_bn_bwd_reduce(const void* x, long long m, int c, int ld, const float* scale_shift, const void* g1, int ldg1,

@@ -242,3 +242,32 @@ def test_act_bwd_fused_bias_gradient(with_g2):
         want = want + g2.float()
     assert (dx.float() - want).abs().max().item() < 2e-2
     assert torch.allclose(sums[:c], want.reshape(-1, c).sum(0), rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("kind,n,h,w,cin,cout", [("conv", 16, 64, 64, 64, 128), ("conv", 4, 64, 96, 128, 256),
+                                                 ("convT", 8, 32, 32, 256, 64), ("convT", 4, 32, 48, 512, 128)])
+def test_bn_statistics_from_the_gemm_epilogue(kind, n, h, w, cin, cout):
+    """pai_conv4x4_fprop_bnstats / pai_convT4x4s2_fprop_bnstats: same raw output as the plain convolution, and the
+    per-CTA partial sums add up to what pai_bn_stats computes from that output (sum, sum of squares per channel);
+    convT 256 -> 64 takes the phase-fused tile path."""
+    ops = _ops()
+    x = _rand((n, h, w, cin), 31)
+    bias = torch.randn(cout, device="cuda")
+    if kind == "conv":
+        wt = torch.randn(cout, cin, 4, 4, device="cuda") * 0.05
+        wp = ops.pack_conv_weight(wt)
+        ref = ops.conv4x4_fprop(x, wp, cout, stride=2, bias=bias)
+        raw, part = ops.conv4x4_fprop_bnstats(x, wp, cout, bias=bias)
+    else:
+        wt = torch.randn(cin, cout, 4, 4, device="cuda") * 0.05
+        wp = ops.pack_convT_weight(wt)
+        ref = ops.convT4x4s2_fprop(x, wp, cout, bias=bias)
+        raw, part = ops.convT4x4s2_fprop_bnstats(x, wp, cout, bias=bias)
+    assert torch.equal(raw, ref)
+    want = ops.bn_stats(ref)
+    got = part.sum(0)
+    assert torch.allclose(got[:cout], want[:cout], rtol=1e-4, atol=1e-2), (got[:cout] - want[:cout]).abs().max()
+    assert torch.allclose(got[cout:], want[cout:], rtol=1e-4, atol=1e-2)
+    f = ref.float().reshape(-1, cout)
+    assert torch.allclose(got[:cout], f.sum(0), rtol=1e-3, atol=5e-2)
+    assert torch.allclose(got[cout:], (f * f).sum(0), rtol=1e-3, atol=5e-2)

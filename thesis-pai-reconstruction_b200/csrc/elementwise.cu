@@ -130,19 +130,39 @@ bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long m, int c, int ld,
 __global__ void bn_finalize_kernel(const float* __restrict__ sums, long long m, int c, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float eps, float momentum, int training,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
-                                   float* __restrict__ ss) {
-    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ch >= c) return;
+                                   float* __restrict__ ss, int nparts) {
+    // block = 32 channels x 8 row groups: the partial rows are summed by 8 threads per channel (coalesced 128-byte
+    // loads), then thread row 0 finishes the channel
+    __shared__ float red_s[8][32], red_q[8][32];
+    const int chl = threadIdx.x & 31, rg = threadIdx.x >> 5;
+    const int ch = blockIdx.x * 32 + chl;
     float mean, var;
     if (training) {
-        mean = sums[ch] / (float)m;
-        var = fmaxf(sums[c + ch] / (float)m - mean * mean, 0.f);
+        // nparts > 1: per-CTA partial sums written by the implicit-GEMM epilogue (pai_conv4x4_fprop_bnstats)
+        float s = 0.f, q = 0.f;
+        if (ch < c)
+            for (int r = rg; r < nparts; r += 8) {
+                s += sums[(size_t)r * 2 * c + ch];
+                q += sums[(size_t)r * 2 * c + c + ch];
+            }
+        red_s[rg][chl] = s;
+        red_q[rg][chl] = q;
+        __syncthreads();
+        if (rg != 0 || ch >= c) return;
+#pragma unroll
+        for (int r = 1; r < 8; ++r) {
+            s += red_s[r][chl];
+            q += red_q[r][chl];
+        }
+        mean = s / (float)m;
+        var = fmaxf(q / (float)m - mean * mean, 0.f);
         if (running_mean != nullptr) {
             const float unbiased = m > 1 ? var * ((float)m / (float)(m - 1)) : var;
             running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * mean;
             running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * unbiased;
         }
     } else {
+        if (rg != 0 || ch >= c) return;
         mean = running_mean[ch];
         var = running_var[ch];
     }
@@ -396,16 +416,21 @@ int pai_bn_stats(const void* x, long long m, int c, int ld, float* sums, void* s
     return 0;
 }
 
+int pai_bn_finalize_partials(const float* sums, int nparts, long long m, int c, const float* gamma, const float* beta,
+                             float eps, float momentum, int training, float* running_mean, float* running_var,
+                             float* scale_shift, void* stream) {
+    PAI_REQUIRE(scale_shift && (training ? (sums != nullptr && nparts >= 1) : (running_mean && running_var)),
+                "pai_bn_finalize: null pointer");
+    bn_finalize_kernel<<<(c + 31) / 32, 256, 0, (cudaStream_t)stream>>>(sums, m, c, gamma, beta, eps, momentum, training,
+                                                                        running_mean, running_var, scale_shift, nparts);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 int pai_bn_finalize(const float* sums, long long m, int c, const float* gamma, const float* beta, float eps,
                     float momentum, int training, float* running_mean, float* running_var, float* scale_shift,
                     void* stream) {
-    PAI_REQUIRE(scale_shift && (training ? sums != nullptr : (running_mean && running_var)),
-                "pai_bn_finalize: null pointer");
-    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, m, c, gamma, beta, eps, momentum,
-                                                                          training, running_mean, running_var,
-                                                                          scale_shift);
-    PAI_CUDA_OK(cudaGetLastError());
-    return 0;
+    return pai_bn_finalize_partials(sums, 1, m, c, gamma, beta, eps, momentum, training, running_mean, running_var,
+                                    scale_shift, stream);
 }
 
 int pai_bn_apply_act(const void* x, long long m, int c, int ld, const float* scale_shift, void* out1, int ld1,

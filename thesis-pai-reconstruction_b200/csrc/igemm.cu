@@ -309,6 +309,29 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         else
                             bias_act_pack<PAI_ACT_NONE>(v, bias_c, p.slope, tile, lane);
                         __syncwarp();
+                        if (p.bn_part != nullptr && which == 0) {
+                            // BatchNorm statistics of exactly what is stored: lane <-> channels 2*lane, 2*lane + 1 of
+                            // the chunk, summed over the valid rows of the 32 x 64 bf16 tile (conflict-free words)
+                            const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
+                            const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
+                            const int chunk = lane >> 2, word = lane & 3;
+                            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+                            for (int row = 0; row < 32; ++row) {
+                                if (!((okmask >> row) & 1u)) continue;
+                                const uint32_t u = tw[(row * 8 + (chunk ^ (row & 7))) * 4 + word];
+                                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+                                s0 += f.x;
+                                s1 += f.y;
+                                q0 = fmaf(f.x, f.x, q0);
+                                q1 = fmaf(f.y, f.y, q1);
+                            }
+                            float* bp = p.bn_part + (size_t)blockIdx.x * (2 * p.cout) + col0 + oc + 2 * lane;
+                            atomicAdd(bp, s0);
+                            atomicAdd(bp + 1, s1);
+                            atomicAdd(bp + p.cout, q0);
+                            atomicAdd(bp + p.cout + 1, q1);
+                        }
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int row = i * 4 + (lane >> 3), ch = lane & 7;
@@ -573,6 +596,13 @@ int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFp
     p.fd_tiles_w = make_fastdiv(p.tiles_w), p.fd_tiles_h = make_fastdiv(p.tiles_h);
     const long long total = (long long)m_tiles * n_tiles * phases * p.splitk;
     const int grid = (int)(total < num_sms ? total : num_sms);
+    if (p.bn_part != nullptr) {
+        // the statistics ride on the coalesced bf16 epilogue: whole 64-channel chunks, one output, no split-K
+        PAI_REQUIRE(!p.out_f32 && p.splitk == 1 && !p.accumulate && (p.n_tile & 63) == 0 && p.cout % p.n_tile == 0 &&
+                        (p.cout & 7) == 0 && p.bn_rows >= grid,
+                    "igemm fprop: fused BatchNorm statistics need a bf16 output with cout %% 64 == 0, no split-K and "
+                    "%d partial rows (cout=%d n_tile=%d splitk=%d rows=%d)", grid, p.cout, p.n_tile, p.splitk, p.bn_rows);
+    }
     igemm_fprop_kernel<<<grid, kFpropThreads, smem, stream>>>(tm_a, tm_b, p);
     PAI_CUDA_OK(cudaGetLastError());
     return 0;

@@ -140,9 +140,9 @@ extern "C" {
 const char* pai_last_error(void) { return g_err; }
 int pai_version(void) { return 100; }
 
-int pai_conv4x4_fprop(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
-                      int cout_pad, int stride, const float* bias, int act, float slope, void* y, int y_ld,
-                      int y_f32, int n_tile, float* splitk_ws, void* stream) {
+static int conv4x4_fprop_impl(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
+                              int cout_pad, int stride, const float* bias, int act, float slope, void* y, int y_ld,
+                              int y_f32, int n_tile, float* splitk_ws, float* bn_part, int bn_rows, void* stream) {
     PAI_REQUIRE(x && w_packed && y, "pai_conv4x4_fprop: null pointer");
     PAI_REQUIRE(stride == 1 || stride == 2, "pai_conv4x4_fprop: stride must be 1 or 2 (got %d)", stride);
     PAI_REQUIRE(cin > 0 && cin % 64 == 0, "pai_conv4x4_fprop: cin must be a multiple of 64 (got %d)", cin);
@@ -189,6 +189,7 @@ int pai_conv4x4_fprop(const void* x, int n, int h, int w, int cin, int x_ld, con
             }
         }
     p.b_rows_per_phase = cout_pad;
+    p.bn_part = bn_part, p.bn_rows = bn_rows;
     const int m_tiles = b.tiles_w * b.tiles_h * b.tiles_n;
     p.splitk = pick_splitk(splitk_ws, (long long)m_tiles * (cout_pad / n_tile), 16 * (cin / 64));
     if (p.splitk > 1) {
@@ -204,9 +205,23 @@ int pai_conv4x4_fprop(const void* x, int n, int h, int w, int cin, int x_ld, con
     return launch_igemm_fprop(tm_a, tm_b, p, m_tiles, cout_pad / n_tile, 1, (cudaStream_t)stream);
 }
 
-int pai_convT4x4s2_fprop(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
-                         int cout_pad, const float* bias, int act, float slope, void* y, int y_ld, int y_f32,
-                         int n_tile, float* splitk_ws, void* stream) {
+int pai_conv4x4_fprop(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
+                      int cout_pad, int stride, const float* bias, int act, float slope, void* y, int y_ld,
+                      int y_f32, int n_tile, float* splitk_ws, void* stream) {
+    return conv4x4_fprop_impl(x, n, h, w, cin, x_ld, w_packed, cout, cout_pad, stride, bias, act, slope, y, y_ld, y_f32,
+                              n_tile, splitk_ws, nullptr, 0, stream);
+}
+int pai_conv4x4_fprop_bnstats(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
+                              int cout_pad, int stride, const float* bias, void* y, int y_ld, int n_tile,
+                              float* bn_partials, int bn_rows, void* stream) {
+    PAI_REQUIRE(bn_partials != nullptr && bn_rows > 0, "pai_conv4x4_fprop_bnstats: null partial-sum buffer");
+    return conv4x4_fprop_impl(x, n, h, w, cin, x_ld, w_packed, cout, cout_pad, stride, bias, PAI_ACT_NONE, 0.f, y, y_ld, 0,
+                              n_tile, nullptr, bn_partials, bn_rows, stream);
+}
+
+static int convT4x4s2_fprop_impl(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
+                                 int cout_pad, const float* bias, int act, float slope, void* y, int y_ld, int y_f32,
+                                 int n_tile, float* splitk_ws, float* bn_part, int bn_rows, void* stream) {
     PAI_REQUIRE(x && w_packed && y, "pai_convT4x4s2_fprop: null pointer");
     PAI_REQUIRE(cin > 0 && cin % 64 == 0, "pai_convT4x4s2_fprop: cin must be a multiple of 64 (got %d)", cin);
     PAI_REQUIRE(cout_pad % 16 == 0 && cout <= cout_pad, "pai_convT4x4s2_fprop: bad cout %d / cout_pad %d", cout, cout_pad);
@@ -238,6 +253,7 @@ int pai_convT4x4s2_fprop(const void* x, int n, int h, int w, int cin, int x_ld, 
                     p.tap_c[i] = 0, p.tap_w[i] = kTd[px][tx], p.tap_p[i] = 0, p.tap_h[i] = kTd[py][ty];
                 }
     p.b_rows_per_phase = cout_pad;
+    p.bn_part = bn_part, p.bn_rows = bn_rows;
     const long long wo = 2LL * w;
     const int m_tiles = b.tiles_w * b.tiles_h * b.tiles_n;
     p.splitk = pick_splitk(splitk_ws, 4LL * m_tiles * (cout_pad / n_tile), 4 * (cin / 64));
@@ -274,6 +290,20 @@ int pai_convT4x4s2_fprop(const void* x, int n, int h, int w, int cin, int x_ld, 
     }
     p.bias = bias, p.act = act, p.slope = slope, p.out_f32 = y_f32, p.out = y;
     return launch_igemm_fprop(tm_a, tm_b, p, m_tiles, cout_pad / n_tile, 4, (cudaStream_t)stream);
+}
+
+int pai_convT4x4s2_fprop(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
+                         int cout_pad, const float* bias, int act, float slope, void* y, int y_ld, int y_f32,
+                         int n_tile, float* splitk_ws, void* stream) {
+    return convT4x4s2_fprop_impl(x, n, h, w, cin, x_ld, w_packed, cout, cout_pad, bias, act, slope, y, y_ld, y_f32, n_tile,
+                                 splitk_ws, nullptr, 0, stream);
+}
+int pai_convT4x4s2_fprop_bnstats(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
+                                 int cout_pad, const float* bias, void* y, int y_ld, int n_tile, float* bn_partials,
+                                 int bn_rows, void* stream) {
+    PAI_REQUIRE(bn_partials != nullptr && bn_rows > 0, "pai_convT4x4s2_fprop_bnstats: null partial-sum buffer");
+    return convT4x4s2_fprop_impl(x, n, h, w, cin, x_ld, w_packed, cout, cout_pad, bias, PAI_ACT_NONE, 0.f, y, y_ld, 0,
+                                 n_tile, nullptr, bn_partials, bn_rows, stream);
 }
 
 // stride: 2 = parity-split taps, 1 = unit-stride 4x4 taps, 0 = pointwise (a single tap at offset 0)

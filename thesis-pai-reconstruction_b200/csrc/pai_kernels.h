@@ -61,6 +61,10 @@ struct IgemmFpropParams {
     int box_users[9][4];               // phase * 4 + tap of every MMA fed by the box, -1 terminated
     int kmma;                  // MMA k-steps (16 channels each) issued per 64-channel K block: 4, or fewer when only the
                                // first 16 * kmma columns of the (single) K block hold data (thin im2col operands)
+    // BatchNorm statistics from the epilogue (coalesced bf16 path only): every CTA adds the per-channel sum and sum of
+    // squares of the bf16-rounded outputs it stores to its own row bn_part[blockIdx.x][2 * cout] (zeroed by the caller)
+    float* bn_part;
+    int bn_rows;
     int splitk;                // K slices per output tile (>1: partial sums are accumulated into fp32 `out`)
     int accumulate;            // generic fp32 path adds into `out` (red.add) instead of storing
 };

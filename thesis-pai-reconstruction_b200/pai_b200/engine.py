@@ -13,6 +13,7 @@ the reference's ``state_dict`` layout; bf16 GEMM packs are rebuilt when a parame
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional
 
 import torch
@@ -21,6 +22,7 @@ from . import dp, ops
 from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH
 
 BN_EPS, BN_MOMENTUM, SLOPE = 1e-5, 0.1, 0.2
+FUSE_BN_STATS = os.environ.get("PAI_NO_BN_FUSION") is None     # BatchNorm statistics from the GEMM epilogue
 
 
 # ------------------------------------------------------------------------------------------ pack cache
@@ -136,13 +138,17 @@ class BNState:
     num_batches_tracked = property(lambda self: self.mod.num_batches_tracked)
 
 
-def _batchnorm(raw, bn: BNState, training: bool, counters=None):
+def _batchnorm(raw, bn: BNState, training: bool, counters=None, partials=None):
     """-> scale_shift [4C] of BN over the pixels of ``raw``; updates running stats when training.  The
-    ``num_batches_tracked`` increments of a whole forward are collected in ``counters`` (one foreach launch)."""
+    ``num_batches_tracked`` increments of a whole forward are collected in ``counters`` (one foreach launch).
+    ``partials``: per-CTA partial sums already produced by the convolution's epilogue (no statistics pass)."""
     m, c, _ = ops._mat(raw)
-    sums = ops.bn_stats(raw) if training else None
+    if training and partials is not None:
+        sums, nparts = partials, partials.shape[0]
+    else:
+        sums, nparts = (ops.bn_stats(raw) if training else None), 1
     ss = ops.bn_finalize(sums, m, c, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
-                         training=training, eps=BN_EPS, momentum=BN_MOMENTUM)
+                         training=training, eps=BN_EPS, momentum=BN_MOMENTUM, nparts=nparts)
     if training:
         if counters is None:
             bn.num_batches_tracked.add_(1)
@@ -288,9 +294,14 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
     for i in range(1, L):
         conv, bn = spec.enc_convs[i], spec.enc_bns[i]
         if i < L - 1:
-            raw = ops.conv4x4_fprop(a_in[i], _fprop_pack(conv.weight), ch[i], stride=2, bias=conv.bias.detach())
+            part = None
+            if bn is not None and training and FUSE_BN_STATS and ops.bn_fusable(n * hs[i] * ws[i], ch[i]):
+                # BatchNorm statistics straight from the GEMM epilogue: no separate pass over the raw output
+                raw, part = ops.conv4x4_fprop_bnstats(a_in[i], _fprop_pack(conv.weight), ch[i], bias=conv.bias.detach())
+            else:
+                raw = ops.conv4x4_fprop(a_in[i], _fprop_pack(conv.weight), ch[i], stride=2, bias=conv.bias.detach())
             if bn is not None:
-                ss = _batchnorm(raw, bn, training, counters)
+                ss = _batchnorm(raw, bn, training, counters, part)
             else:
                 ss = None
             a_in[i + 1] = _bf16(n, hs[i], ws[i], ch[i], device=dev)
@@ -307,8 +318,13 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
     for j in range(L - 1):
         conv, bn = spec.dec_convs[j], spec.dec_bns[j]
         co = spec.dec_out[j]
-        raw = ops.convT4x4s2_fprop(d_in, _fpropT_pack(conv.weight), co, bias=conv.bias.detach())
-        ss = _batchnorm(raw, bn, training, counters)
+        part = None
+        hj, wj = d_in.shape[1], d_in.shape[2]
+        if training and FUSE_BN_STATS and ops.bn_fusable(4 * n * hj * wj, co):
+            raw, part = ops.convT4x4s2_fprop_bnstats(d_in, _fpropT_pack(conv.weight), co, bias=conv.bias.detach())
+        else:
+            raw = ops.convT4x4s2_fprop(d_in, _fpropT_pack(conv.weight), co, bias=conv.bias.detach())
+        ss = _batchnorm(raw, bn, training, counters, part)
         slot = cat[j + 1][..., :co]
         ops.bn_apply_act(raw, ss, slot, ACT_RELU if j + 1 < L - 1 else ACT_NONE)
         if training and spec.dec_dropout[j] > 0:

@@ -78,6 +78,12 @@ SIGNATURES = {
     "pai_adam_pack_conv4x4": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float,
                               c_float, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
     "pai_scale_channels": [c_void_p, c_int, c_void_p, c_int, c_ll, c_int, c_void_p, c_int, c_void_p],
+    "pai_conv4x4_fprop_bnstats": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
+                                  c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
+    "pai_convT4x4s2_fprop_bnstats": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
+                                     c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
+    "pai_bn_finalize_partials": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_float, c_float, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_void_p],
     "pai_wgrad_finish": [c_void_p, c_ll, c_void_p, c_int, c_void_p],
     "pai_adam_prepare": [c_void_p, c_float, c_float, c_float, c_void_p, c_void_p],
     "pai_check_conv2d_f32": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,

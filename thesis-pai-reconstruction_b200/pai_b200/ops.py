@@ -127,6 +127,36 @@ def conv4x4_fprop(x, w_packed, cout, stride=2, bias=None, act=ACT_NONE, slope=0.
     return out
 
 
+BN_PART_ROWS = 160          # >= number of SMs (one partial-sum row per persistent CTA)
+
+
+def bn_fusable(pixels: int, cout: int) -> bool:
+    """The statistics can ride on the GEMM epilogue when the layer is not split along K and has whole 64-channel chunks."""
+    return pixels > SPLITK_MAX_PIXELS and cout % 64 == 0
+
+
+def conv4x4_fprop_bnstats(x, w_packed, cout, bias=None):
+    """Stride-2 4x4 convolution that also yields the BatchNorm partial sums of its (bf16) output:
+    -> (raw ``[n, h/2, w/2, cout]`` bf16, partials ``[BN_PART_ROWS, 2*cout]`` fp32 for ``bn_finalize``)."""
+    n, h, w, cin, ld = _nhwc(x)
+    cp = w_packed.shape[0]
+    out = torch.empty(n, h // 2, w // 2, cout, dtype=torch.bfloat16, device=x.device)
+    part = torch.zeros(BN_PART_ROWS, 2 * cout, dtype=torch.float32, device=x.device)
+    _igemm_call("pai_conv4x4_fprop_bnstats", 2.0 * n * (h // 2) * (w // 2) * cout * 16 * cin, _ptr(x), n, h, w, cin, ld,
+                _ptr(w_packed), cout, cp, 2, _ptr(bias), _ptr(out), cout, 0, _ptr(part), BN_PART_ROWS, _stream())
+    return out, part
+
+
+def convT4x4s2_fprop_bnstats(x, w_packed, cout, bias=None):
+    n, h, w, cin, ld = _nhwc(x)
+    cp = w_packed.shape[1]
+    out = torch.empty(n, 2 * h, 2 * w, cout, dtype=torch.bfloat16, device=x.device)
+    part = torch.zeros(BN_PART_ROWS, 2 * cout, dtype=torch.float32, device=x.device)
+    _igemm_call("pai_convT4x4s2_fprop_bnstats", 2.0 * n * h * w * cout * 16 * cin, _ptr(x), n, h, w, cin, ld,
+                _ptr(w_packed), cout, cp, _ptr(bias), _ptr(out), cout, 0, _ptr(part), BN_PART_ROWS, _stream())
+    return out, part
+
+
 def convT4x4s2_fprop(x, w_packed, cout, bias=None, act=ACT_NONE, slope=0.2, out=None, out_f32=False, n_tile=0):
     n, h, w, cin, ld = _nhwc(x)
     cp = w_packed.shape[1]
@@ -206,11 +236,16 @@ def bn_stats(x, sums=None):
     return sums
 
 
-def bn_finalize(sums, m, c, gamma, beta, running_mean, running_var, training=True, eps=1e-5, momentum=0.1, ss=None):
+def bn_finalize(sums, m, c, gamma, beta, running_mean, running_var, training=True, eps=1e-5, momentum=0.1, ss=None,
+                nparts=1):
     if ss is None:
         ss = torch.empty(4 * c, dtype=torch.float32, device=gamma.device)
-    lib.call("pai_bn_finalize", _ptr(sums), m, c, _ptr(gamma), _ptr(beta), float(eps), float(momentum), int(training),
-             _ptr(running_mean), _ptr(running_var), _ptr(ss), _stream())
+    if nparts > 1:
+        lib.call("pai_bn_finalize_partials", _ptr(sums), nparts, m, c, _ptr(gamma), _ptr(beta), float(eps),
+                 float(momentum), int(training), _ptr(running_mean), _ptr(running_var), _ptr(ss), _stream())
+    else:
+        lib.call("pai_bn_finalize", _ptr(sums), m, c, _ptr(gamma), _ptr(beta), float(eps), float(momentum),
+                 int(training), _ptr(running_mean), _ptr(running_var), _ptr(ss), _stream())
     return ss
 
 
