@@ -148,8 +148,8 @@ def run_reference_arm(args):
     if rank != 0:
         return
     batch = 8            # bounded sample of the 64-image per-GPU batch (config[0]'s CPU-runnable size)
-    steps = max(1, min(args.steps, 12))
-    warmup = max(1, min(args.warmup, 2))
+    steps = max(1, min(args.steps, 40))
+    warmup = max(1, min(args.warmup, 3))
     rate, sec, cores, threads = cpu_reference_step_rate(steps, warmup, batch)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": args.gpus,
@@ -455,10 +455,10 @@ def run_ours(args):
         if world == 1 and not args.no_variants:
             line["variants"] = variant_rates(dev)
         if world == 1 and not args.no_cpu_baseline:
-            rate, sec, cores, threads = cpu_reference_step_rate(steps=3, warmup=1, batch=8)
+            rate, sec, cores, threads = cpu_reference_step_rate(steps=20, warmup=2, batch=8)
             line["cpu_baseline"] = {
                 "value": rate, "unit": "images/s", "cores": threads, "kind": "port",
-                "sample": f"3 GAN training steps of batch 8 (BASELINE.json configs[0]) after 1 warm-up, "
+                "sample": f"20 GAN training steps of batch 8 (BASELINE.json configs[0]) after 2 warm-up steps, "
                           f"{sec:.2f} s/step, torch CPU fp32 with {threads} threads on {cores} cpus"}
         emit(line)
     dp.barrier()
