@@ -116,6 +116,23 @@ def _thin_out_dgrad_pack(w):   # ConvT weight [Cin, 1, 4, 4] -> bf16 [Cin, 64]: 
     return _packs.get("thin_out_d", w, lambda t: _pad_cols(t[:, 0].reshape(t.shape[0], 16)))
 
 
+def _aux_pack(tag: str, p: torch.Tensor, fn):
+    """Packs that the fused Adam kernel does not rewrite: kept apart from ``_pai_packs`` (whose tags tell FusedAdam
+    which operands to refresh in place) and dropped by FusedAdam after every update of the parameter."""
+    store = p.__dict__.setdefault("_pai_aux", {})
+    stamp = (p._version, p.data_ptr())
+    ent = store.get(tag)
+    if ent is None or ent[0] != stamp:
+        with torch.no_grad():
+            ent = (stamp, fn(p.detach()))
+        store[tag] = ent
+    return ent[1]
+
+
+def _head_dgrad_pack(w):       # PatchGAN head Conv2d weight [1, C, 4, 4] -> bf16 [C, 64]: column = tap
+    return _aux_pack("head_d", w, lambda t: _pad_cols(t[0].reshape(t.shape[1], 16)))
+
+
 def _thin_in_dgrad_pack(w, j):  # Conv2d weight [C, cin, 4, 4] -> bf16 [16, C]: row = tap, for input channel j
     return _packs.get(f"thin_in_d{j}", w, lambda t: t[:, j].reshape(t.shape[0], 16).t().contiguous().bfloat16())
 
@@ -498,12 +515,13 @@ def disc_backward(spec: DiscSpec, s: _Saved, g_logits: torch.Tensor, need_params
     h_last = s.hs[-1]
     c_last = h_last.shape[3]
     grads = [None] * (2 * (K - 1) + 1)
+    # head (Conv4x4 s1 p1, 512 -> 1): its backward is 1 channel wide on the gradient side, so -- like dec7 -- the 16
+    # shifted copies of the logit gradient become the K = 16 operand of two tensor-core GEMMs
+    gcol = ops.im2col4x4([g], h_last.shape[1], h_last.shape[2], stride=1, flip=True)    # [N, 16, 16, 64 (16 used)]
     if need_params:
-        dwh = ops.smallc_conv_wgrad(h_last, [g], stride=1, flip=True)             # [c, 16, 1]
-        grads[-1] = dwh.view(c_last, 4, 4, 1).permute(3, 0, 1, 2)
-    dh = _bf16(*h_last.shape, device=dev)
-    ops.smallc_conv_fprop([g], _w_tap_major(head.weight.detach().permute(1, 0, 2, 3)), None, dh, ACT_NONE, stride=1,
-                          flip=True)
+        dwh = ops.pointwise_wgrad(h_last, gcol)[:, :16]                             # [c, 16]
+        grads[-1] = dwh.reshape(1, c_last, 4, 4)
+    dh = ops.pointwise_gemm(gcol, _head_dgrad_pack(head.weight), c_last, k_valid=16)
     for k in range(K - 2, -1, -1):
         conv = spec.convs[k]
         hk = s.hs[k]                                # lrelu output: same sign as the pre-activation

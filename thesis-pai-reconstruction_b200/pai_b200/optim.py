@@ -80,6 +80,7 @@ class FusedAdam(torch.optim.Adam):
     def _launch(self, items, beta1, beta2, step_size, inv_bc2, eps, dyn, stream):
         small = []
         for p, g, st in items:
+            p.__dict__.pop("_pai_aux", None)            # packs the kernels below do not rewrite
             packs = engine.fused_pack_targets(p)
             if packs is None:
                 p.__dict__.pop("_pai_packs", None)      # thin-layer packs are rebuilt lazily
