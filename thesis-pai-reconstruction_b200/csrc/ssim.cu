@@ -616,7 +616,7 @@ static int launch(const void* pred, const void* target, int n, int h, int band_r
 // Interior windows only (rows / columns 5 .. dim-6): what the scalar metrics need.
 namespace stream {
 
-static constexpr int W = 256, GR = 8, NG = 4, NB = 3, VP = 9, VC = W + 10;
+static constexpr int W = 256, GR = 8, NG = 4, NB = 4, VP = 9, VC = W + 10;
 static constexpr int NV = 256, NH = 256, NT = 32 + NV + NH;     // warp 0 producer, warps 1-8 V, warps 9-16 H
 
 using rows::bulk_g2s;
