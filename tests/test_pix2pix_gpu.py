@@ -272,3 +272,42 @@ def test_step_graph_matches_eager_training(loss_type):
         dev_graph = float((np.abs(lg[k] - la[k]) / scale).max())
         dev_eager = float((np.abs(lb[k] - la[k]) / scale).max())
         assert dev_graph <= max(5 * dev_eager, 2e-2), (k, dev_graph, dev_eager, la[k], lb[k], lg[k])
+
+
+def test_step_graph_recaptures_and_optimizer_state_round_trips():
+    """The graph bakes in pointers and hyper-parameters: changing the learning rate or loading a state dict must drop it
+    and capture again (never replay stale arguments), and FusedAdam's device-side step counter must survive
+    ``state_dict()`` -> ``load_state_dict()`` into a fresh optimizer exactly like torch.optim.Adam's per-parameter steps."""
+    data = tuple(t.cuda() for t in port.synthetic_pairs(2, seed=77))
+    m = _build("ssim+psnr", seed=4).train()
+    m.enable_step_graph(warmup=1)
+    runner = m.__dict__["_pai_step_graph"]
+    for i in range(4):
+        m.training_step(data, i)
+    assert runner.replays == 3
+    opt = m.optimizers()
+    import copy
+    sd = copy.deepcopy(opt.state_dict())      # like torch's, state_dict() hands out the LIVE per-parameter state
+    model_sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    assert {float(st["step"]) for st in sd["state"].values()} == {4.0}
+    # new learning rate -> signature mismatch -> one eager warm-up call, then a fresh capture
+    w_before = m.unet.encoders[3].encode[1].weight.detach().clone()
+    for group in opt.param_groups:
+        group["lr"] = 0.0
+    for i in range(3):
+        m.training_step(data, i)
+    torch.cuda.synchronize()
+    assert runner.replays == 3 + 2
+    assert torch.equal(m.unet.encoders[3].encode[1].weight.detach(), w_before), "lr = 0 must freeze the weights"
+    assert {float(st["step"]) for st in opt.state_dict()["state"].values()} == {7.0}
+    # a fresh model + optimizer resumes from the saved state: same step count, then the same update as the original
+    m2 = _build("ssim+psnr", seed=4).train()
+    m2.load_state_dict(model_sd)
+    opt2 = m2.optimizers()
+    opt2.load_state_dict(sd)
+    m2.training_step(data, 0)
+    torch.cuda.synchronize()
+    steps2 = {float(st["step"]) for st in opt2.state_dict()["state"].values()}
+    assert steps2 == {5.0}, steps2
+    moved = (m2.unet.encoders[3].encode[1].weight.detach() - model_sd["unet.encoders.3.encode.1.weight"]).abs().max().item()
+    assert 0 < moved < 1e-3        # one Adam step of lr 2e-4 with the restored moments
