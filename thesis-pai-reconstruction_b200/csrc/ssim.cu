@@ -717,12 +717,22 @@ ssim_fwd_stream_kernel(const T* __restrict__ pred, const T* __restrict__ target,
         const int blocks_per_img = h / 16;
         const int iters = n_mine * blocks_per_img;
         float4* vcol = vbuf + (x + 5) * VP;
+        // the input row is fetched one row ahead, so its shared-memory latency hides behind the 22 FFMA2 of the row
+        // being scattered
+        mbar_wait_sleep(&gfull[0], 0);
+        float pn = ring_ld(ring_p + x), tn = ring_ld(ring_t + x);
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                if ((j & 7) == 0) mbar_wait_sleep(&gfull[G & (NG - 1)], (G / NG) & 1);
-                const int s_in = ((G & (NG - 1)) * GR + (j & 7)) * W + x;
-                float p = ring_ld(ring_p + s_in), t = ring_ld(ring_t + s_in);
+                float p = pn, t = tn;
+                if (j != 15 || it + 1 < iters) {
+                    const bool cross = (j & 7) == 7;               // the next row opens the next granule
+                    const int Gn = G + (cross ? 1 : 0);
+                    if (cross) mbar_wait_sleep(&gfull[Gn & (NG - 1)], (Gn / NG) & 1);
+                    const int s_n = ((Gn & (NG - 1)) * GR + ((j + 1) & 7)) * W + x;
+                    pn = ring_ld(ring_p + s_n);
+                    tn = ring_ld(ring_t + s_n);
+                }
                 if (DENORM) {
                     p = denorm(p);
                     t = denorm(t);
@@ -803,8 +813,8 @@ ssim_fwd_stream_kernel(const T* __restrict__ pred, const T* __restrict__ target,
             float sv[GR];
 #pragma unroll
             for (int o = 0; o < GR; ++o) {
-                const float2 sq = mul2(ma[o], ma[o]);
-                const float2 u = make_float2(sq.x + sq.y, ma[o].x * ma[o].y);
+                const float2 sq = mul2(ma[o], make_float2(ma[o].x, ma[o].x));      // (mu_p^2, mu_p mu_t): mu_p broadcast
+                const float2 u = make_float2(fmaf(ma[o].y, ma[o].y, sq.x), sq.y);
                 const float2 ba1 = fma2(u, one_two, c1);
                 const float2 ba2 = fma2(sub2(mq[o], u), one_two, c2);
                 const float2 dn = mul2(ba1, ba2);
