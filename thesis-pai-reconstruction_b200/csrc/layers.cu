@@ -421,44 +421,77 @@ gconv4_fprop_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, in
     }
 }
 
-// grid (pixel blocks, 9 taps): thread <-> (pixel lane, 8 channels) with 32 partial sums, block reduce
+// grid (pixel blocks, 3 tap rows): thread <-> (pixel lane, 8 channels = 2 groups); the three taps dx = -1, 0, +1 of the
+// row share one load of the output gradient (3 instead of 9 passes over gy, all four 16-byte loads of a pixel in
+// flight together), 96 partial sums per thread, block reduce per tap
 __global__ void __launch_bounds__(kLyThreads)
 gconv4_wgrad_kernel(const __nv_bfloat16* __restrict__ x, int ldx, const __nv_bfloat16* __restrict__ gy, int ldg, int n,
                     int h, int w, int c, float* __restrict__ dw /* [c][9][4] */) {
     __shared__ float red[kLyThreads * 33];
-    const int t = blockIdx.y, dy = t / 3 - 1, dx = t % 3 - 1;
+    const int dy = (int)blockIdx.y - 1;
     const int cv = c >> 3;
     const int vec = threadIdx.x % cv;
     const int ppb = kLyThreads / cv;
-    float acc[8][4];
+    float acc[3][8][4];
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[q][j] = 0.f;
-    const long long total = (long long)n * h * w;
-    for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / cv; p < total; p += (long long)gridDim.x * ppb) {
-        const int x0 = (int)(p % w);
-        const int y0 = (int)((p / w) % h);
-        const int yy = y0 + dy, xx = x0 + dx;
-        if (yy < 0 || yy >= h || xx < 0 || xx >= w) continue;
-        const V8 g = ld8(gy + p * ldg + vec * 8);
-        const V8 v = ld8(x + (p + (long long)dy * w + dx) * ldx + vec * 8);
+    for (int t = 0; t < 3; ++t)
 #pragma unroll
         for (int q = 0; q < 8; ++q)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[q][j] = fmaf(g.v[q], v.v[(q >> 2) * 4 + j], acc[q][j]);
+            for (int j = 0; j < 4; ++j) acc[t][q][j] = 0.f;
+    const long long total = (long long)n * h * w;
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / cv; p < total; p += (long long)gridDim.x * ppb) {
+        const int x0 = (int)(p % w);
+        const int y0 = (int)((p / w) % h);
+        const int yy = y0 + dy;
+        if (yy < 0 || yy >= h) continue;
+        const __nv_bfloat16* xr = x + (p + (long long)dy * w) * ldx + vec * 8;
+        const uint4 rg = *reinterpret_cast<const uint4*>(gy + p * ldg + vec * 8);
+        uint4 rx[3];
+        rx[0] = x0 > 0 ? *reinterpret_cast<const uint4*>(xr - ldx) : zero;
+        rx[1] = *reinterpret_cast<const uint4*>(xr);
+        rx[2] = x0 + 1 < w ? *reinterpret_cast<const uint4*>(xr + ldx) : zero;
+        V8 g;
+        {
+            const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&rg);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __bfloat1622float2(hg[i]);
+                g.v[2 * i] = f.x, g.v[2 * i + 1] = f.y;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            V8 v;
+            const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&rx[t]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 f = __bfloat1622float2(hv[i]);
+                v.v[2 * i] = f.x, v.v[2 * i + 1] = f.y;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[t][q][j] = fmaf(g.v[q], v.v[(q >> 2) * 4 + j], acc[t][q][j]);
+        }
     }
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
+    for (int t = 0; t < 3; ++t) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) red[threadIdx.x * 33 + q * 4 + j] = acc[q][j];
-    __syncthreads();
-    for (int i = threadIdx.x; i < cv * 32; i += kLyThreads) {
-        const int vv = i >> 5, e = i & 31;          // e = q*4 + j
-        float s = 0.f;
-        for (int r = vv; r < kLyThreads; r += cv) s += red[r * 33 + e];
-        const int co = vv * 8 + (e >> 2), j = e & 3;
-        atomicAdd(dw + ((long long)co * 9 + t) * 4 + j, s);
+        for (int q = 0; q < 8; ++q)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) red[threadIdx.x * 33 + q * 4 + j] = acc[t][q][j];
+        __syncthreads();
+        const int tap = ((int)blockIdx.y) * 3 + t;
+        for (int i = threadIdx.x; i < cv * 32; i += kLyThreads) {
+            const int vv = i >> 5, e = i & 31;          // e = q*4 + j
+            float s = 0.f;
+            for (int r = vv; r < kLyThreads; r += cv) s += red[r * 33 + e];
+            const int co = vv * 8 + (e >> 2), j = e & 3;
+            atomicAdd(dw + ((long long)co * 9 + tap) * 4 + j, s);
+        }
+        __syncthreads();
     }
 }
 
@@ -606,8 +639,8 @@ int pai_gconv4_3x3_wgrad(const void* x, int ldx, const void* gy, int ldg, int n,
     PAI_REQUIRE(v8_ok(c, x, ldx) && v8_ok(c, gy, ldg) && cv_divides_block(c), "pai_gconv4_3x3_wgrad: bad channels / alignment");
     const long long ppb = kLyThreads / (c / 8);
     long long blocks = ((long long)n * h * w + ppb - 1) / ppb;
-    if (blocks > 148 * 2) blocks = 148 * 2;
-    gconv4_wgrad_kernel<<<dim3((int)blocks, 9), kLyThreads, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)gy,
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    gconv4_wgrad_kernel<<<dim3((int)blocks, 3), kLyThreads, 0, (cudaStream_t)stream>>>((const bf16*)x, ldx, (const bf16*)gy,
                                                                                       ldg, n, h, w, c, dw);
     PAI_CUDA_OK(cudaGetLastError());
     return 0;

@@ -141,8 +141,7 @@ class _GroupedConv3x3(torch.autograd.Function):
     """nn.Conv2d(c, c, 3, padding=1, groups=c/4) (ResNeXt cardinality 32 x bottleneck 4, res_unet.py:150-156) on the
     tensor cores: every 64-channel slice of the NHWC tensor is a dense 3x3 implicit GEMM whose weight matrix is
     block-diagonal (16 groups of 4x4).  15/16 of the MACs multiply zeros, but the tcgen05 kernel still runs the layer
-    an order of magnitude faster than a CUDA-core kernel can (5.4 ms -> ~0.5 ms at 32 x 256 x 256 x 128); the weight
-    gradient is the diagonal of the dense 64x64 wgrad blocks."""
+    an order of magnitude faster than a CUDA-core kernel can (5.4 ms -> ~0.5 ms at 32 x 256 x 256 x 128)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -170,13 +169,10 @@ class _GroupedConv3x3(torch.autograd.Function):
                 sl = slice(64 * k, 64 * k + 64)
                 ops.conv3x3_fprop(gy[..., sl], wd[k], 64, out=gx[..., sl])
         if ctx.needs_input_grad[1]:
-            ar = torch.arange(64, device=x.device)
-            blocks = []
-            for k in range(c // 64):
-                sl = slice(64 * k, 64 * k + 64)
-                dw = ops.conv3x3_wgrad(x[..., sl], gy[..., sl])                      # [9, 64 out, 64 in] dense
-                blocks.append(dw.view(9, 64, 16, 4)[:, ar, ar // 4])                # diagonal: [9, 64, 4]
-            gw = torch.cat(blocks, dim=1).permute(1, 2, 0).reshape(c, 4, 3, 3)
+            # weight gradient: the dense 64 x 64 wgrad blocks would spend 16x the MACs on off-diagonal entries that are
+            # thrown away and measured slower (5.1 ms per Res U-Net step) than the direct kernel that only forms the
+            # 4 x 4 group blocks (4.0 ms) -- unlike fprop / dgrad, where the tensor cores win by 10x
+            gw = ops.gconv4_3x3_wgrad(x, gy).view(-1, 3, 3, 4).permute(0, 3, 1, 2).contiguous()
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = ops.colsum(gy).clone()
         return gx, gw, gb
