@@ -74,6 +74,15 @@ int pai_conv4x4_fprop_bnstats(const void* x, int n, int h, int w, int cin, int x
 int pai_convT4x4s2_fprop_bnstats(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
                                  int cout_pad, const float* bias, void* y, int y_ld, int n_tile, float* bn_partials,
                                  int bn_rows, void* stream);
+/* Data gradient of a stride-2 4x4 Conv2d FUSED with the activation backward of the layer below it (PatchGAN blocks,
+ * models/wrapper.py:196-206: Conv -> LeakyReLU):  gx = convT(gy, w) * act'(saved_act)  where saved_act [n, 2h, 2w, cin] is
+ * the stored LeakyReLU / ReLU output of the layer below (its sign is the sign of the pre-activation; slope = 0 for ReLU),
+ * laid out exactly like gx (same gx_ld).  colsum_partials (optional, [rows >= #SMs][2*cin] fp32, zeroed by the caller)
+ * receives per-CTA partial column sums of gx in its first cin entries per row = the bias gradient of the layer below.
+ * Replaces pai_convT4x4s2_fprop + pai_act_bwd (one write and two reads of the gradient tensor less). */
+int pai_conv4x4_dgrad_act(const void* gy, int n, int h, int w, int cout, int gy_ld, const void* w_packed_dgrad, int cin,
+                          int cin_pad, const void* saved_act, float slope, void* gx, int gx_ld, int n_tile,
+                          float* colsum_partials, int rows, void* stream);
 
 /* Weight gradients (autograd of the two modules above).
  * pai_conv4x4_wgrad:   dw[ky*4+kx][co][ci] += sum_{n,oh,ow} gy[n,oh,ow,co] * x[n,stride*oh-1+ky,stride*ow-1+kx,ci]

@@ -271,3 +271,23 @@ def test_bn_statistics_from_the_gemm_epilogue(kind, n, h, w, cin, cout):
     f = ref.float().reshape(-1, cout)
     assert torch.allclose(got[:cout], f.sum(0), rtol=1e-3, atol=5e-2)
     assert torch.allclose(got[cout:], (f * f).sum(0), rtol=1e-3, atol=5e-2)
+
+
+@pytest.mark.parametrize("n,h,w,cout,cin", [(8, 32, 32, 128, 64), (4, 32, 32, 256, 128), (4, 16, 48, 512, 256)])
+def test_dgrad_with_fused_activation_backward(n, h, w, cout, cin):
+    """pai_conv4x4_dgrad_act == pai_convT4x4s2_fprop (data gradient) followed by pai_act_bwd (LeakyReLU backward +
+    bias-gradient column sums) of the layer below; cin = 64 takes the phase-fused tile path."""
+    ops = _ops()
+    gy = _rand((n, h, w, cout), 41)
+    wt = torch.randn(cout, cin, 4, 4, device="cuda") * 0.05          # Conv2d weight of the layer being differentiated
+    wd = ops.pack_convT_weight(wt)                                     # its data-gradient operand
+    saved = F.leaky_relu(_rand((n, 2 * h, 2 * w, cin), 42).float(), 0.2).bfloat16()
+    dh = ops.convT4x4s2_fprop(gy, wd, cin)
+    want = torch.empty_like(dh)
+    want_sums = ops.act_bwd(saved, dh, ops.ACT_LEAKY, None, ops.ACT_NONE, want, slope=0.2)
+    got, part = ops.conv4x4_dgrad_act(gy, wd, cin, saved, slope=0.2, want_colsum=True)
+    # the unfused path rounds the data gradient to bf16 before masking, the fused one masks the fp32 accumulator
+    assert (got.float() - want.float()).abs().max().item() <= 2e-2 * max(1.0, want.float().abs().max().item())
+    assert torch.allclose(part.sum(0)[:cin], want_sums[:cin], rtol=2e-2, atol=0.5)
+    got2, none = ops.conv4x4_dgrad_act(gy, wd, cin, saved, slope=0.2, want_colsum=False)
+    assert none is None and torch.equal(got2, got)

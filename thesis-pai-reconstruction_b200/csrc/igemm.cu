@@ -105,6 +105,30 @@ __device__ __forceinline__ void bias_act_pack(const uint32_t (&v)[64], const flo
     }
 }
 
+// out = acc * (saved > 0 ? 1 : slope): the activation backward of the layer whose data gradient this GEMM produces;
+// mrow = this lane's 64 saved activations (nullptr for rows outside the tensor)
+__device__ __forceinline__ void mask_pack(const uint32_t (&v)[64], const __nv_bfloat16* __restrict__ mrow, float slope,
+                                          uint4* tile, int lane) {
+    uint4 m[8];
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch)
+        m[ch] = mrow != nullptr ? __ldg(reinterpret_cast<const uint4*>(mrow) + ch) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+        const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&m[ch]);
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 mf = __bfloat1622float2(mh[k]);
+            const float a = __uint_as_float(v[8 * ch + 2 * k]) * (mf.x > 0.f ? 1.f : slope);
+            const float b = __uint_as_float(v[8 * ch + 2 * k + 1]) * (mf.y > 0.f ? 1.f : slope);
+            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+            w[k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        tile[lane * 8 + (ch ^ (lane & 7))] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 // =============================================================================================
 // Persistent: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The fp32
 // accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
@@ -300,7 +324,10 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         const long long my_off = which == 0 ? off : off2;
                         const float* bias_c = p.bias != nullptr ? p.bias + col0 + oc : nullptr;
                         // activation / bias dispatch hoisted out of the 64-element loop
-                        if (act == PAI_ACT_LEAKY)
+                        if (p.mask_src != nullptr && which == 0)
+                            mask_pack(v, row_ok ? reinterpret_cast<const __nv_bfloat16*>(p.mask_src) + my_off + coff + oc
+                                                : nullptr, p.mask_slope, tile, lane);
+                        else if (act == PAI_ACT_LEAKY)
                             bias_act_pack<PAI_ACT_LEAKY>(v, bias_c, p.slope, tile, lane);
                         else if (act == PAI_ACT_RELU)
                             bias_act_pack<PAI_ACT_RELU>(v, bias_c, p.slope, tile, lane);
@@ -596,6 +623,12 @@ int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFp
     p.fd_tiles_w = make_fastdiv(p.tiles_w), p.fd_tiles_h = make_fastdiv(p.tiles_h);
     const long long total = (long long)m_tiles * n_tiles * phases * p.splitk;
     const int grid = (int)(total < num_sms ? total : num_sms);
+    if (p.mask_src != nullptr)
+        PAI_REQUIRE(!p.out_f32 && p.splitk == 1 && !p.accumulate && (p.n_tile & 63) == 0 && p.cout % p.n_tile == 0 &&
+                        (p.cout & 7) == 0 && p.bias == nullptr && p.act == PAI_ACT_NONE && p.out2 == nullptr &&
+                        (reinterpret_cast<uintptr_t>(p.mask_src) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0,
+                    "igemm fprop: the fused activation backward needs a plain bf16 output with cout %% 64 == 0 and no "
+                    "split-K (cout=%d n_tile=%d splitk=%d)", p.cout, p.n_tile, p.splitk);
     if (p.bn_part != nullptr) {
         // the statistics ride on the coalesced bf16 epilogue: whole 64-channel chunks, one output, no split-K
         PAI_REQUIRE(!p.out_f32 && p.splitk == 1 && !p.accumulate && (p.n_tile & 63) == 0 && p.cout % p.n_tile == 0 &&

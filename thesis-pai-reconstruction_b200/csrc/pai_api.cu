@@ -221,7 +221,8 @@ int pai_conv4x4_fprop_bnstats(const void* x, int n, int h, int w, int cin, int x
 
 static int convT4x4s2_fprop_impl(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
                                  int cout_pad, const float* bias, int act, float slope, void* y, int y_ld, int y_f32,
-                                 int n_tile, float* splitk_ws, float* bn_part, int bn_rows, void* stream) {
+                                 int n_tile, float* splitk_ws, float* bn_part, int bn_rows, void* stream,
+                                 const void* mask_src = nullptr, float mask_slope = 0.f) {
     PAI_REQUIRE(x && w_packed && y, "pai_convT4x4s2_fprop: null pointer");
     PAI_REQUIRE(cin > 0 && cin % 64 == 0, "pai_convT4x4s2_fprop: cin must be a multiple of 64 (got %d)", cin);
     PAI_REQUIRE(cout_pad % 16 == 0 && cout <= cout_pad, "pai_convT4x4s2_fprop: bad cout %d / cout_pad %d", cout, cout_pad);
@@ -254,6 +255,7 @@ static int convT4x4s2_fprop_impl(const void* x, int n, int h, int w, int cin, in
                 }
     p.b_rows_per_phase = cout_pad;
     p.bn_part = bn_part, p.bn_rows = bn_rows;
+    p.mask_src = mask_src, p.mask_slope = mask_slope;
     const long long wo = 2LL * w;
     const int m_tiles = b.tiles_w * b.tiles_h * b.tiles_n;
     p.splitk = pick_splitk(splitk_ws, 4LL * m_tiles * (cout_pad / n_tile), 4 * (cin / 64));
@@ -304,6 +306,15 @@ int pai_convT4x4s2_fprop_bnstats(const void* x, int n, int h, int w, int cin, in
     PAI_REQUIRE(bn_partials != nullptr && bn_rows > 0, "pai_convT4x4s2_fprop_bnstats: null partial-sum buffer");
     return convT4x4s2_fprop_impl(x, n, h, w, cin, x_ld, w_packed, cout, cout_pad, bias, PAI_ACT_NONE, 0.f, y, y_ld, 0,
                                  n_tile, nullptr, bn_partials, bn_rows, stream);
+}
+
+int pai_conv4x4_dgrad_act(const void* gy, int n, int h, int w, int cout, int gy_ld, const void* w_packed_dgrad, int cin,
+                          int cin_pad, const void* saved_act, float slope, void* gx, int gx_ld, int n_tile,
+                          float* colsum_partials, int rows, void* stream) {
+    PAI_REQUIRE(saved_act != nullptr, "pai_conv4x4_dgrad_act: null saved activation");
+    PAI_REQUIRE(colsum_partials == nullptr || rows > 0, "pai_conv4x4_dgrad_act: bad partial-sum buffer");
+    return convT4x4s2_fprop_impl(gy, n, h, w, cout, gy_ld, w_packed_dgrad, cin, cin_pad, nullptr, PAI_ACT_NONE, 0.f, gx,
+                                 gx_ld, 0, n_tile, nullptr, colsum_partials, rows, stream, saved_act, slope);
 }
 
 // stride: 2 = parity-split taps, 1 = unit-stride 4x4 taps, 0 = pointwise (a single tap at offset 0)

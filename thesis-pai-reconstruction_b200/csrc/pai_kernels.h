@@ -65,6 +65,10 @@ struct IgemmFpropParams {
     // squares of the bf16-rounded outputs it stores to its own row bn_part[blockIdx.x][2 * cout] (zeroed by the caller)
     float* bn_part;
     int bn_rows;
+    // activation backward folded into a data-gradient GEMM (coalesced bf16 path): out = acc * act'(mask_src) with the
+    // LeakyReLU / ReLU derivative taken from the sign of the saved activation at the SAME location as the output element
+    const void* mask_src;
+    float mask_slope;
     int splitk;                // K slices per output tile (>1: partial sums are accumulated into fp32 `out`)
     int accumulate;            // generic fp32 path adds into `out` (red.add) instead of storing
 };

@@ -23,6 +23,7 @@ from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH
 
 BN_EPS, BN_MOMENTUM, SLOPE = 1e-5, 0.1, 0.2
 FUSE_BN_STATS = os.environ.get("PAI_NO_BN_FUSION") is None     # BatchNorm statistics from the GEMM epilogue
+FUSE_ACT_BWD = os.environ.get("PAI_NO_ACT_BWD_FUSION") is None  # PatchGAN LeakyReLU backward in the dgrad GEMM epilogue
 
 
 # ------------------------------------------------------------------------------------------ pack cache
@@ -522,18 +523,30 @@ def disc_backward(spec: DiscSpec, s: _Saved, g_logits: torch.Tensor, need_params
         dwh = ops.pointwise_wgrad(h_last, gcol)[:, :16]                             # [c, 16]
         grads[-1] = dwh.reshape(1, c_last, 4, 4)
     dh = ops.pointwise_gemm(gcol, _head_dgrad_pack(head.weight), c_last, k_valid=16)
+    fused = None                                    # (d_pre, bias-gradient column sums) made by the previous dgrad GEMM
     for k in range(K - 2, -1, -1):
         conv = spec.convs[k]
         hk = s.hs[k]                                # lrelu output: same sign as the pre-activation
         ck = hk.shape[3]
-        d_pre = _bf16(*hk.shape, device=dev)
-        sums = ops.act_bwd(hk, dh, ACT_LEAKY, None, ACT_NONE, d_pre, slope=SLOPE)
+        if fused is not None:
+            d_pre, sums = fused
+            fused = None
+        else:
+            d_pre = _bf16(*hk.shape, device=dev)
+            sums = ops.act_bwd(hk, dh, ACT_LEAKY, None, ACT_NONE, d_pre, slope=SLOPE)
         if k > 0:
             if need_params:
                 grads[2 * k] = ops.wgrad_finish(ops.conv4x4_wgrad(s.hs[k - 1], d_pre, stride=2))
                 dp.allreduce_async(grads[2 * k])
                 grads[2 * k + 1] = sums[:ck].clone()
-            dh = ops.convT4x4s2_fprop(d_pre, _dgrad_pack(conv.weight), s.hs[k - 1].shape[3])
+            cprev = s.hs[k - 1].shape[3]
+            if FUSE_ACT_BWD and ops.bn_fusable(s.hs[k - 1].numel() // cprev, cprev):
+                # the LeakyReLU backward of block k-1 (and its bias gradient) rides on this data-gradient GEMM's epilogue
+                d_next, part = ops.conv4x4_dgrad_act(d_pre, _dgrad_pack(conv.weight), cprev, s.hs[k - 1], slope=SLOPE,
+                                                     want_colsum=need_params)
+                fused = (d_next, part.sum(0) if part is not None else None)
+            else:
+                dh = ops.convT4x4s2_fprop(d_pre, _dgrad_pack(conv.weight), cprev)
         else:
             if need_params:
                 dw0 = ops.pointwise_wgrad(d_pre, s.xycol)                        # [c, 64], column = tap*2 + j

@@ -82,6 +82,8 @@ SIGNATURES = {
                                   c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
     "pai_convT4x4s2_fprop_bnstats": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
                                      c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
+    "pai_conv4x4_dgrad_act": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_float,
+                              c_void_p, c_int, c_int, c_void_p, c_int, c_void_p],
     "pai_bn_finalize_partials": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_float, c_float, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p],
     "pai_wgrad_finish": [c_void_p, c_ll, c_void_p, c_int, c_void_p],

@@ -157,6 +157,21 @@ def convT4x4s2_fprop_bnstats(x, w_packed, cout, bias=None):
     return out, part
 
 
+def conv4x4_dgrad_act(gy, w_packed_dgrad, cin, saved_act, slope=0.2, want_colsum=True):
+    """Data gradient of a stride-2 4x4 convolution fused with the LeakyReLU backward of the layer below:
+    ``gx = convT(gy) * act'(saved_act)`` -> (gx ``[n, 2h, 2w, cin]`` bf16, per-CTA partial column sums or None)."""
+    n, h, w, cout, ld = _nhwc(gy)
+    cp = w_packed_dgrad.shape[1]
+    sn, sh, sw, sc, sld = _nhwc(saved_act)
+    assert (sn, sh, sw, sc) == (n, 2 * h, 2 * w, cin) and sld == cin
+    out = torch.empty(n, 2 * h, 2 * w, cin, dtype=torch.bfloat16, device=gy.device)
+    part = torch.zeros(BN_PART_ROWS, 2 * cin, dtype=torch.float32, device=gy.device) if want_colsum else None
+    _igemm_call("pai_conv4x4_dgrad_act", 2.0 * n * h * w * cin * 16 * cout, _ptr(gy), n, h, w, cout, ld,
+                _ptr(w_packed_dgrad), cin, cp, _ptr(saved_act), float(slope), _ptr(out), cin, 0, _ptr(part), BN_PART_ROWS,
+                _stream())
+    return out, part
+
+
 def convT4x4s2_fprop(x, w_packed, cout, bias=None, act=ACT_NONE, slope=0.2, out=None, out_f32=False, n_tile=0):
     n, h, w, cin, ld = _nhwc(x)
     cp = w_packed.shape[1]
