@@ -131,9 +131,10 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, long long m, 
                                    const float* __restrict__ beta, float eps, float momentum, int training,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ ss, int nparts) {
-    // block = 32 channels x 8 row groups: the partial rows are summed by 8 threads per channel (coalesced 128-byte
-    // loads), then thread row 0 finishes the channel
-    __shared__ float red_s[8][32], red_q[8][32];
+    // block = 32 channels x 32 row groups: the partial rows are summed by 32 threads per channel (coalesced 128-byte
+    // loads, 5 rows each for the 160 per-CTA rows of the fused statistics), then thread row 0 finishes the channel
+    constexpr int RG = 32;
+    __shared__ float red_s[RG][32], red_q[RG][32];
     const int chl = threadIdx.x & 31, rg = threadIdx.x >> 5;
     const int ch = blockIdx.x * 32 + chl;
     float mean, var;
@@ -141,7 +142,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, long long m, 
         // nparts > 1: per-CTA partial sums written by the implicit-GEMM epilogue (pai_conv4x4_fprop_bnstats)
         float s = 0.f, q = 0.f;
         if (ch < c)
-            for (int r = rg; r < nparts; r += 8) {
+            for (int r = rg; r < nparts; r += RG) {
                 s += sums[(size_t)r * 2 * c + ch];
                 q += sums[(size_t)r * 2 * c + c + ch];
             }
@@ -150,7 +151,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, long long m, 
         __syncthreads();
         if (rg != 0 || ch >= c) return;
 #pragma unroll
-        for (int r = 1; r < 8; ++r) {
+        for (int r = 1; r < RG; ++r) {
             s += red_s[r][chl];
             q += red_q[r][chl];
         }
@@ -421,8 +422,8 @@ int pai_bn_finalize_partials(const float* sums, int nparts, long long m, int c, 
                              float* scale_shift, void* stream) {
     PAI_REQUIRE(scale_shift && (training ? (sums != nullptr && nparts >= 1) : (running_mean && running_var)),
                 "pai_bn_finalize: null pointer");
-    bn_finalize_kernel<<<(c + 31) / 32, 256, 0, (cudaStream_t)stream>>>(sums, m, c, gamma, beta, eps, momentum, training,
-                                                                        running_mean, running_var, scale_shift, nparts);
+    bn_finalize_kernel<<<(c + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(sums, m, c, gamma, beta, eps, momentum, training,
+                                                                         running_mean, running_var, scale_shift, nparts);
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }
