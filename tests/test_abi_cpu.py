@@ -80,3 +80,35 @@ def test_dropin_package_mirrors_reference_interface():
         assert hasattr(mw.UnetWrapper, meth)
     m = mp.Pix2Pix(1, 1, dropout=0.0, loss_type="ssim")
     assert mu.get_parameter_count(m.unet) == 54_413_313 and m.discriminator is None
+
+
+def test_new_entry_points_validate_arguments_without_gpu(so):
+    """Argument validation of the entry points added for the fused step happens before any CUDA call."""
+    so.pai_last_error.restype = ctypes.c_char_p
+    f32 = ctypes.c_float
+    rc = so.pai_conv4x4_dgrad_act(ctypes.c_void_p(16), 1, 8, 8, 128, 128, ctypes.c_void_p(16), 64, 64, None, f32(0.2),
+                                  ctypes.c_void_p(16), 64, 0, None, 0, None)
+    assert rc != 0 and b"saved activation" in so.pai_last_error()
+    rc = so.pai_conv4x4_fprop_bnstats(ctypes.c_void_p(16), 1, 8, 8, 64, 64, ctypes.c_void_p(16), 64, 64, 2, None,
+                                      ctypes.c_void_p(16), 64, 0, None, 0, None)
+    assert rc != 0 and b"partial-sum buffer" in so.pai_last_error()
+    rc = so.pai_wgrad_finish(None, ctypes.c_longlong(16), ctypes.c_void_p(16), 0, None)
+    assert rc != 0 and b"pai_wgrad_finish" in so.pai_last_error()
+    rc = so.pai_check_conv2d_f32(None, 1, 1, 8, 8, ctypes.c_void_p(16), 1, 4, 2, 1, None, 0, f32(0.2), 0,
+                                 ctypes.c_void_p(16), None)
+    assert rc != 0 and b"null pointer" in so.pai_last_error()
+    rc = so.pai_pointwise_gemm(ctypes.c_void_p(16), ctypes.c_longlong(128), 128, 128, ctypes.c_void_p(16), 64, 64, None, 0,
+                               f32(0.2), ctypes.c_void_p(16), 64, 0, None, 0, 0, 0, 16, None)
+    assert rc != 0 and b"k_valid" in so.pai_last_error()       # k_valid needs cin == 64
+    rc = so.pai_adam_prepare(None, f32(2e-4), f32(0.5), f32(0.999), None, None)
+    assert rc != 0 and b"pai_adam_prepare" in so.pai_last_error()
+
+
+def test_step_graph_and_check_path_are_exposed_on_the_dropin():
+    import models.wrapper as mw
+    from pai_b200 import engine, graph
+    assert hasattr(mw.UnetWrapper, "enable_step_graph") and hasattr(mw.UnetWrapper, "disable_step_graph")
+    assert callable(graph.StepGraph) and not engine.check_path_enabled()
+    with engine.check_path():
+        assert engine.check_path_enabled()
+    assert not engine.check_path_enabled()
