@@ -291,3 +291,23 @@ def test_dgrad_with_fused_activation_backward(n, h, w, cout, cin):
     assert torch.allclose(part.sum(0)[:cin], want_sums[:cin], rtol=2e-2, atol=0.5)
     got2, none = ops.conv4x4_dgrad_act(gy, wd, cin, saved, slope=0.2, want_colsum=False)
     assert none is None and torch.equal(got2, got)
+
+
+def test_dropout2d_layer_node_scales_whole_channels():
+    """layers.dropout2d (Attention / Res U-Net decoders): train mode zeroes whole (sample, channel) planes with
+    probability p and scales the rest by 1 / (1 - p), the backward applies the same mask; eval mode is the identity."""
+    from pai_b200 import layers as L
+    torch.manual_seed(0)
+    x = _rand((4, 8, 8, 64), 51).requires_grad_(True)
+    mod = torch.nn.Dropout2d(0.5).train()
+    y = L.dropout2d(x, mod)
+    ratio = (y.float() / x.detach().float()).reshape(4, 64, 64)            # [n, pixels, c]
+    per_plane = ratio.mean(1)
+    assert torch.all((per_plane.abs() < 1e-6) | ((per_plane - 2.0).abs() < 2e-2)), per_plane
+    kept = per_plane.abs() > 1e-6
+    assert 0.2 < kept.float().mean().item() < 0.8
+    assert torch.all((ratio - per_plane[:, None, :]).abs() < 2e-2)          # one factor per (sample, channel)
+    y.backward(torch.ones_like(y))
+    g = x.grad.float().reshape(4, 64, 64).mean(1)
+    assert torch.allclose(g, per_plane.round(), atol=1e-2)
+    assert L.dropout2d(x, mod.eval()) is x
