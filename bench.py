@@ -372,11 +372,17 @@ def run_ours(args):
 
     # ---- the timed regions run the step as one replayed CUDA graph (model.enable_step_graph(), the public opt-in)
     graphed = not args.no_graph
+    graph_note = None
     if graphed:
-        model.enable_step_graph(warmup=1)
-        for i in range(3):
-            step_resident(i)
-        torch.cuda.synchronize()
+        try:
+            model.enable_step_graph(warmup=1)
+            for i in range(3):
+                step_resident(i)
+            torch.cuda.synchronize()
+        except Exception as ex:  # pragma: no cover  (never seen; the eager path is the same kernels)
+            model.disable_step_graph()
+            graphed, graph_note = False, f"graph capture failed, eager launches timed: {type(ex).__name__}: {ex}"[:200]
+            torch.cuda.synchronize()
         model.logged.clear()
 
     # ---- timed region 1: inputs resident in HBM
@@ -462,7 +468,7 @@ def run_ours(args):
                    "batch_per_gpu": B, "global_batch": B * world, "image": "1x256x256", "loss_type": "gan",
                    "parallelism": f"dp{world}", "precision": "bf16 operands, fp32 accumulate, fp32 master weights",
                    "launch": ("whole training step replayed as one CUDA graph (model.enable_step_graph()); eager launches: "
-                              f"{eager_ms_step:.3f} ms/step" if graphed else "eager launches"),
+                              f"{eager_ms_step:.3f} ms/step" if graphed else (graph_note or "eager launches")),
                    "l2_policy": "per-step working set (activations + weights > 2 GB) is larger than the 126 MB L2; "
                                 "4 distinct input batches are cycled"},
         "clocks": clocks, "gpu_launches": launches,
