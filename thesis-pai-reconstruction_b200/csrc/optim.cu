@@ -61,8 +61,8 @@ adam_pack_conv4x4_kernel(float* __restrict__ w, const float* __restrict__ g, flo
     const int a0 = blockIdx.y * kTA, b0 = blockIdx.x * kTB;
     const int tid = threadIdx.x;
     // ---- pass 1: float4 = 4 taps of one (a, b); a row of the tile is 32 b x 16 taps = 128 float4
-    // (two iterations = 8 independent 16-byte loads in flight per thread)
-#pragma unroll 2
+    // (four iterations = 16 independent 16-byte loads in flight per thread)
+#pragma unroll 4
     for (int i = tid; i < kTA * 128; i += kPackThreads) {
         const int al = i >> 7, r = i & 127, bl = r >> 2, t4 = (r & 3) * 4;
         const int a = a0 + al, b = b0 + bl;
