@@ -10,6 +10,14 @@ Data layout in HBM: activations and gradients NHWC bf16; every decoder input is 
 ``[N, h, w, 2C]`` whose first half is written by the previous decoder's BN+ReLU kernel and whose second
 half is written by the matching encoder's BN kernel (zero-copy ``torch.cat``).  Parameters stay fp32 in
 the reference's ``state_dict`` layout; bf16 GEMM packs are rebuilt when a parameter's version changes.
+
+What rides on the GEMM epilogues (switchable for A/B measurements by the environment variables in brackets):
+* BatchNorm statistics of every layer large enough not to be split along K: per-CTA partial rows from
+  ``conv4x4_fprop_bnstats`` / ``convT4x4s2_fprop_bnstats``, summed by ``bn_finalize``  [PAI_NO_BN_FUSION];
+* the LeakyReLU backward and the bias gradient of the PatchGAN blocks: ``conv4x4_dgrad_act``  [PAI_NO_ACT_BWD_FUSION];
+* bias, activation, second (skip) output and sub-pixel phase placement (always).
+Train-mode Dropout2d (decoders 0-2 of the default constructor) is a per-(sample, channel) mask applied to the concat
+slot; ``check_path()`` switches the forward to the exact fp32 kernels of csrc/check_f32.cu.
 """
 from __future__ import annotations
 
