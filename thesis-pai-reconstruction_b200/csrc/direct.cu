@@ -312,11 +312,13 @@ int pai_smallc_conv_fprop(const float* plane0, const float* plane1, int cin, int
     PAI_REQUIRE(smem <= 96 * 1024, "pai_smallc_conv_fprop: weights do not fit shared memory (c=%d)", c);
     PAI_REQUIRE((stride == 2 && !flip) || (stride == 1 && flip),
                 "pai_smallc_conv_fprop: supported geometries are (stride 2, flip 0) and (stride 1, flip 1)");
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr_once;
+    const int attr_dev = current_device();
+    if (attr_dev < 0) return -1;
+    if (attr_once.need(attr_dev)) {
         PAI_CUDA_OK(cudaFuncSetAttribute(smallc_fprop_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         PAI_CUDA_OK(cudaFuncSetAttribute(smallc_fprop_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr = true;
+        attr_once.mark(attr_dev);
     }
     SmallConvGeom g{n, ih, iw, oh, ow, stride, flip, cin, c};
     PAI_REQUIRE((long long)n * oh * ow * (c / 8) < (1LL << 31), "pai_smallc_conv_fprop: tensor too large");
@@ -340,10 +342,12 @@ int pai_smallc_conv_wgrad(const void* a, int lda, int c, const float* plane0, co
     PAI_REQUIRE(c > 0 && c % 8 == 0 && lda % 8 == 0 && cv * 4 <= kDcThreads && kDcThreads % (cv * 4) == 0,
                 "pai_smallc_conv_wgrad: c=%d must be a multiple of 8 with (c/2) | 256", c);
     const size_t smem = sizeof(float) * kDcThreads * 32 * cin;
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr_once;
+    const int attr_dev = current_device();
+    if (attr_dev < 0) return -1;
+    if (attr_once.need(attr_dev)) {
         PAI_CUDA_OK(cudaFuncSetAttribute(smallc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr = true;
+        attr_once.mark(attr_dev);
     }
     SmallConvGeom g{n, ih, iw, oh, ow, stride, flip, cin, c};
     PAI_REQUIRE((long long)n * oh * ow < (1LL << 30), "pai_smallc_conv_wgrad: tensor too large");

@@ -609,14 +609,12 @@ int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFp
     p.m_tiles = m_tiles, p.n_tiles = n_tiles, p.phases = phases;
     if (p.kmma <= 0 || p.kmma > 4) p.kmma = 4;
     const size_t smem = stage_bytes * p.stages + 1024;
-    static bool attr_done = false;
-    static int num_sms = 148;
-    if (!attr_done) {
+    static DeviceOnce once;
+    const int dev = current_device(), num_sms = sm_count(dev);
+    if (num_sms < 0) return -1;
+    if (once.need(dev)) {
         PAI_CUDA_OK(cudaFuncSetAttribute(igemm_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 194 * 1024));
-        int dev = 0;
-        PAI_CUDA_OK(cudaGetDevice(&dev));
-        PAI_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_done = true;
+        once.mark(dev);
     }
     if (p.splitk < 1) p.splitk = 1;
     p.fd_splitk = make_fastdiv(p.splitk), p.fd_n_tiles = make_fastdiv(n_tiles), p.fd_m_tiles = make_fastdiv(m_tiles);
@@ -662,7 +660,9 @@ int launch_splitk_finish(const float* ws, long long pixels, int cout, const floa
                          int y_ld, int y_f32, cudaStream_t stream) {
     const long long total = pixels * cout;
     long long blocks = (total + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    const int sms = sm_count(current_device());
+    if (sms < 0) return -1;
+    if (blocks > sms * 8) blocks = sms * 8;
     splitk_finish_kernel<<<(int)blocks, 256, 0, stream>>>(ws, total, cout, bias, act, slope, y, y_ld, y_f32);
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
@@ -672,14 +672,12 @@ int launch_igemm_wgrad(const CUtensorMap& tm_u, const CUtensorMap& tm_s, IgemmWg
     const size_t stage_bytes = (size_t)(2 * p.mb + p.nbt) * 8192;
     p.stages = pick_stages(stage_bytes, 196 * 1024);
     const size_t smem = stage_bytes * p.stages + 1024;
-    static bool attr_done = false;
-    static int num_sms = 148;
-    if (!attr_done) {
+    static DeviceOnce once;
+    const int dev = current_device(), num_sms = sm_count(dev);
+    if (num_sms < 0) return -1;
+    if (once.need(dev)) {
         PAI_CUDA_OK(cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        int dev = 0;
-        PAI_CUDA_OK(cudaGetDevice(&dev));
-        PAI_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-        attr_done = true;
+        once.mark(dev);
     }
     const long long units = (long long)p.tiles * p.kblocks;
     // at least ~4 k-blocks per CTA so the pipeline fill / accumulator flush is amortised

@@ -623,10 +623,12 @@ int pai_gconv4_3x3_fprop(const void* x, int n, int h, int w, int c, int ldx, con
                          int ldy, void* stream) {
     PAI_REQUIRE(x && wt && y && n > 0, "pai_gconv4_3x3_fprop: null pointer");
     PAI_REQUIRE(v8_ok(c, x, ldx) && v8_ok(c, y, ldy) && c * 36 * 4 <= 96 * 1024, "pai_gconv4_3x3_fprop: bad channels / alignment");
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr_once;
+    const int attr_dev = current_device();
+    if (attr_dev < 0) return -1;
+    if (attr_once.need(attr_dev)) {
         PAI_CUDA_OK(cudaFuncSetAttribute(gconv4_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr = true;
+        attr_once.mark(attr_dev);
     }
     gconv4_fprop_kernel<<<ly_grid((long long)n * h * w * (c / 8)), kLyThreads, c * 36 * sizeof(float), (cudaStream_t)stream>>>(
         (const bf16*)x, n, h, w, c, ldx, wt, bias, (bf16*)y, ldy);

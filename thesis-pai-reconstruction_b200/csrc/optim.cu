@@ -193,11 +193,13 @@ int pai_adam_pack_conv4x4(float* w, const float* grad, float* exp_avg, float* ex
                     (reinterpret_cast<uintptr_t>(pack1) & 15) == 0 && (reinterpret_cast<uintptr_t>(pack2) & 15) == 0,
                 "pai_adam_pack_conv4x4: pointers must be 16 B aligned");
     PAI_REQUIRE(pack2 == nullptr || b_pad >= b, "pai_adam_pack_conv4x4: b_pad %d < b %d", b_pad, b);
-    static bool attr = false;
+    static DeviceOnce attr_once;
+    const int attr_dev = current_device();
+    if (attr_dev < 0) return -1;
     const int smem = 2 * 16 * kTA * kTB * (int)sizeof(__nv_bfloat16);
-    if (!attr) {
+    if (attr_once.need(attr_dev)) {
         PAI_CUDA_OK(cudaFuncSetAttribute(adam_pack_conv4x4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
+        attr_once.mark(attr_dev);
     }
     AdamHyper hy = {1.f - beta1, beta2, 1.f - beta2, step_size, inv_bias_correction2_sqrt, eps};
     dim3 grid((b + kTB - 1) / kTB, (a + kTA - 1) / kTA);

@@ -26,6 +26,30 @@ int cuda_fail(cudaError_t e, const char* what) {
     return -1;
 }
 
+int current_device() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaGetDevice");
+        return -1;
+    }
+    return dev;
+}
+
+int sm_count(int dev) {
+    static int cached[64] = {0};
+    if (dev < 0) return -1;
+    int v = __atomic_load_n(&cached[dev & 63], __ATOMIC_ACQUIRE);
+    if (v > 0) return v;
+    cudaError_t e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess || v <= 0) {
+        cuda_fail(e, "cudaDeviceGetAttribute(MultiProcessorCount)");
+        return -1;
+    }
+    __atomic_store_n(&cached[dev & 63], v, __ATOMIC_RELEASE);
+    return v;
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (fn == nullptr) {

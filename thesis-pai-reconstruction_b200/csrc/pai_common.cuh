@@ -26,6 +26,17 @@ int cuda_fail(cudaError_t e, const char* what);
         }                                                                   \
     } while (0)
 
+// Per-device one-time set-up (cudaFuncSetAttribute opt-ins, constant uploads): the library may serve several GPUs of
+// one process from several threads, so "done" is a bit per device ordinal, set after the (idempotent) set-up ran.
+struct DeviceOnce {
+    unsigned long long mask = 0;
+    bool need(int dev) const { return ((__atomic_load_n(&mask, __ATOMIC_ACQUIRE) >> (dev & 63)) & 1ull) == 0; }
+    void mark(int dev) { __atomic_fetch_or(&mask, 1ull << (dev & 63), __ATOMIC_RELEASE); }
+};
+// Current device ordinal and its SM count (cached per device); negative on a CUDA error (pai_last_error is set).
+int current_device();
+int sm_count(int dev);
+
 // Encodes a bf16 tiled tensor map (rank <= 5, SWIZZLE_128B, zero OOB fill) through the driver
 // entry point fetched at run time, so the library loads on a box without libcuda.
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,

@@ -47,11 +47,13 @@ static Gauss host_gauss() {
     return k;
 }
 static int upload_gauss() {
-    static bool done = false;
-    if (!done) {
+    static DeviceOnce done_once;
+    const int done_dev = current_device();
+    if (done_dev < 0) return -1;
+    if (done_once.need(done_dev)) {
         Gauss k = host_gauss();
         PAI_CUDA_OK(cudaMemcpyToSymbol(c_gauss, k.g, sizeof(k.g)));
-        done = true;
+        done_once.mark(done_dev);
     }
     return 0;
 }
@@ -574,11 +576,13 @@ ssim_fwd_rows_kernel(const T* __restrict__ pred, const T* __restrict__ target, i
 template <typename T, bool DENORM, bool FULL>
 static int launch(const void* pred, const void* target, int n, int h, int band_rows, float* ssim_sum,
                   float* band_sum, float* sse, float* full_map, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr_once;
+    const int attr_dev = current_device();
+    if (attr_dev < 0) return -1;
+    if (attr_once.need(attr_dev)) {
         PAI_CUDA_OK(cudaFuncSetAttribute(ssim_fwd_rows_kernel<T, DENORM, FULL>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<T>()));
-        attr = true;
+        attr_once.mark(attr_dev);
     }
     const int out_rows = FULL ? h : h - 10;
     // enough CTAs for two resident per SM with a few waves; chunks are whole 8-row batches
@@ -864,11 +868,13 @@ ssim_fwd_stream_kernel(const T* __restrict__ pred, const T* __restrict__ target,
 template <typename T, bool DENORM>
 static int launch(const void* pred, const void* target, int n, int h, int band_rows, float* ssim_sum, float* band_sum,
                   float* sse, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr_once;
+    const int attr_dev = current_device();
+    if (attr_dev < 0) return -1;
+    if (attr_once.need(attr_dev)) {
         PAI_CUDA_OK(cudaFuncSetAttribute(ssim_fwd_stream_kernel<T, DENORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem_bytes<T>()));
-        attr = true;
+        attr_once.mark(attr_dev);
     }
     int dev = 0, sms = 148;
     PAI_CUDA_OK(cudaGetDevice(&dev));
@@ -891,11 +897,13 @@ static bool eligible(int n, int h, int w, int band_rows, const void* full_map) {
 template <typename T, bool DENORM>
 static int fwd_launch(const void* pred, const void* target, int n, int h, int w, int band_rows, float* ssim_sum,
                       float* band_sum, float* sse, float* full_map, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr_once;
+    const int attr_dev = current_device();
+    if (attr_dev < 0) return -1;
+    if (attr_once.need(attr_dev)) {
         PAI_CUDA_OK(cudaFuncSetAttribute(ssim_fwd_kernel<T, DENORM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kSsimSmem));
-        attr = true;
+        attr_once.mark(attr_dev);
     }
     dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH, n);
     ssim_fwd_kernel<T, DENORM><<<grid, kSsimThreads, kSsimSmem, st>>>(
@@ -907,13 +915,15 @@ static int fwd_launch(const void* pred, const void* target, int n, int h, int w,
 template <typename T, bool DENORM>
 static int bwd_launch(const void* pred, const void* target, int n, int h, int w, const float* g_ssim,
                       const float* g_sse, float4* coef, void* grad, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr_once;
+    const int attr_dev = current_device();
+    if (attr_dev < 0) return -1;
+    if (attr_once.need(attr_dev)) {
         PAI_CUDA_OK(cudaFuncSetAttribute(ssim_bwd_coef_kernel<T, DENORM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSsimSmem));
         PAI_CUDA_OK(cudaFuncSetAttribute(ssim_bwd_apply_kernel<T, DENORM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSsimSmem));
-        attr = true;
+        attr_once.mark(attr_dev);
     }
     dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH, n);
     ssim_bwd_coef_kernel<T, DENORM><<<grid, kSsimThreads, kSsimSmem, st>>>((const T*)pred, (const T*)target, h, w,

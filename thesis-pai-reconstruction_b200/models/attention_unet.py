@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from pai_b200 import layers as L
+from pai_b200 import layers as L, lib
 
 from .pix2pix import DecoderBlock, EncoderBlock
 from .wrapper import UnetWrapper
@@ -113,6 +113,10 @@ class AttentionUnet(nn.Module):
         return L.dropout2d(L.batchnorm_act(raw, seq[2], L.ACT_NONE), seq[3])
 
     def forward(self, x):
+        with lib.on_device(x):
+            return self._forward(x)
+
+    def _forward(self, x):
         n, _, hh, ww = x.shape
         depth = len(self.encoders)
         if hh % (1 << depth) or ww % (1 << depth):

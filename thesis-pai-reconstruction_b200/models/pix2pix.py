@@ -7,7 +7,7 @@ from typing import Literal, Sequence
 import torch
 import torch.nn as nn
 
-from pai_b200 import engine
+from pai_b200 import engine, lib
 
 from .wrapper import UnetWrapper
 
@@ -100,6 +100,10 @@ class Unet(nn.Module):
         return self._spec
 
     def forward(self, x):
+        with lib.on_device(x):
+            return self._forward(x)
+
+    def _forward(self, x):
         spec = self._engine_spec()
         if engine.check_path_enabled():
             return engine.unet_forward_check(spec, x, self.training)

@@ -14,7 +14,7 @@ from typing import Literal, Sequence
 import torch
 import torch.nn as nn
 
-from pai_b200 import layers as L
+from pai_b200 import layers as L, lib
 
 from .wrapper import UnetWrapper
 
@@ -235,6 +235,10 @@ class ResUnet(nn.Module):
         self.out = nn.Sequential(nn.Conv2d(widths[0], out_channels, kernel_size=3, padding=1), nn.Tanh())
 
     def forward(self, x):
+        with lib.on_device(x):
+            return self._forward(x)
+
+    def _forward(self, x):
         n, _, hh, ww = x.shape
         depth = len(self.encoders)
         if hh % (1 << depth) or ww % (1 << depth):

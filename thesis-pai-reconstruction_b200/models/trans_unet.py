@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 from einops.layers.torch import Rearrange
 
-from pai_b200 import layers as L
+from pai_b200 import layers as L, lib
 
 from .wrapper import UnetWrapper
 
@@ -174,6 +174,10 @@ class TransUnet(nn.Module):
         self.out = nn.Sequential(nn.Conv2d(64, out_channels, kernel_size=3, padding=1), nn.Tanh())
 
     def forward(self, x):
+        with lib.on_device(x):
+            return self._forward(x)
+
+    def _forward(self, x):
         n, _, hh, ww = x.shape
         h = L.conv_in(L.to_plane(x), self.in_conv)
         skips = []

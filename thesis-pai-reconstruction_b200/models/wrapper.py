@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from pai_b200 import dp, engine, metrics
+from pai_b200 import dp, engine, lib, metrics
 from pai_b200.optim import FusedAdam
 
 from ._lightning import LightningModule
@@ -26,7 +26,13 @@ _ADAM = dict(lr=2e-4, betas=(0.5, 0.999), eps=1e-7)        # wrapper.py:98-111
 class UnetWrapper(LightningModule):
     """U-net wrapper with the five reference loss types: "gan", "ssim", "psnr", "ssim+psnr", "mse"."""
 
-    def __init__(self, unet: nn.Module, loss_type: Literal["gan", "ssim", "psnr", "ssim+psnr", "mse"] = "gan"):
+    def __init__(self, unet: nn.Module, loss_type: Literal["gan", "ssim", "psnr", "ssim+psnr", "mse"] = "gan",
+                 discriminator_in_channels: int = None):
+        """``discriminator_in_channels`` is the one addition to the reference signature (wrapper.py:21-25): the
+        reference always builds ``Discriminator()`` = 3 channels per image (wrapper.py:34), which cannot run on the
+        1-channel models main.py constructs (its first conv wants 6 planes, cat([x, y]) has 2).  ``None``
+        keeps that behaviour bit for bit (same RNG consumption, same state_dict); pass 1 to get a working grayscale GAN
+        without swapping ``self.discriminator`` by hand."""
         super().__init__()
         self.automatic_optimization = False
         self.unet = unet
@@ -34,7 +40,8 @@ class UnetWrapper(LightningModule):
         self.discriminator = None
         if loss_type == "gan":
             # same construction order as the reference so a shared seed gives identical weights
-            self.discriminator = Discriminator()
+            self.discriminator = (Discriminator() if discriminator_in_channels is None
+                                  else Discriminator(in_channels=discriminator_in_channels))
             self.discriminator.apply(init_weights)
         self.unet.apply(init_weights)
 
@@ -90,9 +97,20 @@ class UnetWrapper(LightningModule):
 
     def training_step(self, batch, batch_idx):
         runner = self.__dict__.get("_pai_step_graph")
-        if runner is not None:
-            return runner(batch, batch_idx)
-        return self._training_step_eager(batch, batch_idx)
+        with lib.on_device(batch[0]):
+            if runner is not None:
+                return runner(batch, batch_idx)
+            return self._training_step_eager(batch, batch_idx)
+
+    def _pai_log(self, name, value):
+        """``self.log`` -- except while pai_b200.graph.StepGraph captures the step: then the (static) tensor is handed
+        to the capture, which logs a clone after every replay.  Nothing here depends on the fallback shim: under real
+        pytorch_lightning ``self.log`` would call into the Trainer, which must not happen on a capturing stream."""
+        sink = self.__dict__.get("_pai_log_sink")
+        if sink is not None:
+            sink.append((name, value.detach()))
+        else:
+            self.log(name, value, prog_bar=True)
 
     def _training_step_eager(self, batch, batch_idx):
         x, target = batch
@@ -103,7 +121,7 @@ class UnetWrapper(LightningModule):
             target_label = self.discriminator(x, target)
             pred_label = self.discriminator(x, pred)
             d_loss = self.discriminator_loss(pred_label, target_label)
-            self.log("d_loss", d_loss, prog_bar=True)
+            self._pai_log("d_loss", d_loss)
             self.discriminator.zero_grad(set_to_none=True)
             self.manual_backward(d_loss)
             opt_d.step()
@@ -124,10 +142,10 @@ class UnetWrapper(LightningModule):
             loss = -(30 * s + p)
         else:
             loss = self.loss(x, pred, target)
-        self.log("loss", loss, prog_bar=True)
-        self.log("train_ssim", s, prog_bar=True)
-        self.log("train_psnr", p, prog_bar=True)
-        self.log("train_rmse", r, prog_bar=True)
+        self._pai_log("loss", loss)
+        self._pai_log("train_ssim", s)
+        self._pai_log("train_psnr", p)
+        self._pai_log("train_rmse", r)
         self.unet.zero_grad(set_to_none=True)
         self.manual_backward(loss)
         opt_g.step()
@@ -182,6 +200,10 @@ class Discriminator(nn.Module):
         return self._spec
 
     def forward(self, x, y):
+        with lib.on_device(x):
+            return self._forward(x, y)
+
+    def _forward(self, x, y):
         spec = self._engine_spec()
         if engine.check_path_enabled():
             return engine.disc_forward_check(spec, x, y)

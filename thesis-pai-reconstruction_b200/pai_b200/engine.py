@@ -455,14 +455,22 @@ class UnetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, spec: UnetSpec, training: bool, x: torch.Tensor, *params):
         need = any(ctx.needs_input_grad[3:])
+        if ctx.needs_input_grad[2]:
+            raise RuntimeError("pai_b200: the fused generator node has no gradient w.r.t. its input image "
+                               "(the reference never asks for one, models/wrapper.py:117-162); detach x")
         y, saved = unet_forward(spec, x, training, save=need)
-        ctx.spec, ctx.saved = spec, saved
+        ctx.spec, ctx.saved, ctx.training = spec, saved, training
         return y
 
     @staticmethod
     def backward(ctx, grad_y):
         if ctx.saved is None:
             raise RuntimeError("pai_b200: generator backward requested but the forward ran without a graph")
+        if not ctx.training and any(b is not None for b in ctx.spec.enc_bns + ctx.spec.dec_bns):
+            # the fused backward implements the TRAIN-mode BatchNorm backward (batch-statistic terms); with running
+            # statistics the gradient is a different formula -- refuse instead of returning wrong numbers
+            raise RuntimeError("pai_b200: gradients through an eval-mode BatchNorm generator are not implemented "
+                               "(the reference only differentiates in train mode, models/wrapper.py:117-162)")
         grads = unet_backward(ctx.spec, ctx.saved, grad_y)
         ctx.saved = None
         need = ctx.needs_input_grad[3:]
@@ -574,6 +582,9 @@ class DiscFunction(torch.autograd.Function):
     def forward(ctx, spec: DiscSpec, x, y, *params):
         need_params = any(ctx.needs_input_grad[3:])
         need_y = ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1]:
+            raise RuntimeError("pai_b200: the fused PatchGAN node has no gradient w.r.t. its first (conditioning) input "
+                               "x (models/wrapper.py:126-128,147 only differentiate w.r.t. the prediction y); detach x")
         logits, saved = disc_forward(spec, x, y, save=need_params or need_y)
         ctx.spec, ctx.saved, ctx.need_params, ctx.need_y = spec, saved, need_params, need_y
         return logits

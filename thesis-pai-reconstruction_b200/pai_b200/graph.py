@@ -60,23 +60,37 @@ class StepGraph:
                     sig.append(st["exp_avg"].data_ptr())
         return tuple(sig)
 
+    def _drop_lazy_packs(self):
+        """Forgets every weight pack that the optimizer does NOT refresh in place (thin-layer / auxiliary packs and
+        all packs of the layer-node models): FusedAdam drops them after each update and the next forward rebuilds
+        them.  A pack built eagerly before the capture would be baked into the graph as a pointer to memory that the
+        captured optimizer step releases -- the replays would read weights frozen at capture time (or freed memory).
+        Dropping them first makes the capture rebuild each of them INSIDE the graph, from the live parameters, into
+        graph-pool memory, at every replay."""
+        from . import engine
+        for p in self.module.parameters():
+            p.__dict__.pop("_pai_aux", None)
+            if p.__dict__.get("_pai_packs") and engine.fused_pack_targets(p) is None:
+                p.__dict__.pop("_pai_packs", None)
+
     def _capture(self, ent: _Entry, x, target, batch_idx):
         m = self.module
         ent.static_x, ent.static_t = x.clone(), target.clone()
+        self._drop_lazy_packs()
         ent.signature = self._signature()
         torch.cuda.synchronize()
-        saved_log, m.logged = m.logged, {}
+        sink = []
+        m.__dict__["_pai_log_sink"] = sink           # _training_step_eager logs into it instead of calling self.log
         launches0 = lib.launches
         graph = torch.cuda.CUDAGraph()
         try:
             with torch.cuda.graph(graph):
                 m._training_step_eager((ent.static_x, ent.static_t), batch_idx)
-            captured = m.logged
         finally:
-            m.logged = saved_log
+            m.__dict__.pop("_pai_log_sink", None)
         ent.launches = lib.launches - launches0
         lib.launches = launches0                     # nothing ran during capture
-        ent.outputs = [(k, v) for k, vals in captured.items() for v in vals]
+        ent.outputs = list(sink)
         ent.graph = graph
         if self._signature() != ent.signature:       # e.g. a pack built for the first time inside the capture
             ent.signature = self._signature()
@@ -102,6 +116,6 @@ class StepGraph:
         ent.graph.replay()
         self.replays += 1
         lib.launches += ent.launches
-        for name, v in ent.outputs:
+        for name, v in ent.outputs:               # static graph outputs -> the module's own log (Lightning's or the shim's)
             m.log(name, v.clone(), prog_bar=True)
         return None

@@ -4,6 +4,7 @@ There is no fallback: if the shared library is missing or a call fails, a Runtim
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import os
 
@@ -122,6 +123,13 @@ def load() -> ctypes.CDLL:
             fn.restype = res
         _lib = lib
     return _lib
+
+
+def on_device(t):
+    """Context manager: make ``t``'s GPU the current device (kernels are enqueued on the *current* device's
+    current stream and the library keeps per-device state), so a model on cuda:1 works after cuda:0 was used."""
+    import torch
+    return torch.cuda.device(t.device) if t.is_cuda else contextlib.nullcontext()
 
 
 def call(name: str, *args, kernels: int = 1) -> None:

@@ -63,8 +63,9 @@ def _launch_fwd(pred, target, denormalize, want_bands, want_map):
     sse = torch.empty(n, dtype=torch.float32, device=dev)
     bands = torch.empty(n, 16, dtype=torch.float32, device=dev) if want_bands else None
     fmap = torch.empty(b, c, h, w, dtype=torch.float32, device=dev) if want_map else None
-    lib.call("pai_ssim_psnr_fwd", _ptr(pred), _ptr(target), _BF16 if pred.dtype == torch.bfloat16 else _F32, n, h, w,
-             int(denormalize), _ptr(ssim_sum), _ptr(bands), _ptr(sse), _ptr(fmap), _stream())
+    with lib.on_device(pred):
+        lib.call("pai_ssim_psnr_fwd", _ptr(pred), _ptr(target), _BF16 if pred.dtype == torch.bfloat16 else _F32, n, h, w,
+                 int(denormalize), _ptr(ssim_sum), _ptr(bands), _ptr(sse), _ptr(fmap), _stream())
     return ssim_sum, sse, bands, fmap
 
 
@@ -89,8 +90,9 @@ class _SsimSse(torch.autograd.Function):
         g_sse = None if g_sse is None else g_sse.float().contiguous()
         work = torch.empty(n * h * w * 4, dtype=torch.float32, device=pred.device)
         grad = torch.empty_like(pred)
-        lib.call("pai_ssim_psnr_bwd", _ptr(pred), _ptr(target), _BF16 if pred.dtype == torch.bfloat16 else _F32, n, h,
-                 w, int(ctx.denormalize), _ptr(g_ssim), _ptr(g_sse), _ptr(work), _ptr(grad), _stream(), kernels=2)
+        with lib.on_device(pred):
+            lib.call("pai_ssim_psnr_bwd", _ptr(pred), _ptr(target), _BF16 if pred.dtype == torch.bfloat16 else _F32, n, h,
+                     w, int(ctx.denormalize), _ptr(g_ssim), _ptr(g_sse), _ptr(work), _ptr(grad), _stream(), kernels=2)
         return grad.to(ctx.in_dtype), None, None
 
 
