@@ -23,6 +23,7 @@ import pix2pix_port as port
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FWD_MAX_ABS, FWD_MEAN_ABS = 3e-2, 5e-3      # train-mode generator output at bf16 (see test_pix2pix_gpu.py header)
 
 
 def _build(loss_type, seed=0):
@@ -55,7 +56,7 @@ def test_batch64_gan_step_against_oracle():
         y = m(x.cuda())
     d = (y.cpu() - yo).abs()
     print(f"batch-64 train-mode generator output: max-abs {d.max().item():.3e} mean-abs {d.mean().item():.3e}")
-    assert d.max().item() < 1e-2 and d.mean().item() < 1.5e-3, (d.max().item(), d.mean().item())
+    assert d.max().item() < FWD_MAX_ABS and d.mean().item() < FWD_MEAN_ABS, (d.max().item(), d.mean().item())
     # the forward above advanced the BatchNorm running statistics once on both sides: reset so the step starts equal
     m.load_state_dict(sd)
     tr = port.OracleTrainer(sd, "gan")
@@ -76,7 +77,10 @@ def test_batch64_gan_step_against_oracle():
             assert gn < 1e-3, (k, gn)
             continue
         cos = float((g.cpu().double() * go.double()).sum() / (gn * on + 1e-30))
-        if abs(gn - on) > 0.08 * on or cos < 0.97:
+        # same profile as tests/test_pix2pix_gpu.py: the deep layers sit at the bf16 noise floor of the reference itself
+        # (oracle/bf16_selfcheck.py: cos 0.954 .. 0.97 there, 0.9995+ on the outer layers)
+        deep = any(f"encoders.{i}." in k for i in (3, 4, 5, 6, 7)) or any(f"decoders.{j}." in k for j in (0, 1, 2, 3))
+        if abs(gn - on) > 0.08 * on or cos < (0.93 if deep else 0.98):
             bad.append((k, gn, on, cos))
     assert not bad, bad
     # parameters after the two Adam updates: |delta| = lr exactly where the gradient sign is unambiguous
