@@ -194,6 +194,35 @@ int pai_col2im4x4s2(const float* p, int ldp, int n, int h, int w, const float* b
                     void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * The same degenerate layers as SINGLE-PASS tcgen05 kernels (csrc/thin.cu): the thin operand of the GEMM is built in
+ * shared memory by the CTA itself, so no im2col / col2im carrier ever exists in HBM and the wide tensor is read or
+ * written exactly once (these layers are HBM-bound).
+ *   pai_thin_conv4x4s2_fprop   Conv2d(cin in {1,2}, cout, 4, 2, 1) from fp32 planes [n,ih,iw] (enc0 models/pix2pix.py:141-147,
+ *                              D0 on cat([x,y]) models/wrapper.py:229,237; also the data gradient of dec7
+ *                              ConvTranspose2d(C,1,4,2,1) models/pix2pix.py:186-192 fed the output-gradient plane):
+ *                              out[n,oy,ox,co] = act(bias[co] + sum_{t,j} plane_j[n,2oy-1+ky,2ox-1+kx] * w_packed[co][t*cin+j])
+ *                              w_packed bf16 [cout][64] (zero padded columns), cout in {64,128,192,256}; optional second
+ *                              bf16 output with its own activation / pixel stride.
+ *   pai_thin_conv4x4s2_wgrad   dw[c][t*cin+j] += sum_pix u[pix,c] * plane_j[n,2oy-1+ky,2ox-1+kx]   (dw fp32 [c][16*cin], zeroed by
+ *                              the caller; c in {64,128}; iw %% 128 == 0): weight gradients of enc0 / D0 (u = dL/d pre-activation)
+ *                              and of dec7 (u = its input, plane = output gradient).
+ *   pai_thin_convT4x4s2_plane  ConvTranspose2d(c, 1, 4, 2, 1) (+bias, optional Tanh) from NHWC bf16 [n,h,128,c] to an fp32 plane
+ *                              [n,2h,256] (dec7 forward models/pix2pix.py:186-195; data gradient of D0 w.r.t. one input plane):
+ *                              w_taps bf16 [16][c], w_taps[ky*4+kx][ci] = W[ci,0,ky,kx]; rows are streamed once.
+ *   pai_col2im4x4s1            out[n,oy,ox] = sum_{ky,kx} p[n,oy-1+ky,ox-1+kx, ky*4+kx] over an [n,h,w,ldp] fp32 tensor of per-tap
+ *                              partial products -> [n,h-1,w-1]: the PatchGAN head Conv2d(512,1,4,1,1) (models/wrapper.py:233)
+ *                              after ONE pointwise GEMM over its input instead of 16 shifted ones.
+ */
+int pai_thin_conv4x4s2_fprop(const float* plane0, const float* plane1, int cin, int n, int ih, int iw,
+                             const void* w_packed, int cout, const float* bias, void* out1, int ld1, int act1, void* out2,
+                             int ld2, int act2, float slope, void* stream);
+int pai_thin_conv4x4s2_wgrad(const void* u, int u_ld, int c, const float* plane0, const float* plane1, int cin, int n,
+                             int ih, int iw, float* dw, void* stream);
+int pai_thin_convT4x4s2_plane(const void* x, int n, int h, int w, int c, int x_ld, const void* w_taps, const float* bias,
+                              int act, float* out, void* stream);
+int pai_col2im4x4s1(const float* p, int ldp, int n, int h, int w, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Optimizer step: torch.optim.Adam(lr=2e-4, betas=(0.5,0.999), eps=1e-7) of
  * UnetWrapper.configure_optimizers / training_step (models/wrapper.py:97-115,136,160), fused with
  * the bf16 operand repack of the implicit-GEMM kernels.  step_size = lr / (1 - beta1^t),

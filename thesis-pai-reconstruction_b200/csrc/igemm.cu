@@ -17,8 +17,10 @@
 // (one SWIZZLE_128B row).  Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator,
 // 4..7 = epilogue (TMEM -> registers -> global).
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "pai_common.cuh"
+#include "pai_epilogue.cuh"
 #include "pai_kernels.h"
 
 namespace pai {
@@ -35,104 +37,18 @@ struct __align__(8) PipeSmem {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ uint32_t tmem_cols_for(int n) {
-    uint32_t c = 32;
-    while ((int)c < n) c <<= 1;
-    return c;
-}
-
-__device__ __forceinline__ float apply_act(float v, int act, float slope) {
-    if (act == PAI_ACT_LEAKY) return v > 0.f ? v : v * slope;
-    if (act == PAI_ACT_RELU) return fmaxf(v, 0.f);
-    if (act == PAI_ACT_TANH) return tanhf(v);
-    return v;
-}
-
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
-                 : "memory");
-}
-
-// 16 consecutive channels of one pixel -> bf16, vectorised when aligned and fully inside the tensor
-__device__ __forceinline__ void store_bf16_16(__nv_bfloat16* o, const float (&f)[16], int act, float slope, bool vec,
-                                              int valid) {
-    if (vec) {
-        uint32_t w[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(apply_act(f[2 * j], act, slope), apply_act(f[2 * j + 1], act, slope));
-            w[j] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-            if (j < valid) o[j] = __float2bfloat16_rn(apply_act(f[j], act, slope));
-    }
-}
-
-// 64 fp32 accumulator columns of one row -> (+bias) -> activation -> bf16 -> one XOR-swizzled 128-byte row
-// of the warp's transpose tile.  ACT is a template parameter so the element loop carries no dispatch.
-template <int ACT>
-__device__ __forceinline__ float act_t(float v, float slope) {
-    if (ACT == PAI_ACT_LEAKY) return fmaxf(v, v * slope);      // slope in (0, 1)
-    if (ACT == PAI_ACT_RELU) return fmaxf(v, 0.f);
-    if (ACT == PAI_ACT_TANH) return tanhf(v);
-    return v;
-}
-template <int ACT>
-__device__ __forceinline__ void bias_act_pack(const uint32_t (&v)[64], const float* __restrict__ bias, float slope,
-                                              uint4* tile, int lane) {
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-        float f[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(v[8 * ch + k]);
-        if (bias != nullptr) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + 8 * ch));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + 8 * ch) + 1);
-            f[0] += b0.x, f[1] += b0.y, f[2] += b0.z, f[3] += b0.w;
-            f[4] += b1.x, f[5] += b1.y, f[6] += b1.z, f[7] += b1.w;
-        }
-        uint32_t w[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(act_t<ACT>(f[2 * k], slope), act_t<ACT>(f[2 * k + 1], slope));
-            w[k] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        tile[lane * 8 + (ch ^ (lane & 7))] = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-}
-
-// out = acc * (saved > 0 ? 1 : slope): the activation backward of the layer whose data gradient this GEMM produces;
-// mrow = this lane's 64 saved activations (nullptr for rows outside the tensor)
-__device__ __forceinline__ void mask_pack(const uint32_t (&v)[64], const __nv_bfloat16* __restrict__ mrow, float slope,
-                                          uint4* tile, int lane) {
-    uint4 m[8];
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch)
-        m[ch] = mrow != nullptr ? __ldg(reinterpret_cast<const uint4*>(mrow) + ch) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-        const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&m[ch]);
-        uint32_t w[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 mf = __bfloat1622float2(mh[k]);
-            const float a = __uint_as_float(v[8 * ch + 2 * k]) * (mf.x > 0.f ? 1.f : slope);
-            const float b = __uint_as_float(v[8 * ch + 2 * k + 1]) * (mf.y > 0.f ? 1.f : slope);
-            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-            w[k] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        tile[lane * 8 + (ch ^ (lane & 7))] = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-}
-
 // =============================================================================================
 // Persistent: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The fp32
 // accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Tile order: output-channel tile fastest, so CTAs running at the same time share the A tile in L2.
+//
+// PAIR = true: the kernel runs as 2-CTA clusters (the two SMs of a TPC).  A pair owns an M = 256 tile: each CTA stages its
+// own 128 pixels of A and HALF of the weight tile (n_tile / 2 rows), the leader CTA issues tcgen05.mma.cta_group::2 and
+// the accumulator rows of each half land in that CTA's own TMEM, so every SM pulls a third less operand data through L2
+// per FLOP (the large layers are L2 -> SM bound, profiles/r1_igemm_fprop_step_summary.txt) and one instruction stream
+// drives two tensor cores.  `full` barriers live in the leader (both CTAs' TMA loads complete on them), `empty` /
+// `acc_full` are signalled in both CTAs by multicast commits, both epilogues release the leader's `acc_empty`.
+template <bool PAIR>
 __global__ void __launch_bounds__(kFpropThreads, 1)
 igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const IgemmFpropParams p) {
@@ -144,14 +60,19 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tile = p.n_tile;
     const bool fused = p.fused_phases != 0;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;    // 0 = leader (issues the MMAs)
+    const int cta_n = PAIR ? n_tile / 2 : n_tile;           // weight-tile rows staged by this CTA
     const uint32_t a_bytes = 128 * 128;
-    const uint32_t b_bytes = (uint32_t)n_tile * 128;
+    const uint32_t b_bytes = (uint32_t)cta_n * 128;
     const uint32_t stage_bytes = a_bytes + (fused ? 4 : 1) * b_bytes;
     const int stages = p.stages;
     const int num_kb = (fused ? 9 : p.ntaps) * p.kc_per_tap;
     const int acc_n = fused ? 4 * n_tile : n_tile;          // accumulator columns per tile
     const uint32_t acc_cols = tmem_cols_for(acc_n);
+    // p.m_tiles counts the units a worker walks: 128-pixel tiles, or (PAIR) pairs of them
     const int total_tiles = p.n_tiles * p.m_tiles * p.phases * p.splitk;
+    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tm_a);
@@ -164,13 +85,21 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&ps.acc_full[a], 1);
-            mbar_init(&ps.acc_empty[a], 256);
+            mbar_init(&ps.acc_empty[a], PAIR ? 512 : 256);
         }
         mbar_fence_init();
     }
-    if (warp == 2) tmem_alloc(&ps.tmem_base, 2 * acc_cols);
+    if (warp == 2) {
+        if (PAIR)
+            tmem_alloc_pair(&ps.tmem_base, 2 * acc_cols);
+        else
+            tmem_alloc(&ps.tmem_base, 2 * acc_cols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR)
+        cluster_sync_all();          // the peer's barriers are initialised before anything remote touches them
+    else
+        __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = ps.tmem_base;
 
@@ -178,11 +107,12 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = worker; t < total_tiles; t += workers) {
                 int ks, tt, nt, r, mt, phase_idx, tw, th, tn;
                 p.fd_splitk.divmod(t, tt, ks);
                 p.fd_n_tiles.divmod(tt, r, nt);
                 p.fd_m_tiles.divmod(r, phase_idx, mt);
+                if (PAIR) mt = 2 * mt + (int)rank;       // an odd tile count leaves the last peer tile out of bounds: zero fill
                 p.fd_tiles_w.divmod(mt, mt, tw);
                 p.fd_tiles_h.divmod(mt, tn, th);
                 const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
@@ -194,22 +124,39 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                     mbar_wait(&ps.empty[stage], phase ^ 1);
                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
                     uint8_t* sb = sa + a_bytes;
+                    const int brow = PAIR ? (int)rank * cta_n : 0;     // this CTA's half of the weight tile
                     if (fused) {
                         int nu = 0;
                         while (nu < 4 && p.box_users[tap][nu] >= 0) ++nu;
-                        mbar_expect_tx(&ps.full[stage], a_bytes + nu * b_bytes);
-                        tma_load_5d(sa, &tm_a, &ps.full[stage], kc * 64, w0 + p.box_w[tap], 0, h0 + p.box_h[tap], n0);
+                        if (PAIR) {
+                            if (rank == 0) mbar_expect_tx(&ps.full[stage], 2 * (a_bytes + nu * b_bytes));
+                            tma_load_5d_pair(sa, &tm_a, &ps.full[stage], kc * 64, w0 + p.box_w[tap], 0, h0 + p.box_h[tap], n0);
+                        } else {
+                            mbar_expect_tx(&ps.full[stage], a_bytes + nu * b_bytes);
+                            tma_load_5d(sa, &tm_a, &ps.full[stage], kc * 64, w0 + p.box_w[tap], 0, h0 + p.box_h[tap], n0);
+                        }
                         for (int u = 0; u < nu; ++u) {
                             const int pt = p.box_users[tap][u], ph = pt >> 2, tp = pt & 3;
-                            tma_load_2d(sb + u * b_bytes, &tm_b, &ps.full[stage], (tp * p.kc_per_tap + kc) * 64,
-                                        ph * p.b_rows_per_phase);
+                            if (PAIR)
+                                tma_load_2d_pair(sb + u * b_bytes, &tm_b, &ps.full[stage], (tp * p.kc_per_tap + kc) * 64,
+                                                 ph * p.b_rows_per_phase + brow);
+                            else
+                                tma_load_2d(sb + u * b_bytes, &tm_b, &ps.full[stage], (tp * p.kc_per_tap + kc) * 64,
+                                            ph * p.b_rows_per_phase);
                         }
                     } else {
                         const int ti = phase_idx * p.ntaps + tap;
-                        mbar_expect_tx(&ps.full[stage], stage_bytes);
-                        tma_load_5d(sa, &tm_a, &ps.full[stage], p.tap_c[ti] + kc * 64, w0 + p.tap_w[ti], p.tap_p[ti],
-                                    h0 + p.tap_h[ti], n0);
-                        tma_load_2d(sb, &tm_b, &ps.full[stage], kb * 64, phase_idx * p.b_rows_per_phase + col0);
+                        if (PAIR) {
+                            if (rank == 0) mbar_expect_tx(&ps.full[stage], 2 * stage_bytes);
+                            tma_load_5d_pair(sa, &tm_a, &ps.full[stage], p.tap_c[ti] + kc * 64, w0 + p.tap_w[ti], p.tap_p[ti],
+                                             h0 + p.tap_h[ti], n0);
+                            tma_load_2d_pair(sb, &tm_b, &ps.full[stage], kb * 64, phase_idx * p.b_rows_per_phase + col0 + brow);
+                        } else {
+                            mbar_expect_tx(&ps.full[stage], stage_bytes);
+                            tma_load_5d(sa, &tm_a, &ps.full[stage], p.tap_c[ti] + kc * 64, w0 + p.tap_w[ti], p.tap_p[ti],
+                                        h0 + p.tap_h[ti], n0);
+                            tma_load_2d(sb, &tm_b, &ps.full[stage], kb * 64, phase_idx * p.b_rows_per_phase + col0);
+                        }
                     }
                     if (++stage == stages) {
                         stage = 0;
@@ -219,12 +166,12 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             }
         }
     } else if (warp == 1) {
-        if (elect_one()) {
-            const uint32_t idesc = umma_idesc_bf16(128, n_tile, 0, 0);
+        if (rank == 0 && elect_one()) {
+            const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, n_tile, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            for (int t = worker; t < total_tiles; t += workers, ++it) {
                 const int a = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&ps.acc_empty[a], acc_phase ^ 1);   // epilogue has drained this accumulator
@@ -248,25 +195,43 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                             const int ph = p.box_users[box][u] >> 2;
                             const uint64_t dbu = db0 + (uint64_t)u * (b_bytes >> 4);
                             const uint32_t td = tmem_d + ph * n_tile;
-                            umma_bf16_ss(td, da0, dbu, idesc, (started >> ph) & 1);
-                            umma_bf16_acc(td, da0 + 2, dbu + 2, idesc);
-                            umma_bf16_acc(td, da0 + 4, dbu + 4, idesc);
-                            umma_bf16_acc(td, da0 + 6, dbu + 6, idesc);
+                            if (PAIR) {
+                                umma_bf16_ss_pair(td, da0, dbu, idesc, (started >> ph) & 1);
+                                umma_bf16_acc_pair(td, da0 + 2, dbu + 2, idesc);
+                                umma_bf16_acc_pair(td, da0 + 4, dbu + 4, idesc);
+                                umma_bf16_acc_pair(td, da0 + 6, dbu + 6, idesc);
+                            } else {
+                                umma_bf16_ss(td, da0, dbu, idesc, (started >> ph) & 1);
+                                umma_bf16_acc(td, da0 + 2, dbu + 2, idesc);
+                                umma_bf16_acc(td, da0 + 4, dbu + 4, idesc);
+                                umma_bf16_acc(td, da0 + 6, dbu + 6, idesc);
+                            }
                             started |= 1u << ph;
                         }
+                    } else if (PAIR) {
+                        umma_bf16_ss_pair(tmem_d, da0, db0, idesc, kb != kb_begin);
+                        if (p.kmma > 1) umma_bf16_acc_pair(tmem_d, da0 + 2, db0 + 2, idesc);
+                        if (p.kmma > 2) umma_bf16_acc_pair(tmem_d, da0 + 4, db0 + 4, idesc);
+                        if (p.kmma > 3) umma_bf16_acc_pair(tmem_d, da0 + 6, db0 + 6, idesc);
                     } else {
                         umma_bf16_ss(tmem_d, da0, db0, idesc, kb != kb_begin);
                         if (p.kmma > 1) umma_bf16_acc(tmem_d, da0 + 2, db0 + 2, idesc);
                         if (p.kmma > 2) umma_bf16_acc(tmem_d, da0 + 4, db0 + 4, idesc);
                         if (p.kmma > 3) umma_bf16_acc(tmem_d, da0 + 6, db0 + 6, idesc);
                     }
-                    umma_commit(&ps.empty[stage]);
+                    if (PAIR)
+                        umma_commit_pair(&ps.empty[stage]);     // frees the stage in both CTAs
+                    else
+                        umma_commit(&ps.empty[stage]);
                     if (++stage == stages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(&ps.acc_full[a]);
+                if (PAIR)
+                    umma_commit_pair(&ps.acc_full[a]);          // both epilogues
+                else
+                    umma_commit(&ps.acc_full[a]);
             }
         }
     } else if (warp >= 4) {
@@ -280,11 +245,12 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         const int ni = r / (p.bw * p.bh);
         const int n_out = p.out2 != nullptr ? 2 : 1;
         int it = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        for (int t = worker; t < total_tiles; t += workers, ++it) {
             int nt, rr, mt, phase_idx, tw, th, tn;
             const int tt = p.fd_splitk.quot(t);
             p.fd_n_tiles.divmod(tt, rr, nt);
             p.fd_m_tiles.divmod(rr, phase_idx, mt);
+            if (PAIR) mt = 2 * mt + (int)rank;
             p.fd_tiles_w.divmod(mt, mt, tw);
             p.fd_tiles_h.divmod(mt, tn, th);
             const int col0 = nt * n_tile;
@@ -419,14 +385,23 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             }
             __syncwarp();
             tc_fence_before();
-            mbar_arrive(&ps.acc_empty[a]);      // 256 arrivals release the accumulator to the MMA warp
+            if (PAIR)
+                mbar_arrive_leader(&ps.acc_empty[a]);   // 2 x 256 arrivals (both CTAs) release the accumulator pair
+            else
+                mbar_arrive(&ps.acc_empty[a]);          // 256 arrivals release the accumulator to the MMA warp
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR)
+        cluster_sync_all();      // neither CTA may exit (or free TMEM) while the other's MMAs / barriers still reference it
+    else
+        __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * acc_cols);
+        if (PAIR)
+            tmem_dealloc_pair(tmem_base, 2 * acc_cols);
+        else
+            tmem_dealloc(tmem_base, 2 * acc_cols);
     }
 }
 
@@ -602,25 +577,42 @@ static int pick_stages(size_t stage_bytes, size_t budget) {
     return s;
 }
 
+// The 2-CTA form pays off when the layer has enough 256-pixel tiles to fill the machine; it needs a weight tile that
+// splits into two UMMA-legal halves and no split-K.  PAI_NO_CTA_PAIR=1 forces the 1-CTA kernel (A/B measurements).
+bool igemm_fprop_use_pair(int n_tile, long long m_tiles, int n_tiles, int phases, int splitk) {
+    static const bool off = getenv("PAI_NO_CTA_PAIR") != nullptr;
+    if (off || splitk > 1 || n_tile % 32 != 0) return false;
+    return ((m_tiles + 1) / 2) * n_tiles * phases >= 74;
+}
+
 int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFpropParams p, int m_tiles,
                        int n_tiles, int phases, cudaStream_t stream) {
-    const size_t stage_bytes = 128 * 128 + (size_t)(p.fused_phases ? 4 : 1) * p.n_tile * 128;
+    const bool pair = p.pair != 0;
+    const size_t stage_bytes = 128 * 128 + (size_t)(p.fused_phases ? 4 : 1) * (pair ? p.n_tile / 2 : p.n_tile) * 128;
     p.stages = pick_stages(stage_bytes, 192 * 1024);
-    p.m_tiles = m_tiles, p.n_tiles = n_tiles, p.phases = phases;
+    p.m_tiles = pair ? (m_tiles + 1) / 2 : m_tiles, p.n_tiles = n_tiles, p.phases = phases;
     if (p.kmma <= 0 || p.kmma > 4) p.kmma = 4;
     const size_t smem = stage_bytes * p.stages + 1024;
     static DeviceOnce once;
     const int dev = current_device(), num_sms = sm_count(dev);
     if (num_sms < 0) return -1;
     if (once.need(dev)) {
-        PAI_CUDA_OK(cudaFuncSetAttribute(igemm_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 194 * 1024));
+        PAI_CUDA_OK(cudaFuncSetAttribute(igemm_fprop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 194 * 1024));
+        PAI_CUDA_OK(cudaFuncSetAttribute(igemm_fprop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 194 * 1024));
         once.mark(dev);
     }
     if (p.splitk < 1) p.splitk = 1;
-    p.fd_splitk = make_fastdiv(p.splitk), p.fd_n_tiles = make_fastdiv(n_tiles), p.fd_m_tiles = make_fastdiv(m_tiles);
+    PAI_REQUIRE(!pair || (p.splitk == 1 && p.n_tile % 32 == 0), "igemm fprop: the CTA-pair kernel needs n_tile %% 32 == 0 and no split-K");
+    p.fd_splitk = make_fastdiv(p.splitk), p.fd_n_tiles = make_fastdiv(n_tiles), p.fd_m_tiles = make_fastdiv(p.m_tiles);
     p.fd_tiles_w = make_fastdiv(p.tiles_w), p.fd_tiles_h = make_fastdiv(p.tiles_h);
-    const long long total = (long long)m_tiles * n_tiles * phases * p.splitk;
-    const int grid = (int)(total < num_sms ? total : num_sms);
+    const long long total = (long long)p.m_tiles * n_tiles * phases * p.splitk;
+    int grid;
+    if (pair) {
+        const long long pairs = total < num_sms / 2 ? total : num_sms / 2;
+        grid = (int)(2 * pairs);
+    } else {
+        grid = (int)(total < num_sms ? total : num_sms);
+    }
     if (p.mask_src != nullptr)
         PAI_REQUIRE(!p.out_f32 && p.splitk == 1 && !p.accumulate && (p.n_tile & 63) == 0 && p.cout % p.n_tile == 0 &&
                         (p.cout & 7) == 0 && p.bias == nullptr && p.act == PAI_ACT_NONE && p.out2 == nullptr &&
@@ -634,7 +626,17 @@ int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFp
                     "igemm fprop: fused BatchNorm statistics need a bf16 output with cout %% 64 == 0, no split-K and "
                     "%d partial rows (cout=%d n_tile=%d splitk=%d rows=%d)", grid, p.cout, p.n_tile, p.splitk, p.bn_rows);
     }
-    igemm_fprop_kernel<<<grid, kFpropThreads, smem, stream>>>(tm_a, tm_b, p);
+    if (pair) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(kFpropThreads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr, cfg.numAttrs = 1;
+        PAI_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_fprop_kernel<true>, tm_a, tm_b, p));
+    } else {
+        igemm_fprop_kernel<false><<<grid, kFpropThreads, smem, stream>>>(tm_a, tm_b, p);
+    }
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }

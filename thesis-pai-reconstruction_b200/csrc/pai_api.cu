@@ -189,14 +189,18 @@ static int conv4x4_fprop_impl(const void* x, int n, int h, int w, int cin, int x
     CUtensorMap tm_a, tm_b;
     int rc = stride == 2 ? map_split(&tm_a, x, n, h, w, cin, b) : map_unit(&tm_a, x, n, h, w, cin, x_ld, b);
     if (rc) return rc;
+    const int m_tiles = b.tiles_w * b.tiles_h * b.tiles_n;
+    const int splitk = pick_splitk(splitk_ws, (long long)m_tiles * (cout_pad / n_tile), 16 * (cin / 64));
+    const bool pair = igemm_fprop_use_pair(n_tile, m_tiles, cout_pad / n_tile, 1, splitk);
     uint64_t bd[2] = {(uint64_t)16 * cin, (uint64_t)cout_pad};
     uint64_t bs[1] = {(uint64_t)16 * cin * 2};
-    uint32_t bb[2] = {64, (uint32_t)n_tile};
+    uint32_t bb[2] = {64, (uint32_t)(pair ? n_tile / 2 : n_tile)};
     rc = encode_tmap_bf16(&tm_b, w_packed, 2, bd, bs, bb);
     if (rc) return rc;
 
     IgemmFpropParams p;
     memset(&p, 0, sizeof(p));
+    p.pair = pair;
     p.bw = b.bw, p.bh = b.bh, p.bn = b.bn, p.tiles_w = b.tiles_w, p.tiles_h = b.tiles_h;
     p.gw = wo, p.gh = ho, p.gn = n;
     p.n_tile = n_tile, p.cout = cout, p.kc_per_tap = cin / 64, p.ntaps = 16;
@@ -214,8 +218,7 @@ static int conv4x4_fprop_impl(const void* x, int n, int h, int w, int cin, int x
         }
     p.b_rows_per_phase = cout_pad;
     p.bn_part = bn_part, p.bn_rows = bn_rows;
-    const int m_tiles = b.tiles_w * b.tiles_h * b.tiles_n;
-    p.splitk = pick_splitk(splitk_ws, (long long)m_tiles * (cout_pad / n_tile), 16 * (cin / 64));
+    p.splitk = splitk;
     if (p.splitk > 1) {
         p.out_sn = (long long)ho * wo * cout, p.out_sh = (long long)wo * cout, p.out_sw = cout;
         p.out_f32 = 1, p.accumulate = 1, p.out = splitk_ws;
@@ -259,14 +262,23 @@ static int convT4x4s2_fprop_impl(const void* x, int n, int h, int w, int cin, in
     CUtensorMap tm_a, tm_b;
     int rc = map_unit(&tm_a, x, n, h, w, cin, x_ld, b);
     if (rc) return rc;
+    const int m_tiles = b.tiles_w * b.tiles_h * b.tiles_n;
+    const int splitk = pick_splitk(splitk_ws, 4LL * m_tiles * (cout_pad / n_tile), 4 * (cin / 64));
+    // phase fusion for the 64-channel layers (dec6, the data gradients of enc1 / D1): the activation tile is the
+    // L2-bound operand there, and 9 boxes per channel block instead of 16 feed all four phases
+    const bool fuse = splitk == 1 && cout == 64 && cout_pad == 64 && n_tile == 64 && !y_f32 && y_ld % 8 == 0 &&
+                      aligned16(y) && (bias == nullptr || aligned16(bias)) && getenv("PAI_NO_PHASE_FUSION") == nullptr;
+    const bool pair = fuse ? igemm_fprop_use_pair(n_tile, m_tiles, 1, 1, 1)
+                           : igemm_fprop_use_pair(n_tile, m_tiles, cout_pad / n_tile, 4, splitk);
     uint64_t bd[2] = {(uint64_t)4 * cin, (uint64_t)4 * cout_pad};
     uint64_t bs[1] = {(uint64_t)4 * cin * 2};
-    uint32_t bb[2] = {64, (uint32_t)n_tile};
+    uint32_t bb[2] = {64, (uint32_t)(pair ? n_tile / 2 : n_tile)};
     rc = encode_tmap_bf16(&tm_b, w_packed, 2, bd, bs, bb);
     if (rc) return rc;
 
     IgemmFpropParams p;
     memset(&p, 0, sizeof(p));
+    p.pair = pair;
     p.bw = b.bw, p.bh = b.bh, p.bn = b.bn, p.tiles_w = b.tiles_w, p.tiles_h = b.tiles_h;
     p.gw = w, p.gh = h, p.gn = n;
     p.n_tile = n_tile, p.cout = cout, p.kc_per_tap = cin / 64, p.ntaps = 4;
@@ -281,16 +293,11 @@ static int convT4x4s2_fprop_impl(const void* x, int n, int h, int w, int cin, in
     p.bn_part = bn_part, p.bn_rows = bn_rows;
     p.mask_src = mask_src, p.mask_slope = mask_slope;
     const long long wo = 2LL * w;
-    const int m_tiles = b.tiles_w * b.tiles_h * b.tiles_n;
-    p.splitk = pick_splitk(splitk_ws, 4LL * m_tiles * (cout_pad / n_tile), 4 * (cin / 64));
+    p.splitk = splitk;
     const long long ld = p.splitk > 1 ? cout : y_ld;
     p.out_sn = 4LL * h * w * ld, p.out_sh = 2 * wo * ld, p.out_sw = 2LL * ld;
     for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px) p.out_phase_off[py * 2 + px] = (py * wo + px) * ld;
-    // phase fusion for the 64-channel layers (dec6, the data gradients of enc1 / D1): the activation tile is the
-    // L2-bound operand there, and 9 boxes per channel block instead of 16 feed all four phases
-    const bool fuse = p.splitk == 1 && cout == 64 && cout_pad == 64 && n_tile == 64 && !y_f32 && y_ld % 8 == 0 &&
-                      aligned16(y) && (bias == nullptr || aligned16(bias)) && getenv("PAI_NO_PHASE_FUSION") == nullptr;
     if (fuse) {
         p.fused_phases = 1;
         for (int bx = 0; bx < 9; ++bx) {

@@ -69,6 +69,7 @@ struct IgemmFpropParams {
     // LeakyReLU / ReLU derivative taken from the sign of the saved activation at the SAME location as the output element
     const void* mask_src;
     float mask_slope;
+    int pair;                  // run as 2-CTA clusters (cta_group::2, M = 256): tm_b's box must hold n_tile / 2 rows
     int splitk;                // K slices per output tile (>1: partial sums are accumulated into fp32 `out`)
     int accumulate;            // generic fp32 path adds into `out` (red.add) instead of storing
 };
@@ -89,6 +90,7 @@ struct IgemmWgradParams {
     float* out;                // [ntaps][cu][cs] fp32, accumulated with vector reductions
 };
 
+bool igemm_fprop_use_pair(int n_tile, long long m_tiles, int n_tiles, int phases, int splitk);
 int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFpropParams p, int m_tiles,
                        int n_tiles, int phases, cudaStream_t stream);
 // y[pix * ld + c] = act(ws[pix * c_count + c] + bias[c]) for a dense fp32 split-K workspace

@@ -16,6 +16,8 @@ What rides on the GEMM epilogues (switchable for A/B measurements by the environ
   ``conv4x4_fprop_bnstats`` / ``convT4x4s2_fprop_bnstats``, summed by ``bn_finalize``  [PAI_NO_BN_FUSION];
 * the LeakyReLU backward and the bias gradient of the PatchGAN blocks: ``conv4x4_dgrad_act``  [PAI_NO_ACT_BWD_FUSION];
 * bias, activation, second (skip) output and sub-pixel phase placement (always).
+The 1- and 2-channel layers (enc0, D0, dec7 and their gradients, the PatchGAN head) run as single-pass kernels that build
+the thin GEMM operand in shared memory (csrc/thin.cu) instead of an im2col / col2im carrier in HBM  [PAI_NO_THIN_DIRECT].
 Train-mode Dropout2d (decoders 0-2 of the default constructor) is a per-(sample, channel) mask applied to the concat
 slot; ``check_path()`` switches the forward to the exact fp32 kernels of csrc/check_f32.cu.
 """
@@ -32,6 +34,7 @@ from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH
 BN_EPS, BN_MOMENTUM, SLOPE = 1e-5, 0.1, 0.2
 FUSE_BN_STATS = os.environ.get("PAI_NO_BN_FUSION") is None     # BatchNorm statistics from the GEMM epilogue
 FUSE_ACT_BWD = os.environ.get("PAI_NO_ACT_BWD_FUSION") is None  # PatchGAN LeakyReLU backward in the dgrad GEMM epilogue
+THIN_DIRECT = os.environ.get("PAI_NO_THIN_DIRECT") is None      # 1-2 channel layers as single-pass kernels (csrc/thin.cu)
 
 
 # ------------------------------------------------------------------------------------------ pack cache
@@ -140,6 +143,10 @@ def _aux_pack(tag: str, p: torch.Tensor, fn):
 
 def _head_dgrad_pack(w):       # PatchGAN head Conv2d weight [1, C, 4, 4] -> bf16 [C, 64]: column = tap
     return _aux_pack("head_d", w, lambda t: _pad_cols(t[0].reshape(t.shape[1], 16)))
+
+
+def _head_fprop_pack(w):       # PatchGAN head Conv2d weight [1, C, 4, 4] -> bf16 [16, C]: row = tap (per-tap partial products)
+    return _aux_pack("head_f", w, lambda t: t[0].reshape(t.shape[1], 16).t().contiguous().bfloat16())
 
 
 def _thin_in_dgrad_pack(w, j):  # Conv2d weight [C, cin, 4, 4] -> bf16 [16, C]: row = tap, for input channel j
@@ -313,9 +320,15 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
     # The last decoder is a bare ConvTranspose2d (models/pix2pix.py:185-193): no ReLU in front of it, so
     # its concat buffer cat[L-1] holds UN-activated values; every other decoder starts with a ReLU.
     # enc0 (1 input channel) = im2col of the plane + one tensor-core GEMM with two fused outputs
-    xcol = ops.im2col4x4([plane], hs[0], ws[0], stride=2)
-    ops.pointwise_gemm(xcol, _thin_in_pack(conv0.weight), c0, bias=conv0.bias.detach(), act=ACT_LEAKY, slope=SLOPE,
-                       out=a_in[1], out2=cat[L - 1][..., c0:], act2=ACT_NONE, k_valid=16)
+    xcol = None
+    if THIN_DIRECT and c0 <= 256:
+        # one pass: the 16-tap rows are built in shared memory, both consumers are written by the same epilogue
+        ops.thin_conv_fprop([plane], _thin_in_pack(conv0.weight), c0, conv0.bias.detach(), a_in[1], ACT_LEAKY,
+                            cat[L - 1][..., c0:], ACT_NONE, slope=SLOPE)
+    else:
+        xcol = ops.im2col4x4([plane], hs[0], ws[0], stride=2)
+        ops.pointwise_gemm(xcol, _thin_in_pack(conv0.weight), c0, bias=conv0.bias.detach(), act=ACT_LEAKY, slope=SLOPE,
+                           out=a_in[1], out2=cat[L - 1][..., c0:], act2=ACT_NONE, k_valid=16)
     # ---- encoders 1..L-1
     for i in range(1, L):
         conv, bn = spec.enc_convs[i], spec.enc_bns[i]
@@ -363,8 +376,11 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
     last = spec.dec_convs[L - 1]
     # last decoder (1 output channel): 16 per-tap partial products per input pixel (GEMM, the wide input is
     # read once) + col2im with bias and Tanh
-    part = ops.pointwise_gemm(d_in, _thin_out_fprop_pack(last.weight), 16, out_f32=True)
-    y = ops.col2im4x4s2(part, last.bias.detach(), ACT_TANH).view(n, 1, h, w)
+    if THIN_DIRECT and ops.thin_plane_ok(d_in):
+        y = ops.thin_convT_plane(d_in, _thin_out_fprop_pack(last.weight), last.bias.detach(), ACT_TANH).view(n, 1, h, w)
+    else:
+        part = ops.pointwise_gemm(d_in, _thin_out_fprop_pack(last.weight), 16, out_f32=True)
+        y = ops.col2im4x4s2(part, last.bias.detach(), ACT_TANH).view(n, 1, h, w)
     if counters:
         torch._foreach_add_(counters, 1)
     if not save:
@@ -387,10 +403,20 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
     # ---- last decoder: ConvT(2*c0 -> 1)
     last = spec.dec_convs[L - 1]
     cin_last = last.weight.shape[0]
-    gcol = ops.im2col4x4([g_pre], h // 2, w // 2, stride=2)                      # [N, h/2, w/2, 64], 16 taps of g
-    dw = ops.pointwise_wgrad(s.cat[L - 1], gcol)                                 # [cin, 64]
+    gcol = None
+    if THIN_DIRECT and ops.thin_wgrad_ok(s.cat[L - 1], [g_pre]):
+        dw = ops.thin_conv_wgrad(s.cat[L - 1], [g_pre])                          # [cin, 16]
+    else:
+        gcol = ops.im2col4x4([g_pre], h // 2, w // 2, stride=2)                  # [N, h/2, w/2, 64], 16 taps of g
+        dw = ops.pointwise_wgrad(s.cat[L - 1], gcol)                             # [cin, 64]
     grads[(1, L - 1)] = (dw[:, :16].reshape(cin_last, 1, 4, 4), g_pre.sum().reshape(1))
-    dcat = ops.pointwise_gemm(gcol, _thin_out_dgrad_pack(last.weight), cin_last, k_valid=16)
+    if THIN_DIRECT and cin_last <= 256:
+        dcat = _bf16(n, h // 2, w // 2, cin_last, device=dev)
+        ops.thin_conv_fprop([g_pre], _thin_out_dgrad_pack(last.weight), cin_last, None, dcat, ACT_NONE)
+    else:
+        if gcol is None:
+            gcol = ops.im2col4x4([g_pre], h // 2, w // 2, stride=2)
+        dcat = ops.pointwise_gemm(gcol, _thin_out_dgrad_pack(last.weight), cin_last, k_valid=16)
     # ---- decoders L-2 .. 0
     dskip = [None] * L                          # dskip[i]: grad w.r.t. relu(skip_i) (second half of dcat)
     for j in range(L - 2, -1, -1):
@@ -440,7 +466,11 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
     c0 = ch[0]
     d_raw = _bf16(*s.a_in[1].shape, device=dev)
     sums = ops.act_bwd(s.a_in[1], d_a, ACT_LEAKY, dskip[0], ACT_NONE, d_raw, slope=SLOPE)
-    dw0 = ops.pointwise_wgrad(d_raw, s.xcol)                                     # [c0, 64]
+    if THIN_DIRECT and ops.thin_wgrad_ok(d_raw, [s.plane]):
+        dw0 = ops.thin_conv_wgrad(d_raw, [s.plane])                              # [c0, 16]
+    else:
+        xcol = s.xcol if s.xcol is not None else ops.im2col4x4([s.plane], h // 2, w // 2, stride=2)
+        dw0 = ops.pointwise_wgrad(d_raw, xcol)                                   # [c0, 64]
     grads[(0, 0)] = (dw0[:, :16].reshape(c0, 1, 4, 4), sums[:c0].clone())
     out = []
     for i in range(L):
@@ -503,9 +533,14 @@ def disc_forward(spec: DiscSpec, x: torch.Tensor, y: torch.Tensor, save: bool):
     px = x.contiguous().float().view(n, h, w)
     py = y.contiguous().float().view(n, h, w)
     c0 = spec.convs[0]
-    xycol = ops.im2col4x4([px, py], h // 2, w // 2, stride=2)                    # cat([x, y]) never materialised
-    hcur = ops.pointwise_gemm(xycol, _thin_in_pack(c0.weight), spec.ch[0], bias=c0.bias.detach(), act=ACT_LEAKY,
-                              slope=SLOPE, k_valid=32)
+    xycol = None                                                                 # cat([x, y]) is never materialised
+    if THIN_DIRECT and spec.ch[0] <= 256:
+        hcur = _bf16(n, h // 2, w // 2, spec.ch[0], device=dev)
+        ops.thin_conv_fprop([px, py], _thin_in_pack(c0.weight), spec.ch[0], c0.bias.detach(), hcur, ACT_LEAKY, slope=SLOPE)
+    else:
+        xycol = ops.im2col4x4([px, py], h // 2, w // 2, stride=2)
+        hcur = ops.pointwise_gemm(xycol, _thin_in_pack(c0.weight), spec.ch[0], bias=c0.bias.detach(), act=ACT_LEAKY,
+                                  slope=SLOPE, k_valid=32)
     hs = [hcur]
     for k in range(1, len(spec.convs) - 1):
         c = spec.convs[k]
@@ -513,8 +548,15 @@ def disc_forward(spec: DiscSpec, x: torch.Tensor, y: torch.Tensor, save: bool):
                                  act=ACT_LEAKY, slope=SLOPE)
         hs.append(hcur)
     head = spec.convs[-1]
-    logits = ops.conv4x4_fprop(hcur, _fprop_pack(head.weight), 1, stride=1, out_f32=True)
-    nb, lh, lw, _ = logits.shape
+    if THIN_DIRECT:
+        # 512 -> 1 channels: ONE GEMM over the input gives the 16 per-tap partial products of every pixel, a small gather
+        # sums the 4x4 window (instead of 16 shifted tensor-core passes over the same 16 MB for a 1-column output)
+        part = ops.pointwise_gemm(hcur, _head_fprop_pack(head.weight), 16, out_f32=True)
+        logits = ops.col2im4x4s1(part)
+        nb, lh, lw = logits.shape
+    else:
+        logits = ops.conv4x4_fprop(hcur, _fprop_pack(head.weight), 1, stride=1, out_f32=True)
+        nb, lh, lw, _ = logits.shape
     logits = logits.view(nb, 1, lh, lw)
     if not save:
         return logits, None
@@ -564,15 +606,22 @@ def disc_backward(spec: DiscSpec, s: _Saved, g_logits: torch.Tensor, need_params
             else:
                 dh = ops.convT4x4s2_fprop(d_pre, _dgrad_pack(conv.weight), cprev)
         else:
+            h, w = s.px.shape[1], s.px.shape[2]
             if need_params:
-                dw0 = ops.pointwise_wgrad(d_pre, s.xycol)                        # [c, 64], column = tap*2 + j
+                if THIN_DIRECT and ops.thin_wgrad_ok(d_pre, [s.px, s.py]):
+                    dw0 = ops.thin_conv_wgrad(d_pre, [s.px, s.py])               # [c, 32], column = tap*2 + j
+                else:
+                    xycol = s.xycol if s.xycol is not None else ops.im2col4x4([s.px, s.py], h // 2, w // 2, stride=2)
+                    dw0 = ops.pointwise_wgrad(d_pre, xycol)                      # [c, 64]
                 grads[0] = dw0[:, :32].reshape(ck, 4, 4, 2).permute(0, 3, 1, 2)
                 grads[1] = sums[:ck].clone()
             gy = None
             if need_y:
-                h, w = s.px.shape[1], s.px.shape[2]
-                part = ops.pointwise_gemm(d_pre, _thin_in_dgrad_pack(conv.weight, 1), 16, out_f32=True)
-                gy = ops.col2im4x4s2(part).view(n, 1, h, w)
+                if THIN_DIRECT and ops.thin_plane_ok(d_pre):
+                    gy = ops.thin_convT_plane(d_pre, _thin_in_dgrad_pack(conv.weight, 1)).view(n, 1, h, w)
+                else:
+                    part = ops.pointwise_gemm(d_pre, _thin_in_dgrad_pack(conv.weight, 1), 16, out_f32=True)
+                    gy = ops.col2im4x4s2(part).view(n, 1, h, w)
     dp.finish_async()
     return grads, gy
 

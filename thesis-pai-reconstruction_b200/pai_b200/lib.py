@@ -94,6 +94,11 @@ SIGNATURES = {
     "pai_check_batchnorm_f32": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
                                 c_float, c_void_p, c_void_p],
     "pai_check_act_f32": [c_void_p, c_ll, c_int, c_float, c_void_p, c_void_p],
+    "pai_thin_conv4x4s2_fprop": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                 c_int, c_void_p, c_int, c_int, c_float, c_void_p],
+    "pai_thin_conv4x4s2_wgrad": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "pai_thin_convT4x4s2_plane": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    "pai_col2im4x4s1": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "pai_adam_multi": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float,
                        c_float, c_void_p, c_void_p],
 }

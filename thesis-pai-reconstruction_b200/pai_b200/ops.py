@@ -396,6 +396,69 @@ def col2im4x4s2(p, bias=None, act=ACT_NONE):
     return out
 
 
+# ------------------------------------------------------------------------------------------ thin layers, single pass
+def thin_conv_fprop(planes, w_packed, cout, bias, out1, act1=ACT_NONE, out2=None, act2=ACT_NONE, slope=0.2):
+    """Conv2d(len(planes), cout, 4, 2, 1) straight from 1|2 fp32 planes ``[n, ih, iw]`` (csrc/thin.cu): the im2col rows
+    are built in shared memory.  ``w_packed``: bf16 ``[cout, 64]``, column = tap*cin + j; ``out1`` / ``out2``: NHWC bf16."""
+    p0 = planes[0]
+    p1 = planes[1] if len(planes) > 1 else None
+    n, ih, iw = p0.shape
+    assert p0.is_contiguous() and p0.dtype == torch.float32 and (p1 is None or (p1.is_contiguous() and p1.shape == p0.shape))
+    on, oh, ow, oc, ld1 = _nhwc(out1)
+    assert (on, oh, ow, oc) == (n, ih // 2, iw // 2, cout) and tuple(w_packed.shape) == (cout, 64)
+    ld2 = 0
+    if out2 is not None:
+        assert tuple(out2.shape) == (n, ih // 2, iw // 2, cout)
+        ld2 = _nhwc(out2)[4]
+    _igemm_call("pai_thin_conv4x4s2_fprop", 2.0 * n * (ih // 2) * (iw // 2) * cout * 16 * len(planes), _ptr(p0), _ptr(p1),
+                len(planes), n, ih, iw, _ptr(w_packed), cout, _ptr(bias), _ptr(out1), ld1, act1, _ptr(out2), ld2, act2,
+                float(slope), _stream())
+    return out1
+
+
+def thin_wgrad_ok(u, planes) -> bool:
+    return u.shape[3] in (64, 128) and planes[0].shape[2] % 128 == 0
+
+
+def thin_conv_wgrad(u, planes):
+    """-> fp32 ``[c, 16*cin]`` = sum over pixels of ``u[pix, c] * plane_j[2*oy-1+ky, 2*ox-1+kx]`` (column = tap*cin + j):
+    the weight gradient of a 1|2-input-channel stride-2 4x4 convolution (``u`` = gradient of its output), and of a
+    1-output-channel transposed one (``u`` = its input, plane = the output gradient)."""
+    n, oh, ow, c, uld = _nhwc(u)
+    p0 = planes[0]
+    p1 = planes[1] if len(planes) > 1 else None
+    pn, ih, iw = p0.shape
+    assert (pn, ih, iw) == (n, 2 * oh, 2 * ow) and p0.is_contiguous() and p0.dtype == torch.float32
+    dw = torch.zeros(c, 16 * len(planes), dtype=torch.float32, device=u.device)
+    _igemm_call("pai_thin_conv4x4s2_wgrad", 2.0 * n * oh * ow * c * 16 * len(planes), _ptr(u), uld, c, _ptr(p0), _ptr(p1),
+                len(planes), n, ih, iw, _ptr(dw), _stream())
+    return dw
+
+
+def thin_plane_ok(x) -> bool:
+    return x.shape[2] == 128 and x.shape[3] % 64 == 0 and x.shape[3] <= 256
+
+
+def thin_convT_plane(x, w_taps, bias=None, act=ACT_NONE):
+    """ConvTranspose2d(c, 1, 4, 2, 1) (+bias, optional Tanh): NHWC bf16 ``[n, h, 128, c]`` -> fp32 ``[n, 2h, 256]`` in one
+    streaming pass; ``w_taps``: bf16 ``[16, c]`` (row = ky*4+kx)."""
+    n, h, w, c, ld = _nhwc(x)
+    assert tuple(w_taps.shape) == (16, c) and w_taps.is_contiguous()
+    out = torch.empty(n, 2 * h, 2 * w, dtype=torch.float32, device=x.device)
+    _igemm_call("pai_thin_convT4x4s2_plane", 2.0 * n * h * w * c * 16, _ptr(x), n, h, w, c, ld, _ptr(w_taps), _ptr(bias),
+                act, _ptr(out), _stream())
+    return out
+
+
+def col2im4x4s1(p):
+    """fp32 per-tap partial products ``[n, h, w, >=16]`` -> fp32 ``[n, h-1, w-1]`` (4x4 conv, stride 1, pad 1, 1 output channel)."""
+    n, h, w, c = p.shape
+    assert p.dtype == torch.float32 and p.stride(3) == 1 and c >= 16
+    out = torch.empty(n, h - 1, w - 1, dtype=torch.float32, device=p.device)
+    lib.call("pai_col2im4x4s1", _ptr(p), p.stride(2), n, h, w, _ptr(out), _stream())
+    return out
+
+
 # ------------------------------------------------------------------------------------------ Res / Attention / Trans U-Net layers
 def pack_conv1x1_weight(w: torch.Tensor) -> torch.Tensor:
     """Conv2d weight ``[Cout, Cin, 1, 1]`` (or a Linear ``[out, in]``) -> bf16 ``[cout_pad, Cin]``."""
