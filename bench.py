@@ -148,16 +148,19 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    batch = 8            # bounded sample of the 64-image per-GPU batch (config[0]'s CPU-runnable size)
-    steps = max(1, min(args.steps, 40))
-    warmup = max(1, min(args.warmup, 3))
+    batch = args.batch   # the SAME per-GPU batch as our arm (64): about 3-4 s per step on the box's host cores
+    steps = max(1, min(args.steps, 20))
+    warmup = max(1, min(args.warmup, 2))
     rate, sec, cores, threads = cpu_reference_step_rate(steps, warmup, batch)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Pix2Pix U-Net + PatchGAN GAN training step, synthetic 1x256x256, batch 64 per GPU "
-                               "(reference arm: PyTorch CPU fp32, bounded sample of 8 images per step)"},
+        "config": {"workload": "Pix2Pix U-Net + PatchGAN GAN training step (reference UnetWrapper.training_step), "
+                               "synthetic 1x256x256 grayscale pairs, batch 64 per GPU",
+                   "batch_per_gpu": batch, "global_batch": batch, "image": "1x256x256", "loss_type": "gan",
+                   "parallelism": "cpu", "precision": "fp32 (reference default --precision 32, main.py:169-173)",
+                   "launch": "PyTorch CPU eager, all host threads"},
         "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
                          "sample": f"{steps} GAN training steps of batch {batch} (oracle/pix2pix_port.py == reference "
                                    f"models/wrapper.py:117-162 on torch CPU fp32, {threads} threads of {cores} cpus)"},
@@ -165,6 +168,94 @@ def run_reference_arm(args):
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def gpu_reference_step_rates(device, batch, steps=6, warmup=3):
+    """The honest same-box competitor (main.py:134 ``benchmark=True``): the reference's training step as
+    PyTorch eager + cuDNN on THIS GPU -- the oracle's functional restatement of models/wrapper.py:117-162 (no kernel,
+    model or engine of this repo on the path), fp32 (the reference's default precision, TF32 allowed as main.py:15
+    asks) and bf16 autocast with channels_last.  Reported next to `value`; never part of it."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pix2pix_port as port
+    out = {}
+    old = (torch.backends.cudnn.benchmark, torch.get_float32_matmul_precision())
+    torch.backends.cudnn.benchmark = True
+    torch.set_float32_matmul_precision("medium")          # main.py:15
+    torch.backends.cudnn.allow_tf32 = True
+    try:
+        x, target = synthetic_pairs(batch, seed=1234)
+        x, target = x.to(device), target.to(device)
+        for name, autocast in (("fp32_tf32_cudnn", False), ("bf16_autocast_channels_last", True)):
+            sd = port.init_state(0, in_channels=1, out_channels=1, loss_type="gan", disc_in_channels=1)
+            sd = {k: v.to(device) for k, v in sd.items()}
+            xi, ti = x, target
+            if autocast:
+                sd = {k: (v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v) for k, v in sd.items()}
+                xi, ti = x.contiguous(memory_format=torch.channels_last), target.contiguous(memory_format=torch.channels_last)
+            tr = port.OracleTrainer(sd, "gan")
+
+            def step():
+                if autocast:
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        tr.training_step(xi, ti)
+                else:
+                    tr.training_step(xi, ti)
+                tr.logged.clear()
+
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"images_per_s": batch / (ms * 1e-3), "ms_per_step": ms, "batch": batch, "steps": steps}
+            del tr, sd
+            torch.cuda.empty_cache()
+    except Exception as ex:  # pragma: no cover
+        out["error"] = f"{type(ex).__name__}: {ex}"[:300]
+    finally:
+        torch.backends.cudnn.benchmark = old[0]
+        torch.set_float32_matmul_precision(old[1])
+    out["what"] = ("reference training step (oracle/pix2pix_port.py == models/wrapper.py:117-162) as PyTorch eager + cuDNN "
+                   "on the same GPU, cudnn.benchmark=True; no code of this repo on the path")
+    return out
+
+
+def ssim_loss_roofline(device, peaks):
+    """SSIM+PSNR loss forward + fused backward (``-(30*ssim + psnr)``, models/wrapper.py:59-63) on 2048 pairs (1.07 GB
+    of inputs > L2): algorithmic 1 310 720 B per pair (forward reads, backward re-reads, gradient write)."""
+    from pai_b200 import metrics
+    n = 2048
+    g = torch.Generator(device=device).manual_seed(11)
+    base = torch.rand(n, 1, IMG, IMG, device=device, generator=g) * 2 - 1
+    pred = (base + 0.1 * torch.randn(n, 1, IMG, IMG, device=device, generator=g)).clamp_(-1, 1).requires_grad_(True)
+
+    def once():
+        s, p, _ = metrics.train_metrics(pred, base, denormalize=True)
+        loss = -(30 * s + p)
+        pred.grad = None
+        loss.backward()
+
+    for _ in range(2):
+        once()
+    torch.cuda.synchronize()
+    reps = 5
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        once()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    gbs = n * 1310720 / (ms * 1e-3) / 1e9
+    return {"kernel": "ssim_fwd_rows_kernel + ssim_bwd_coef / ssim_bwd_apply (loss forward + fused backward)", "bound": "hbm",
+            "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "pairs": n,
+            "ms": ms, "algorithmic_bytes_per_pair": 1310720, "traffic": None,
+            "includes": "the scalar torch ops of the loss (log10, mean) and autograd bookkeeping"}
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -420,15 +511,22 @@ def run_ours(args):
                 f.write(f"{name:24s} {flops / 1e9:10.2f} GFLOP {ms * 1e3:9.1f} us {flops / ms / 1e9 if ms > 0 else 0:8.1f} TFLOP/s\n")
     tot_f = sum(v[0] for v in kern.values())
     tot_t = sum(v[1] for v in kern.values())
-    peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    # the timed window is ~0.2 s at full clocks with no power cap: the burst figure is the right denominator
+    peak_tf = peaks["bf16_tflops"]
     achieved = tot_f / tot_t / 1e12 if tot_t > 0 else 0.0
+    traffic = None
+    try:        # DRAM read+write bytes per launch from the ncu pass over one step of THIS tree (profiles/scripts/step_traffic.py)
+        with open(os.path.join(ROOT, "profiles", "r2_igemm_step_traffic.json")) as f:
+            traffic = json.load(f)["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {
-        "kernel": "igemm_fprop_kernel + igemm_wgrad_kernel (tcgen05 implicit GEMM: conv/convT fprop, dgrad, wgrad)",
+        "kernel": "igemm_fprop_kernel + igemm_wgrad_kernel + thin_* (tcgen05 implicit GEMM: conv/convT fprop, dgrad, wgrad; "
+                  "every convolution launch of the step, the HBM-bound 1-2 channel layers included)",
         "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-        "peak_kind": f"{peak_kind} bf16_tflops_sustained (kernels timed inside a long step)",
-        # DRAM read+write bytes per launch, averaged over the 96 launches of one step: ncu capture in
-        # profiles/r1_igemm_step_traffic.txt (9.998 GB per step)
-        "traffic": 104.1e6,
+        "peak_kind": f"{peak_kind} bf16_tflops (burst: cuBLAS bf16 GEMM timed alone)",
+        "frac_of_sustained": achieved / peaks.get("bf16_tflops_sustained", peak_tf),
+        "traffic": traffic,
         "launches_per_step": sum(v[2] for v in kern.values()) / prof_steps,
         "algorithmic_gflop_per_step": tot_f / prof_steps / 1e9,
         "share_of_step": (tot_t / prof_steps) / (ms_step * 1e-3),
@@ -485,13 +583,20 @@ def run_ours(args):
         sweep = {"error": f"{type(ex).__name__}: {ex}"[:300]}
     if rank == 0:
         line["ssim_roofline"] = sweep
+        if world == 1:
+            try:
+                line["ssim_bwd_roofline"] = ssim_loss_roofline(dev, peaks)
+            except Exception as ex:  # pragma: no cover
+                line["ssim_bwd_roofline"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+        if world == 1 and not args.no_gpu_reference:
+            line["gpu_reference"] = gpu_reference_step_rates(dev, B)
         if world == 1 and not args.no_variants:
             line["variants"] = variant_rates(dev)
         if world == 1 and not args.no_cpu_baseline:
-            rate, sec, cores, threads = cpu_reference_step_rate(steps=20, warmup=2, batch=8)
+            rate, sec, cores, threads = cpu_reference_step_rate(steps=4, warmup=1, batch=B)
             line["cpu_baseline"] = {
                 "value": rate, "unit": "images/s", "cores": threads, "kind": "port",
-                "sample": f"20 GAN training steps of batch 8 (BASELINE.json configs[0]) after 2 warm-up steps, "
+                "sample": f"4 GAN training steps of batch {B} (the same per-GPU batch as `value`) after 1 warm-up step, "
                           f"{sec:.2f} s/step, torch CPU fp32 with {threads} threads on {cores} cpus"}
         emit(line)
     dp.barrier()
@@ -512,6 +617,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the Res / Attention / Trans U-Net step rates")
+    ap.add_argument("--no-gpu-reference", action="store_true", help="skip the PyTorch eager + cuDNN competitor on this GPU")
     ap.add_argument("--no-graph", action="store_true", help="time eager kernel launches instead of the CUDA-graph step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -329,7 +329,7 @@ int pai_attn_bwd(const void* qkv, const void* dout, int s, int b, int heads, int
 /* ---------------------------------------------------------------------------------------------
  * fp32 check path (north star: "1e-5 with the fp32 accumulate check path").  Slow, exact twins of the tensor-core
  * layers on fp32 NCHW tensors in the reference's own layouts: one thread per output element, fp32 FMA accumulation,
- * no bf16 rounding.  Forward only; used by tests through pai_b200.engine.check_path(), never by training / bench.
+ * no bf16 rounding.  Forward and backward; used by tests through pai_b200.engine.check_path(), never by training / bench.
  *   pai_check_conv2d_f32     nn.Conv2d (transposed = 0, weight [cout,cin,k,k]) or nn.ConvTranspose2d (transposed = 1,
  *                            weight [cin,cout,k,k]) with square kernel k, stride, zero padding pad; pre_act is the
  *                            activation the reference applies in front of the conv (models/pix2pix.py:62,98,
@@ -344,6 +344,17 @@ int pai_check_batchnorm_f32(const float* x, int n, int c, int hw, const float* g
                             float* running_mean, float* running_var, int training, float eps, float momentum, float* y,
                             void* stream);
 int pai_check_act_f32(const float* x, long long count, int act, float slope, float* y, void* stream);
+/* Backward twins (autograd of the three layers above, fp32, double-precision reductions):
+ *   pai_check_conv2d_wgrad_f32   dW (same layout as wt) and, if dbias != NULL, dbias[cout] = sum of g, for the layer
+ *                                y = conv(pre_act(x)); g = dL/dy [n,cout,ho,wo].  (The data gradient is pai_check_conv2d_f32
+ *                                on g with transposed flipped, followed by pai_check_act_bwd_f32 for the pre-activation.)
+ *   pai_check_batchnorm_bwd_f32  train-mode BatchNorm2d: dx, dgamma, dbeta from x and g
+ *   pai_check_act_bwd_f32        dx = g * act'(x) */
+int pai_check_conv2d_wgrad_f32(const float* x, int n, int cin, int h, int w, const float* g, int cout, int k, int stride,
+                               int pad, int pre_act, float slope, int transposed, float* dw, float* dbias, void* stream);
+int pai_check_batchnorm_bwd_f32(const float* x, const float* g, int n, int c, int hw, const float* gamma, float eps,
+                                float* dx, float* dgamma, float* dbeta, void* stream);
+int pai_check_act_bwd_f32(const float* x, const float* g, long long count, int act, float slope, float* dx, void* stream);
 
 #ifdef __cplusplus
 }

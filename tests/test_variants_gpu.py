@@ -25,6 +25,10 @@ CASES = {
     "res_50_small": ("models.res_unet", "ResUnetGAN", dict(res_type="50", channel_mults=(1, 2, 4, 8)), 4, 64, "ssim+psnr"),
     "attention": ("models.attention_unet", "AttentionUnetGAN", dict(), 2, 256, "ssim"),
     "trans_small": ("models.trans_unet", "TransUnetGAN", dict(channel_mults=(1, 2, 2), patch_size=4), 2, 256, "ssim"),
+    # the configurations BASELINE.json names (configs 3 and 4): the 8-level ResNeXt U-Net at batch 8, and the Trans U-Net
+    # main.py:93-101 builds (mults 1,2,2,4,4, patch 4: d = 4096, 1.03 G parameters)
+    "res_next_b8": ("models.res_unet", "ResUnetGAN", dict(res_type="next"), 8, 256, "ssim"),
+    "trans_full": ("models.trans_unet", "TransUnetGAN", dict(channel_mults=(1, 2, 2, 4, 4), patch_size=4), 2, 256, "ssim"),
 }
 
 

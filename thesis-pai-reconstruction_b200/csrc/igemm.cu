@@ -25,6 +25,16 @@
 
 namespace pai {
 
+// Optional role timing (build.sh -DPAI_PROFILE_ROLES): CTA 0 prints how its TMA producer, MMA issuer and one epilogue
+// warp split their cycles between waiting and working -- the measurement that says which role starves the tensor pipe.
+#ifdef PAI_PROFILE_ROLES
+#define ROLE_T0() const long long _t0 = clock64()
+#define ROLE_ADD(var) var += clock64() - _t0
+#else
+#define ROLE_T0()
+#define ROLE_ADD(var)
+#endif
+
 static constexpr int kThreads = 256;       // wgrad: 4 control/idle warps + 4 epilogue warps
 static constexpr int kFpropThreads = 384;  // fprop: 4 control/idle warps + 8 epilogue warps
 static constexpr int kMaxStages = 8;
@@ -103,10 +113,24 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = ps.tmem_base;
 
-    if (warp == 0) {
+    long long prof_wait = 0, prof_wait2 = 0, prof_total = 0;
+    (void)prof_wait, (void)prof_wait2, (void)prof_total;
+    // TMA producers: warps 0, 2 and 3 deal the k-blocks round-robin.  One elected thread needs ~250 cycles per
+    // cp.async.bulk.tensor (coordinate set-up, barrier wait, issue) -- measured with -DPAI_PROFILE_ROLES: a single
+    // producer was busy 78 % of the kernel and the MMA thread waited on it -- while an N = 128 k-block is only 256 cycles
+    // of tensor time.
+    const int pidx = warp == 0 ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : -1));
+    if (pidx >= 0) {
         if (elect_one()) {
-            int stage = 0;
+            constexpr int P = 3;
+            int g = 0, mine = pidx;              // running k-block count of this CTA / the next one this thread loads
+            int stage = pidx;
             uint32_t phase = 0;
+            while (stage >= stages) stage -= stages, phase ^= 1;
+            const int brow = PAIR ? (int)rank * cta_n : 0;     // this CTA's half of the weight tile
+#ifdef PAI_PROFILE_ROLES
+            const long long tstart = clock64();
+#endif
             for (int t = worker; t < total_tiles; t += workers) {
                 int ks, tt, nt, r, mt, phase_idx, tw, th, tn;
                 p.fd_splitk.divmod(t, tt, ks);
@@ -117,14 +141,19 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 p.fd_tiles_h.divmod(mt, tn, th);
                 const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
                 const int col0 = nt * n_tile;
-                const int kb_end = num_kb * (ks + 1) / p.splitk;
-                for (int kb = num_kb * ks / p.splitk; kb < kb_end; ++kb) {
-                    const int tap = kb / p.kc_per_tap;          // fused: box index 0..8
-                    const int kc = kb - tap * p.kc_per_tap;
-                    mbar_wait(&ps.empty[stage], phase ^ 1);
+                const int kb_begin = num_kb * ks / p.splitk, kb_end = num_kb * (ks + 1) / p.splitk;
+                const int g_end = g + (kb_end - kb_begin);
+                for (; mine < g_end; mine += P) {
+                    const int kb = kb_begin + (mine - g);
+                    int tap, kc;
+                    p.fd_kc.divmod(kb, tap, kc);                // fused: tap = box index 0..8
+                    {
+                        ROLE_T0();
+                        mbar_wait(&ps.empty[stage], phase ^ 1);
+                        ROLE_ADD(prof_wait);
+                    }
                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
                     uint8_t* sb = sa + a_bytes;
-                    const int brow = PAIR ? (int)rank * cta_n : 0;     // this CTA's half of the weight tile
                     if (fused) {
                         int nu = 0;
                         while (nu < 4 && p.box_users[tap][nu] >= 0) ++nu;
@@ -158,12 +187,14 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                             tma_load_2d(sb, &tm_b, &ps.full[stage], kb * 64, phase_idx * p.b_rows_per_phase + col0);
                         }
                     }
-                    if (++stage == stages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+                    stage += P;
+                    while (stage >= stages) stage -= stages, phase ^= 1;
                 }
+                g = g_end;
             }
+#ifdef PAI_PROFILE_ROLES
+            if (blockIdx.x == 0 && pidx == 0) printf("[roles] producer 0 of 3: total %lld cyc, waiting for empty stages %lld\n", clock64() - tstart, prof_wait);
+#endif
         }
     } else if (warp == 1) {
         if (rank == 0 && elect_one()) {
@@ -171,17 +202,28 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
+#ifdef PAI_PROFILE_ROLES
+            const long long tstart = clock64();
+#endif
             for (int t = worker; t < total_tiles; t += workers, ++it) {
                 const int a = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(&ps.acc_empty[a], acc_phase ^ 1);   // epilogue has drained this accumulator
+                {
+                    ROLE_T0();
+                    mbar_wait(&ps.acc_empty[a], acc_phase ^ 1);   // epilogue has drained this accumulator
+                    ROLE_ADD(prof_wait2);
+                }
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + a * acc_cols;
                 const int ks = t - p.fd_splitk.quot(t) * p.splitk;
                 const int kb_begin = num_kb * ks / p.splitk, kb_end = num_kb * (ks + 1) / p.splitk;
                 uint32_t started = 0;      // fused: phases whose accumulator already holds a partial sum
                 for (int kb = kb_begin; kb < kb_end; ++kb) {
-                    mbar_wait(&ps.full[stage], phase);
+                    {
+                        ROLE_T0();
+                        mbar_wait(&ps.full[stage], phase);
+                        ROLE_ADD(prof_wait);
+                    }
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
                     const uint32_t sb = sa + a_bytes;
@@ -233,6 +275,11 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 else
                     umma_commit(&ps.acc_full[a]);
             }
+#ifdef PAI_PROFILE_ROLES
+            if (blockIdx.x == 0)
+                printf("[roles] mma: total %lld cyc, waiting for full stages %lld, for a drained accumulator %lld, tiles %d, k-blocks/tile %d\n",
+                       clock64() - tstart, prof_wait, prof_wait2, it, num_kb / p.splitk);
+#endif
         }
     } else if (warp >= 4) {
         // 8 epilogue warps: warp w may read TMEM lanes (w % 4) * 32 .. +31, so the two warps of a lane quarter
@@ -261,14 +308,33 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             const long long off2 = (long long)gn * p.out2_sn + (long long)gh * p.out2_sh + (long long)gw * p.out2_sw + col0;
             const int a = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            mbar_wait(&ps.acc_full[a], acc_phase);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + a * acc_cols + ((uint32_t)(q * 32) << 16);
             const bool vec_ok = ((p.cout & 7) == 0) && ((off & 7) == 0) && ((off2 & 7) == 0);
             const bool all_vec = __all_sync(0xffffffffu, vec_ok || !row_ok);
             const bool fast = !p.out_f32 && all_vec && (n_tile & 63) == 0 && col0 + n_tile <= p.cout &&
                               (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
             // (the fused-phase mode is only launched when this holds: cout == n_tile == 64, bf16 output)
+            // fused activation backward: the saved activations of this warp's first chunk are fetched while the MMAs of
+            // the tile are still running, those of the next chunk while the current one is packed and stored
+            const bool masked = p.mask_src != nullptr && fast;
+            uint4 mreg[8];
+            auto mask_fetch = [&](int c) {
+                const long long coff = fused ? p.out_phase_off[c >> 6] : 0;
+                const __nv_bfloat16* mrow = reinterpret_cast<const __nv_bfloat16*>(p.mask_src) + off + coff + (fused ? 0 : c);
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch)
+                    mreg[ch] = row_ok ? __ldg(reinterpret_cast<const uint4*>(mrow) + ch) : make_uint4(0, 0, 0, 0);
+            };
+            if (masked && 64 * half < acc_n) mask_fetch(64 * half);
+            {
+                ROLE_T0();
+                mbar_wait(&ps.acc_full[a], acc_phase);
+                ROLE_ADD(prof_wait);
+            }
+#ifdef PAI_PROFILE_ROLES
+            const long long twork = clock64();
+#endif
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + a * acc_cols + ((uint32_t)(q * 32) << 16);
             if (fast) {
                 // ---- coalesced path: 64 channels of 32 rows are transposed through a swizzled smem tile so
                 // that 8 lanes write one full 128-byte row segment (4 rows per store instruction)
@@ -290,10 +356,10 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         const long long my_off = which == 0 ? off : off2;
                         const float* bias_c = p.bias != nullptr ? p.bias + col0 + oc : nullptr;
                         // activation / bias dispatch hoisted out of the 64-element loop
-                        if (p.mask_src != nullptr && which == 0)
-                            mask_pack(v, row_ok ? reinterpret_cast<const __nv_bfloat16*>(p.mask_src) + my_off + coff + oc
-                                                : nullptr, p.mask_slope, tile, lane);
-                        else if (act == PAI_ACT_LEAKY)
+                        if (masked && which == 0) {
+                            mask_pack(v, mreg, p.mask_slope, tile, lane);
+                            if (c + 128 < acc_n) mask_fetch(c + 128);      // this warp's next chunk (n_out == 1)
+                        } else if (act == PAI_ACT_LEAKY)
                             bias_act_pack<PAI_ACT_LEAKY>(v, bias_c, p.slope, tile, lane);
                         else if (act == PAI_ACT_RELU)
                             bias_act_pack<PAI_ACT_RELU>(v, bias_c, p.slope, tile, lane);
@@ -309,15 +375,30 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                             const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
                             const int chunk = lane >> 2, word = lane & 3;
                             float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll 8
-                            for (int row = 0; row < 32; ++row) {
-                                if (!((okmask >> row) & 1u)) continue;
-                                const uint32_t u = tw[(row * 8 + (chunk ^ (row & 7))) * 4 + word];
-                                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
-                                s0 += f.x;
-                                s1 += f.y;
-                                q0 = fmaf(f.x, f.x, q0);
-                                q1 = fmaf(f.y, f.y, q1);
+                            // all 32 shared-memory loads are issued before the first add (a per-row `continue` kept the
+                            // loop a chain of load -> use round trips: 35 cycles x 32 rows per chunk)
+                            uint32_t u[32];
+#pragma unroll
+                            for (int row = 0; row < 32; ++row) u[row] = tw[(row * 8 + (chunk ^ (row & 7))) * 4 + word];
+                            if (okmask == 0xffffffffu) {
+#pragma unroll
+                                for (int row = 0; row < 32; ++row) {
+                                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[row]));
+                                    s0 += f.x;
+                                    s1 += f.y;
+                                    q0 = fmaf(f.x, f.x, q0);
+                                    q1 = fmaf(f.y, f.y, q1);
+                                }
+                            } else {
+#pragma unroll
+                                for (int row = 0; row < 32; ++row) {
+                                    if (!((okmask >> row) & 1u)) continue;
+                                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[row]));
+                                    s0 += f.x;
+                                    s1 += f.y;
+                                    q0 = fmaf(f.x, f.x, q0);
+                                    q1 = fmaf(f.y, f.y, q1);
+                                }
                             }
                             float* bp = p.bn_part + (size_t)blockIdx.x * (2 * p.cout) + col0 + oc + 2 * lane;
                             atomicAdd(bp, s0);
@@ -389,7 +470,14 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 mbar_arrive_leader(&ps.acc_empty[a]);   // 2 x 256 arrivals (both CTAs) release the accumulator pair
             else
                 mbar_arrive(&ps.acc_empty[a]);          // 256 arrivals release the accumulator to the MMA warp
+#ifdef PAI_PROFILE_ROLES
+            prof_total += clock64() - twork;
+#endif
         }
+#ifdef PAI_PROFILE_ROLES
+        if (blockIdx.x == 0 && threadIdx.x == 128)
+            printf("[roles] epilogue warp 4: waiting for a full accumulator %lld cyc, working %lld cyc over %d tiles\n", prof_wait, prof_total, it);
+#endif
     }
     tc_fence_before();
     if (PAIR)
@@ -453,11 +541,16 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = ps.tmem_base;
 
-    if (warp == 0) {
+    // three TMA producer warps deal the work units round-robin (see igemm_fprop_kernel: one thread cannot issue the up
+    // to 8 boxes of a stage as fast as the tensor core consumes them)
+    const int pidx = warp == 0 ? 0 : (warp == 2 ? 1 : (warp == 3 ? 2 : -1));
+    if (pidx >= 0) {
         if (elect_one()) {
-            int stage = 0;
+            constexpr int P = 3;
+            int stage = pidx;
             uint32_t phase = 0;
-            for (long long u = u_begin; u < u_end; ++u) {
+            while (stage >= stages) stage -= stages, phase ^= 1;
+            for (long long u = u_begin + pidx; u < u_end; u += P) {
                 const int tile = (int)(u / p.kblocks);
                 int mt = (int)(u - (long long)tile * p.kblocks);
                 const int ng = tile % p.n_groups, cu0 = (tile / p.n_groups) * 128 * mb;
@@ -477,10 +570,8 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_consta
                     tma_load_5d(sb + nb * blk_bytes, &tm_s, &ps.full[stage], p.tap_c[tap] + cb * 64, w0 + p.tap_w[tap],
                                 p.tap_p[tap], h0 + p.tap_h[tap], n0);
                 }
-                if (++stage == stages) {
-                    stage = 0;
-                    phase ^= 1;
-                }
+                stage += P;
+                while (stage >= stages) stage -= stages, phase ^= 1;
             }
         }
     } else if (warp == 1) {
@@ -604,7 +695,7 @@ int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFp
     if (p.splitk < 1) p.splitk = 1;
     PAI_REQUIRE(!pair || (p.splitk == 1 && p.n_tile % 32 == 0), "igemm fprop: the CTA-pair kernel needs n_tile %% 32 == 0 and no split-K");
     p.fd_splitk = make_fastdiv(p.splitk), p.fd_n_tiles = make_fastdiv(n_tiles), p.fd_m_tiles = make_fastdiv(p.m_tiles);
-    p.fd_tiles_w = make_fastdiv(p.tiles_w), p.fd_tiles_h = make_fastdiv(p.tiles_h);
+    p.fd_tiles_w = make_fastdiv(p.tiles_w), p.fd_tiles_h = make_fastdiv(p.tiles_h), p.fd_kc = make_fastdiv(p.kc_per_tap);
     const long long total = (long long)p.m_tiles * n_tiles * phases * p.splitk;
     int grid;
     if (pair) {

@@ -77,13 +77,8 @@ __device__ __forceinline__ void bias_act_pack(const uint32_t (&v)[64], const flo
 }
 
 // out = acc * (saved > 0 ? 1 : slope): the activation backward of the layer whose data gradient this GEMM produces;
-// mrow = this lane's 64 saved activations (nullptr for rows outside the tensor)
-__device__ __forceinline__ void mask_pack(const uint32_t (&v)[64], const __nv_bfloat16* __restrict__ mrow, float slope,
-                                          uint4* tile, int lane) {
-    uint4 m[8];
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch)
-        m[ch] = mrow != nullptr ? __ldg(reinterpret_cast<const uint4*>(mrow) + ch) : make_uint4(0, 0, 0, 0);
+// m = this lane's 64 saved activations (zeros for rows outside the tensor), fetched by the caller ahead of time
+__device__ __forceinline__ void mask_pack(const uint32_t (&v)[64], const uint4 (&m)[8], float slope, uint4* tile, int lane) {
 #pragma unroll
     for (int ch = 0; ch < 8; ++ch) {
         const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&m[ch]);

@@ -52,7 +52,7 @@ struct IgemmFpropParams {
     void* out2;
     int act2;
     long long out2_sn, out2_sh, out2_sw;
-    FastDiv fd_splitk, fd_n_tiles, fd_m_tiles, fd_tiles_w, fd_tiles_h;   // filled by launch_igemm_fprop
+    FastDiv fd_splitk, fd_n_tiles, fd_m_tiles, fd_tiles_w, fd_tiles_h, fd_kc;   // filled by launch_igemm_fprop
     // phase-fused transposed convolution (cout_pad == n_tile == 64): one tile owns the 4 sub-pixel phases of its
     // input pixels; the 9 distinct activation boxes (dy, dx in {-1,0,1}) of a channel block are staged once and each
     // feeds the 1, 2 or 4 (phase, tap) MMAs that read it (instead of 16 separate box loads)

@@ -11,11 +11,21 @@
 //
 // Index math: SURVEY.md Appendix B (stride-2 taps  in = 2*o - 1 + k;  ConvT phases T[0] = {(k=1,d=0),(k=3,d=-1)},
 // T[1] = {(k=0,d=+1),(k=2,d=0)}).
+#include <stdlib.h>
+
 #include "pai_common.cuh"
 #include "pai_epilogue.cuh"
 #include "pai_kernels.h"
 
 namespace pai {
+
+#ifdef PAI_PROFILE_ROLES
+#define TROLE_T0() const long long _t0 = clock64()
+#define TROLE_ADD(var) var += clock64() - _t0
+#else
+#define TROLE_T0()
+#define TROLE_ADD(var)
+#endif
 
 // =============================================================================================
 // thin_conv_fprop: out[pix, co] = act(bias[co] + sum_{t, j} plane_j[n, 2*oy-1+ky, 2*ox-1+kx] * W[co][t*CIN + j])
@@ -71,16 +81,38 @@ __device__ __forceinline__ void thin_store_dispatch(const uint32_t (&v)[64], con
         thin_store_chunk<PAI_ACT_NONE>(v, bias, slope, tile, lane, dst, row_off, row_ok);
 }
 
-template <int CIN>
+//
+// STREAM (256-pixel wide images: a tile is one output row): the CTA owns a contiguous range of output rows and the input
+// rows arrive through a 16-slot shared-memory ring of two-row granules filled by bulk async copies (one thread, many KB
+// in flight), so the producers read shared memory instead of waiting a DRAM round trip per tile and every input row is
+// fetched once per CTA instead of twice.  Granule g holds input rows 2g+1 and 2g+2; output row oy needs granules oy-1, oy.
+static constexpr int kThinRing = 16;
+static constexpr int kThinRowW = 256;
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int CIN, bool STREAM>
 __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(const ThinFpropParams p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ ThinPipe ps;
+    __shared__ uint64_t ring_full[kThinRing], ring_empty[kThinRing];
     __shared__ uint4 stage_buf[8][32 * 8];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;                       // 2 x [128 rows x 128 B]
     uint8_t* sB = smem + 2 * 16384;           // [cout rows x 128 B]
+    float* ring = reinterpret_cast<float*>(sB + (size_t)p.cout * 128);   // STREAM: [slot][plane][2 rows][256] fp32
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t acc_cols = tmem_cols_for(p.cout);
+    // tiles of this CTA: STREAM -> the output rows [t_begin, t_begin + t_count), else strided over the grid
+    const long long t_begin = STREAM ? (long long)p.tiles * blockIdx.x / gridDim.x : (long long)blockIdx.x;
+    const long long t_step = STREAM ? 1 : (long long)gridDim.x;
+    const int t_count = STREAM ? (int)((long long)p.tiles * (blockIdx.x + 1) / gridDim.x - t_begin)
+                               : (int)(((long long)p.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
     // resident weight tile (generic-proxy writes, made visible to the tensor core by the proxy fence below)
     for (int i = threadIdx.x; i < p.cout * 8; i += kThinFpropThreads) {
@@ -95,6 +127,11 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
             mbar_init(&ps.acc_full[s], 1);
             mbar_init(&ps.acc_empty[s], 128);
         }
+        if (STREAM)
+            for (int s = 0; s < kThinRing; ++s) {
+                mbar_init(&ring_full[s], 1);
+                mbar_init(&ring_empty[s], 128);
+            }
         mbar_fence_init();
     }
     if (warp == 4) tmem_alloc(&ps.tmem_base, 2 * acc_cols);
@@ -103,8 +140,120 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
     tc_fence_after();
     const uint32_t tmem_base = ps.tmem_base;
 
-    if (warp < 4) {
-        // ---------------- producers: one im2col row (= output pixel) per thread
+    if (warp < 4 && STREAM) {
+        // ---------------- producers (streaming): thread r <-> output column r of the CTA's current output row
+        const int r = warp * 32 + lane;
+        int gc = 0;                                   // granule counter of this CTA (same sequence as the loader's)
+        int i = 0;
+        long long row = t_begin;
+        const long long row_end = t_begin + t_count;
+        long long w_ring = 0, w_slot = 0;
+        (void)w_ring, (void)w_slot;
+#ifdef PAI_PROFILE_ROLES
+        const long long tstart = clock64();
+#endif
+        while (row < row_end) {
+            const int img = (int)(row / p.oh);
+            const int a_lo = (int)(row - (long long)img * p.oh);
+            const long long img_end = (long long)(img + 1) * p.oh;
+            const int a_hi = (int)((img_end < row_end ? img_end : row_end) - (long long)img * p.oh);
+            mbar_wait(&ring_full[gc % kThinRing], (uint32_t)((gc / kThinRing) & 1));          // granule a_lo - 1
+            for (int a = a_lo; a < a_hi; ++a, ++i, ++gc) {
+                const int g1 = gc + 1;                                                       // granule a
+                {
+                    TROLE_T0();
+                    mbar_wait(&ring_full[g1 % kThinRing], (uint32_t)((g1 / kThinRing) & 1));
+                    TROLE_ADD(w_ring);
+                }
+                uint32_t words[8 * CIN];
+#pragma unroll
+                for (int j = 0; j < CIN; ++j) {
+                    float v[16];
+#pragma unroll
+                    for (int ky = 0; ky < 4; ++ky) {
+                        const int iy = 2 * a - 1 + ky;
+                        const bool rok = iy >= 0 && iy < p.ih;
+                        const int gsl = (ky < 2 ? gc : g1) % kThinRing;
+                        // granule rows: ky 0 -> row 2(a-1)+1 (first row of granule a-1), ky 1 -> its second, ky 2, 3 -> granule a
+                        const float* rp = ring + ((size_t)(gsl * CIN + j) * 2 + (ky & 1)) * kThinRowW;
+                        float2 mid = make_float2(0.f, 0.f);
+                        float lft = 0.f, rgt = 0.f;
+                        if (rok) {
+                            mid = *reinterpret_cast<const float2*>(rp + 2 * r);
+                            if (r > 0) lft = rp[2 * r - 1];
+                            if (2 * r + 2 < kThinRowW) rgt = rp[2 * r + 2];
+                        }
+                        v[ky * 4 + 0] = lft, v[ky * 4 + 1] = mid.x, v[ky * 4 + 2] = mid.y, v[ky * 4 + 3] = rgt;
+                    }
+                    if (CIN == 1) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+                            words[q] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                    } else {
+                        // word q = (plane 0, plane 1) of tap q: plane 0 fills the low halves first, plane 1 the high ones
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[q]));
+                            words[q] = j == 0 ? hb : (words[q] | (hb << 16));
+                        }
+                    }
+                }
+                mbar_arrive(&ring_empty[gc % kThinRing]);           // granule a-1 is not needed after this tile
+                const int s = i & 1;
+                {
+                    TROLE_T0();
+                    mbar_wait(&ps.a_empty[s], (uint32_t)(((i >> 1) & 1) ^ 1));
+                    TROLE_ADD(w_slot);
+                }
+                uint8_t* a_tile = sA + s * 16384;
+#pragma unroll
+                for (int c = 0; c < 2 * CIN; ++c)
+                    *reinterpret_cast<uint4*>(a_tile + sw128_off(r, c)) =
+                        make_uint4(words[4 * c], words[4 * c + 1], words[4 * c + 2], words[4 * c + 3]);
+                fence_proxy_async_smem();
+                mbar_arrive(&ps.a_full[s]);
+            }
+            mbar_arrive(&ring_empty[gc % kThinRing]);               // last granule of the segment
+            ++gc;
+            row = (long long)img * p.oh + a_hi;
+        }
+#ifdef PAI_PROFILE_ROLES
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            printf("[thin roles] producer: total %lld cyc, waiting for input rows %lld, for a free A slot %lld, tiles %d\n",
+                   clock64() - tstart, w_ring, w_slot, i);
+#endif
+    } else if (warp == 5 && STREAM) {
+        // ---------------- loader: bulk async copies of the input rows into the granule ring
+        if (elect_one()) {
+            int gc = 0;
+            long long row = t_begin;
+            const long long row_end = t_begin + t_count;
+            while (row < row_end) {
+                const int img = (int)(row / p.oh);
+                const int a_lo = (int)(row - (long long)img * p.oh);
+                const long long img_end = (long long)(img + 1) * p.oh;
+                const int a_hi = (int)((img_end < row_end ? img_end : row_end) - (long long)img * p.oh);
+                for (int g = a_lo - 1; g < a_hi; ++g, ++gc) {
+                    const int sl = gc % kThinRing;
+                    mbar_wait(&ring_empty[sl], (uint32_t)(((gc / kThinRing) & 1) ^ 1));
+                    const int r0 = 2 * g + 1, r1 = 2 * g + 2;
+                    const bool ok0 = r0 >= 0, ok1 = r1 < p.ih;
+                    mbar_expect_tx(&ring_full[sl], (uint32_t)(((ok0 ? 1 : 0) + (ok1 ? 1 : 0)) * CIN * kThinRowW * 4));
+#pragma unroll
+                    for (int j = 0; j < CIN; ++j) {
+                        const float* src = (j == 0 ? p.p0 : p.p1) + (size_t)img * p.ih * p.iw;
+                        float* dst = ring + (size_t)(sl * CIN + j) * 2 * kThinRowW;
+                        if (ok0) bulk_g2s(dst, src + (size_t)r0 * p.iw, kThinRowW * 4, &ring_full[sl]);
+                        if (ok1) bulk_g2s(dst + kThinRowW, src + (size_t)r1 * p.iw, kThinRowW * 4, &ring_full[sl]);
+                    }
+                }
+                row = (long long)img * p.oh + a_hi;
+            }
+        }
+    } else if (warp < 4) {
+        // ---------------- producers (gather): one im2col row (= output pixel) per thread, loads straight from global
         const int r = warp * 32 + lane;
         float v[CIN][16];
         auto load_tile = [&](long long tile) {
@@ -129,8 +278,8 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
                 }
             }
         };
-        if (blockIdx.x < p.tiles) load_tile(blockIdx.x);
-        for (int i = 0; (long long)blockIdx.x + (long long)i * gridDim.x < p.tiles; ++i) {
+        if (t_count > 0) load_tile(t_begin);
+        for (int i = 0; i < t_count; ++i) {
             const int s = i & 1;
             uint32_t words[8 * CIN];
             if (CIN == 1) {
@@ -146,8 +295,7 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
                     words[q] = *reinterpret_cast<uint32_t*>(&h);
                 }
             }
-            const long long next = (long long)blockIdx.x + (long long)(i + 1) * gridDim.x;
-            if (next < p.tiles) load_tile(next);                         // in flight during the wait / stores below
+            if (i + 1 < t_count) load_tile(t_begin + (long long)(i + 1) * t_step);   // in flight during the wait / stores below
             mbar_wait(&ps.a_empty[s], (uint32_t)(((i >> 1) & 1) ^ 1));   // the MMAs that read this slot have completed
             uint8_t* a_tile = sA + s * 16384;
 #pragma unroll
@@ -162,11 +310,24 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
         if (elect_one()) {
             const uint32_t idesc = umma_idesc_bf16(128, p.cout, 0, 0);
             const uint64_t db0 = umma_desc_kmajor_sw128(smem_u32(sB));
-            for (int i = 0; (long long)blockIdx.x + (long long)i * gridDim.x < p.tiles; ++i) {
+            long long w_acc = 0, w_a = 0;
+            (void)w_acc, (void)w_a;
+#ifdef PAI_PROFILE_ROLES
+            const long long tstart = clock64();
+#endif
+            for (int i = 0; i < t_count; ++i) {
                 const int s = i & 1;
                 const uint32_t ph = (uint32_t)((i >> 1) & 1);
-                mbar_wait(&ps.acc_empty[s], ph ^ 1);
-                mbar_wait(&ps.a_full[s], ph);
+                {
+                    TROLE_T0();
+                    mbar_wait(&ps.acc_empty[s], ph ^ 1);
+                    TROLE_ADD(w_acc);
+                }
+                {
+                    TROLE_T0();
+                    mbar_wait(&ps.a_full[s], ph);
+                    TROLE_ADD(w_a);
+                }
                 tc_fence_after();
                 const uint64_t da0 = umma_desc_kmajor_sw128(smem_u32(sA + s * 16384));
                 const uint32_t td = tmem_base + s * acc_cols;
@@ -175,6 +336,11 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
                 umma_commit(&ps.a_empty[s]);
                 umma_commit(&ps.acc_full[s]);
             }
+#ifdef PAI_PROFILE_ROLES
+            if (blockIdx.x == 0)
+                printf("[thin roles] mma: total %lld cyc, waiting for a drained accumulator %lld, for a built A tile %lld\n",
+                       clock64() - tstart, w_acc, w_a);
+#endif
         }
     } else if (warp >= 8) {
         // ---------------- epilogue: group g drains accumulator g (tiles of parity g)
@@ -183,11 +349,20 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
         const int r = q * 32 + lane;
         uint4* tile_buf = stage_buf[warp - 8];
         int k = 0;
-        for (int i = g; (long long)blockIdx.x + (long long)i * gridDim.x < p.tiles; i += 2, ++k) {
-            const long long tile = (long long)blockIdx.x + (long long)i * gridDim.x;
+        long long ep_wait = 0, ep_work = 0;
+        (void)ep_wait, (void)ep_work;
+        for (int i = g; i < t_count; i += 2, ++k) {
+            const long long tile = t_begin + (long long)i * t_step;
             const long long pix = tile * 128 + r;
             const bool row_ok = pix < p.total_pix;
-            mbar_wait(&ps.acc_full[g], (uint32_t)(k & 1));
+            {
+                TROLE_T0();
+                mbar_wait(&ps.acc_full[g], (uint32_t)(k & 1));
+                TROLE_ADD(ep_wait);
+            }
+#ifdef PAI_PROFILE_ROLES
+            const long long tw0 = clock64();
+#endif
             tc_fence_after();
             const uint32_t td = tmem_base + g * acc_cols + ((uint32_t)(q * 32) << 16);
             for (int c0 = 0; c0 < p.cout; c0 += 64) {
@@ -203,7 +378,15 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
             }
             tc_fence_before();
             mbar_arrive(&ps.acc_empty[g]);
+#ifdef PAI_PROFILE_ROLES
+            ep_work += clock64() - tw0;
+#endif
         }
+#ifdef PAI_PROFILE_ROLES
+        if (blockIdx.x == 0 && lane == 0 && (warp == 8 || warp == 12))
+            printf("[thin roles] epilogue warp %d: waiting for a full accumulator %lld cyc, working %lld cyc over %d tiles\n", warp,
+                   ep_wait, ep_work, k);
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -615,7 +798,7 @@ extern "C" {
 
 int pai_thin_conv4x4s2_fprop(const float* plane0, const float* plane1, int cin, int n, int ih, int iw,
                              const void* w_packed, int cout, const float* bias, void* out1, int ld1, int act1, void* out2,
-                             int ld2, int act2, float slope, void* stream) {
+                             int ld2, int act2, float slope, void* stream_) {
     PAI_REQUIRE(plane0 && w_packed && out1 && (cin == 1 || (cin == 2 && plane1)), "pai_thin_conv4x4s2_fprop: bad planes / cin=%d", cin);
     PAI_REQUIRE(ih % 2 == 0 && iw % 2 == 0 && n > 0, "pai_thin_conv4x4s2_fprop: even image sizes (got %dx%d)", ih, iw);
     PAI_REQUIRE(cout >= 64 && cout <= 256 && cout % 64 == 0, "pai_thin_conv4x4s2_fprop: cout (%d) must be 64..256, %% 64", cout);
@@ -633,18 +816,29 @@ int pai_thin_conv4x4s2_fprop(const float* plane0, const float* plane1, int cin, 
     p.fd_ow = make_fastdiv(p.ow), p.fd_oh = make_fastdiv(p.oh);
     const int dev = current_device(), sms = sm_count(dev);
     if (sms < 0) return -1;
-    const size_t smem = 2 * 16384 + (size_t)cout * 128 + 1024;
+    // 256-pixel wide images take the row-streaming form (bulk-copied input rows in a shared-memory ring)
+    const bool stream = iw == kThinRowW && (reinterpret_cast<uintptr_t>(plane0) & 15) == 0 &&
+                        (plane1 == nullptr || (reinterpret_cast<uintptr_t>(plane1) & 15) == 0) && getenv("PAI_THIN_GATHER") == nullptr;
+    const size_t smem = 2 * 16384 + (size_t)cout * 128 + (stream ? (size_t)kThinRing * cin * 2 * kThinRowW * 4 : 0) + 1024;
     static DeviceOnce once;
     if (once.need(dev)) {
-        PAI_CUDA_OK(cudaFuncSetAttribute(thin_conv_fprop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-        PAI_CUDA_OK(cudaFuncSetAttribute(thin_conv_fprop_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        const int cap = 2 * 16384 + 256 * 128 + kThinRing * 2 * 2 * kThinRowW * 4 + 1024;
+        PAI_CUDA_OK(cudaFuncSetAttribute(thin_conv_fprop_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        PAI_CUDA_OK(cudaFuncSetAttribute(thin_conv_fprop_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        PAI_CUDA_OK(cudaFuncSetAttribute(thin_conv_fprop_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+        PAI_CUDA_OK(cudaFuncSetAttribute(thin_conv_fprop_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
         once.mark(dev);
     }
     const int grid = p.tiles < sms ? p.tiles : sms;
-    if (cin == 1)
-        thin_conv_fprop_kernel<1><<<grid, kThinFpropThreads, smem, (cudaStream_t)stream>>>(p);
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (cin == 1 && stream)
+        thin_conv_fprop_kernel<1, true><<<grid, kThinFpropThreads, smem, st>>>(p);
+    else if (cin == 1)
+        thin_conv_fprop_kernel<1, false><<<grid, kThinFpropThreads, smem, st>>>(p);
+    else if (stream)
+        thin_conv_fprop_kernel<2, true><<<grid, kThinFpropThreads, smem, st>>>(p);
     else
-        thin_conv_fprop_kernel<2><<<grid, kThinFpropThreads, smem, (cudaStream_t)stream>>>(p);
+        thin_conv_fprop_kernel<2, false><<<grid, kThinFpropThreads, smem, st>>>(p);
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -195,9 +195,11 @@ _check = False
 
 
 class check_path:
-    """``with engine.check_path(): y = model(x)`` runs the drop-in generator / PatchGAN forward on the exact fp32
-    kernels of csrc/check_f32.cu (fp32 NCHW tensors, fp32 FMA accumulation, no bf16 operands) instead of the
-    tcgen05 path -- the north star's "1e-5 with the fp32 accumulate check path".  Forward only (no autograd graph)."""
+    """``with engine.check_path(): y = model(x)`` runs the drop-in generator / PatchGAN on the exact fp32 kernels of
+    csrc/check_f32.cu (fp32 NCHW tensors, fp32 FMA accumulation, no bf16 operands) instead of the tcgen05 path -- the
+    north star's "1e-5 with the fp32 accumulate check path".  Forward AND backward: ``loss.backward()`` on a graph built
+    inside the context gives fp32 check-path gradients of every parameter (wrong index math in a deep wgrad shows up as a
+    1e-1 error here, while the bf16 path can only be held to its 8-12 % noise floor)."""
 
     def __enter__(self):
         global _check
@@ -214,19 +216,77 @@ def check_path_enabled() -> bool:
     return _check
 
 
+class _CheckConv(torch.autograd.Function):
+    """``y = conv(pre_act(x), w) + b`` (Conv2d or ConvTranspose2d) on the fp32 check kernels, with its exact fp32 backward:
+    data gradient = the opposite convolution of ``g`` times ``pre_act'(x)``, weight / bias gradients by
+    ``pai_check_conv2d_wgrad_f32`` (double-precision reductions)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, pad, pre_act, transposed):
+        y = ops.check_conv2d(x, w, b, stride=stride, pad=pad, pre_act=pre_act, slope=SLOPE, transposed=transposed)
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (stride, pad, pre_act, transposed, b is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        stride, pad, pre_act, transposed, has_b = ctx.cfg
+        g = g.contiguous().float()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = ops.check_conv2d(g, w, None, stride=stride, pad=pad, pre_act=ACT_NONE, transposed=not transposed)
+            if gx.shape != x.shape:          # stride-2 transposed convolution of an odd-sized gradient cannot happen here
+                raise RuntimeError(f"pai_b200 check path: data-gradient shape {tuple(gx.shape)} != input {tuple(x.shape)}")
+            if pre_act != ACT_NONE:
+                gx = ops.check_act_bwd(x, gx, pre_act, SLOPE)
+        if ctx.needs_input_grad[1] or (has_b and ctx.needs_input_grad[2]):
+            gw, gb = ops.check_conv2d_wgrad(x, g, tuple(w.shape), stride=stride, pad=pad, pre_act=pre_act, slope=SLOPE,
+                                            transposed=transposed, want_bias=has_b)
+        return gx, gw, gb, None, None, None, None
+
+
+class _CheckBN(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, bn, training):
+        y = ops.check_batchnorm(x, gamma, beta, bn.running_mean, bn.running_var, training, eps=BN_EPS, momentum=BN_MOMENTUM)
+        if training:
+            bn.num_batches_tracked.add_(1)
+        ctx.save_for_backward(x, gamma)
+        ctx.training = training
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        if not ctx.training:
+            raise RuntimeError("pai_b200 check path: BatchNorm backward is implemented for train mode (batch statistics)")
+        x, gamma = ctx.saved_tensors
+        dx, dgamma, dbeta = ops.check_batchnorm_bwd(x, g.contiguous().float(), gamma, eps=BN_EPS)
+        return dx, dgamma, dbeta, None, None
+
+
+class _CheckAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act):
+        ctx.save_for_backward(x)
+        ctx.act = act
+        return ops.check_act(x, act)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return ops.check_act_bwd(x, g.contiguous().float(), ctx.act, SLOPE), None
+
+
 def _check_bn(v, bn, training):
     if bn is None:
         return v
-    y = ops.check_batchnorm(v, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, training,
-                            eps=BN_EPS, momentum=BN_MOMENTUM)
-    if training:
-        bn.num_batches_tracked.add_(1)
-    return y
+    return _CheckBN.apply(v, bn.weight, bn.bias, bn, training)
 
 
-@torch.no_grad()
 def unet_forward_check(spec: "UnetSpec", x: torch.Tensor, training: bool) -> torch.Tensor:
-    """``Unet.forward`` (models/pix2pix.py:198-216) layer by layer on the fp32 check kernels."""
+    """``Unet.forward`` (models/pix2pix.py:198-216) layer by layer on the fp32 check kernels (differentiable: every
+    node has an exact fp32 backward, so ``loss.backward()`` under ``check_path()`` yields check-path gradients)."""
     if training and any(p > 0 for p in spec.dec_dropout):
         raise RuntimeError("pai_b200: the fp32 check path has no Dropout2d (it is a deterministic forward check)")
     L = spec.levels
@@ -234,8 +294,7 @@ def unet_forward_check(spec: "UnetSpec", x: torch.Tensor, training: bool) -> tor
     v = x.contiguous().float()
     for i in range(L):
         conv = spec.enc_convs[i]
-        v = ops.check_conv2d(v, conv.weight.detach(), conv.bias.detach(), pre_act=ACT_NONE if i == 0 else ACT_LEAKY,
-                             slope=SLOPE)
+        v = _CheckConv.apply(v, conv.weight, conv.bias, 2, 1, ACT_NONE if i == 0 else ACT_LEAKY, False)
         v = _check_bn(v, spec.enc_bns[i], training)
         skips.append(v)
     for j in range(L):
@@ -243,21 +302,18 @@ def unet_forward_check(spec: "UnetSpec", x: torch.Tensor, training: bool) -> tor
         if j > 0:
             v = torch.cat([v, skips[L - 1 - j]], dim=1)            # models/pix2pix.py:212
         # every DecoderBlock starts with a ReLU; the last decoder is a bare ConvTranspose2d (:185-193)
-        v = ops.check_conv2d(v, conv.weight.detach(), conv.bias.detach(), pre_act=ACT_RELU if j < L - 1 else ACT_NONE,
-                             transposed=True)
+        v = _CheckConv.apply(v, conv.weight, conv.bias, 2, 1, ACT_RELU if j < L - 1 else ACT_NONE, True)
         v = _check_bn(v, spec.dec_bns[j], training)
-    return ops.check_act(v, ACT_TANH)
+    return _CheckAct.apply(v, ACT_TANH)
 
 
-@torch.no_grad()
 def disc_forward_check(spec: "DiscSpec", x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     """``Discriminator.forward`` (models/wrapper.py:236-238): conv -> LeakyReLU blocks, bias-free stride-1 head."""
     v = torch.cat([x.float(), y.float()], dim=1).contiguous()
     K = len(spec.convs)
     for k, conv in enumerate(spec.convs):
         head = k == K - 1
-        v = ops.check_conv2d(v, conv.weight.detach(), None if conv.bias is None else conv.bias.detach(),
-                             stride=1 if head else 2, pad=1, pre_act=ACT_NONE if k == 0 else ACT_LEAKY, slope=SLOPE)
+        v = _CheckConv.apply(v, conv.weight, conv.bias, 1 if head else 2, 1, ACT_NONE if k == 0 else ACT_LEAKY, False)
     return v
 
 

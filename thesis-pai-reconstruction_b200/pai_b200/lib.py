@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpai_b200.so")
+# PAI_LIB_PATH: an alternative build of the same library (e.g. csrc/build.sh -DPAI_PROFILE_ROLES), for profiling runs
+LIB_PATH = os.environ.get("PAI_LIB_PATH") or os.path.join(_HERE, "libpai_b200.so")
 
 c_int, c_float, c_void_p, c_ll = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_longlong
 
@@ -94,6 +95,11 @@ SIGNATURES = {
     "pai_check_batchnorm_f32": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
                                 c_float, c_void_p, c_void_p],
     "pai_check_act_f32": [c_void_p, c_ll, c_int, c_float, c_void_p, c_void_p],
+    "pai_check_conv2d_wgrad_f32": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float,
+                                   c_int, c_void_p, c_void_p, c_void_p],
+    "pai_check_batchnorm_bwd_f32": [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                    c_void_p],
+    "pai_check_act_bwd_f32": [c_void_p, c_void_p, c_ll, c_int, c_float, c_void_p, c_void_p],
     "pai_thin_conv4x4s2_fprop": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                  c_int, c_void_p, c_int, c_int, c_float, c_void_p],
     "pai_thin_conv4x4s2_wgrad": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],

@@ -705,3 +705,34 @@ def check_act(x, act, slope=0.2):
     y = torch.empty_like(x)
     lib.call("pai_check_act_f32", _ptr(x), x.numel(), act, slope, _ptr(y), _stream())
     return y
+
+
+def check_conv2d_wgrad(x, g, w_shape, stride=2, pad=1, pre_act=ACT_NONE, slope=0.2, transposed=False, want_bias=True):
+    """-> (dW in the weight's own layout, dbias or None) of ``y = conv(pre_act(x))`` given ``g = dL/dy`` (fp32 NCHW)."""
+    x, g = x.contiguous(), g.contiguous()
+    n, cin, h, wd = x.shape
+    cout, k = g.shape[1], w_shape[2]
+    dw = torch.empty(w_shape, dtype=torch.float32, device=x.device)
+    db = torch.empty(cout, dtype=torch.float32, device=x.device) if want_bias else None
+    lib.call("pai_check_conv2d_wgrad_f32", _ptr(x), n, cin, h, wd, _ptr(g), cout, k, stride, pad, pre_act, slope,
+             1 if transposed else 0, _ptr(dw), _ptr(db), _stream(), kernels=2 if want_bias else 1)
+    return dw, db
+
+
+def check_batchnorm_bwd(x, g, gamma, eps=1e-5):
+    x, g = x.contiguous(), g.contiguous()
+    n, c = x.shape[0], x.shape[1]
+    hw = x.numel() // max(n * c, 1)
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+    lib.call("pai_check_batchnorm_bwd_f32", _ptr(x), _ptr(g), n, c, hw, _ptr(gamma), eps, _ptr(dx), _ptr(dgamma), _ptr(dbeta),
+             _stream())
+    return dx, dgamma, dbeta
+
+
+def check_act_bwd(x, g, act, slope=0.2):
+    x, g = x.contiguous(), g.contiguous()
+    dx = torch.empty_like(x)
+    lib.call("pai_check_act_bwd_f32", _ptr(x), _ptr(g), x.numel(), act, slope, _ptr(dx), _stream())
+    return dx
