@@ -90,14 +90,36 @@ def test_check_path_against_oracle_port_other_seeds(n):
     assert float((lg.cpu() - lo).abs().max()) < 1e-5
 
 
+def _oracle_grads(sd, loss_type, x, target, dtype):
+    """Generator-loss gradients of the oracle in ``dtype`` (fp32 = the reference's arithmetic, fp64 = the exact answer)."""
+    import bf16_sites                                    # oracle/: dtype-agnostic restatement of Unet.forward (train mode)
+    s = {}
+    for k, v in sd.items():
+        if v.is_floating_point():
+            w = v.detach().clone().to(dtype)
+            if port._is_param(k):
+                w.requires_grad_(True)
+            s[k] = w
+        else:
+            s[k] = v.clone()
+    xx, tt = x.to(dtype), target.to(dtype)
+    y = bf16_sites.fwd(s, xx, set())
+    loss = port.generator_loss(s, loss_type, xx, y, tt)
+    loss.backward()
+    g = {k: v.grad.double() for k, v in s.items() if k.startswith("unet.") and v.is_floating_point() and v.grad is not None}
+    return g, float(loss.detach()), s
+
+
 @pytest.mark.parametrize("loss_type,n", [("gan", 2), ("ssim+psnr", 3)])
 def test_check_path_backward_every_parameter_gradient(loss_type, n):
     """The fp32 check path is differentiable (csrc/check_f32.cu: fp32 dgrad / wgrad / BatchNorm / activation backward):
     EVERY generator parameter gradient of one loss evaluation -- and, for the GAN loss, every PatchGAN gradient of the
-    discriminator loss -- must equal the CPU oracle's fp32 autograd gradient to 2e-3 of its norm (measured: <= 3e-4;
-    train-mode BatchNorm over N*4 values amplifies fp32 summation-order differences, nothing else does).  The bf16
-    tensor-core path can only be held to its 8-12 % noise floor on the deep layers, so wrong index math in a deep
-    weight gradient is caught HERE."""
+    discriminator loss -- is compared with the oracle evaluated in **fp64** (the exact gradient).  The randomly
+    initialised network is badly conditioned at these batch sizes (train-mode BatchNorm over N*4 values): the
+    reference's own fp32 arithmetic on the CPU is 0.5-1.1e-2 away from its fp64 evaluation on the deep layers
+    (oracle/grad_conditioning.py), so the bound per tensor is 3x the CPU-fp32 error of that tensor + 2e-3 -- i.e. the check path
+    must be as good as the reference's fp32, which wrong index math in a deep weight gradient (a 1e-1 .. 1 error) is
+    not.  The bf16 tensor-core path can only be held to its 8-12 % noise floor there."""
     from pai_b200 import engine
     m = _build(seed=11)
     if loss_type != "gan":
@@ -105,45 +127,45 @@ def test_check_path_backward_every_parameter_gradient(loss_type, n):
     m.train()
     sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
     x, target = port.synthetic_pairs(n, seed=90 + n)
-    tr = port.OracleTrainer(sd, loss_type if loss_type != "gan" else "gan")
-    # ---- oracle: generator loss gradients
-    yo = port.unet_forward(tr.sd, x, training=True)
-    lo = port.generator_loss(tr.sd, loss_type, x, yo, target)
-    lo.backward()
-    ref = {k: tr.sd[k].grad.clone() for k in tr.g_keys}
+    r32, l32, _ = _oracle_grads(sd, loss_type, x, target, torch.float32)
+    r64, l64, s64 = _oracle_grads(sd, loss_type, x, target, torch.float64)
     with engine.check_path():
         y = m(x.cuda())
         loss = m.loss(x.cuda(), y, target.cuda())
         loss.backward()
-    assert float(loss.detach()) == pytest.approx(float(lo.detach()), rel=1e-4, abs=1e-5)
+    assert float(loss.detach()) == pytest.approx(l64, rel=1e-4, abs=1e-5)
     named = dict(m.named_parameters())
-    worst = 0.0
-    for k in tr.g_keys:
-        g, go = named[k].grad.cpu().double(), ref[k].double()
+    worst = (0.0, 0.0, "")
+    for k, go in r64.items():
+        g = named[k].grad.cpu().double()
         gn = float(go.norm())
         if gn < 1e-5:            # conv bias in front of a BatchNorm: exactly cancelled, only rounding noise
             assert float(g.norm()) < 1e-4, k
             continue
-        rel = float((g - go).norm()) / gn
-        worst = max(worst, rel)
-        assert rel < 2e-3, (k, rel, gn)
-    print(f"check-path generator gradients ({loss_type}): worst relative error {worst:.2e}")
+        e_check = float((g - go).norm()) / gn
+        e_cpu = float((r32[k] - go).norm()) / gn
+        worst = max(worst, (e_check, e_cpu, k))
+        assert e_check < 3 * e_cpu + 2e-3, (k, e_check, e_cpu)
+    print(f"check-path generator gradients ({loss_type}): worst error vs fp64 {worst[0]:.2e} (CPU fp32: {worst[1]:.2e}) at {worst[2]}")
     if loss_type == "gan":
-        # ---- discriminator loss gradients (models/wrapper.py:126-135)
-        for kk in tr.g_keys + tr.d_keys:
-            tr.sd[kk].grad = None
-        m.zero_grad(set_to_none=True)
+        # ---- discriminator loss gradients (models/wrapper.py:126-135), against the fp64 oracle
         with torch.no_grad():
-            pred_o = port.unet_forward(tr.sd, x, training=True)
-        d_lo = port.discriminator_loss(port.disc_forward(tr.sd, x, pred_o), port.disc_forward(tr.sd, x, target))
+            pred64 = __import__("bf16_sites").fwd(s64, x.double(), set())
+        for v in s64.values():
+            if v.is_floating_point():
+                v.grad = None
+        d_lo = port.discriminator_loss(port.disc_forward(s64, x.double(), pred64), port.disc_forward(s64, x.double(), target.double()))
         d_lo.backward()
+        m.zero_grad(set_to_none=True)
         with engine.check_path():
             with torch.no_grad():
                 pred = m.unet(x.cuda())
             d_loss = m.discriminator_loss(m.discriminator(x.cuda(), pred), m.discriminator(x.cuda(), target.cuda()))
             d_loss.backward()
         assert float(d_loss.detach()) == pytest.approx(float(d_lo.detach()), rel=1e-4)
-        for k in tr.d_keys:
-            g, go = named[k].grad.cpu().double(), tr.sd[k].grad.double()
+        for k, v in s64.items():
+            if not (k.startswith("discriminator.") and v.is_floating_point()):
+                continue
+            g, go = named[k].grad.cpu().double(), v.grad.double()
             rel = float((g - go).norm()) / float(go.norm())
             assert rel < 2e-3, (k, rel)

@@ -59,26 +59,33 @@ struct __align__(8) ThinPipe {
     uint32_t tmem_base;
 };
 
+// The warp's 32 rows are 32 consecutive pixels pix0 .. pix0+31 of a tensor with pixel stride ld: the row addresses
+// follow from the (warp-uniform) first pixel, no shuffles.
 template <int ACT>
-__device__ __forceinline__ void thin_store_chunk(const uint32_t (&v)[64], const float* bias, float slope, uint4* tile,
-                                                 int lane, __nv_bfloat16* dst, long long row_off, bool row_ok) {
-    bias_act_pack<ACT>(v, bias, slope, tile, lane);
+__device__ __forceinline__ void thin_store_chunk(const uint32_t (&v)[64], float slope, uint4* tile, int lane,
+                                                 __nv_bfloat16* dst, long long pix0, int ld, long long total_pix) {
+    bias_act_pack<ACT>(v, nullptr, slope, tile, lane);
     __syncwarp();
-    store_tile_rows(tile, dst, row_off, row_ok, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + (lane >> 3), ch = lane & 7;
+        const uint4 val = tile[row * 8 + (ch ^ (row & 7))];
+        const long long pix = pix0 + row;
+        if (pix < total_pix) *reinterpret_cast<uint4*>(dst + pix * ld + ch * 8) = val;
+    }
     __syncwarp();
 }
 
-__device__ __forceinline__ void thin_store_dispatch(const uint32_t (&v)[64], const float* bias, int act, float slope,
-                                                    uint4* tile, int lane, __nv_bfloat16* dst, long long row_off,
-                                                    bool row_ok) {
+__device__ __forceinline__ void thin_store_dispatch(const uint32_t (&v)[64], int act, float slope, uint4* tile, int lane,
+                                                    __nv_bfloat16* dst, long long pix0, int ld, long long total_pix) {
     if (act == PAI_ACT_LEAKY)
-        thin_store_chunk<PAI_ACT_LEAKY>(v, bias, slope, tile, lane, dst, row_off, row_ok);
+        thin_store_chunk<PAI_ACT_LEAKY>(v, slope, tile, lane, dst, pix0, ld, total_pix);
     else if (act == PAI_ACT_RELU)
-        thin_store_chunk<PAI_ACT_RELU>(v, bias, slope, tile, lane, dst, row_off, row_ok);
+        thin_store_chunk<PAI_ACT_RELU>(v, slope, tile, lane, dst, pix0, ld, total_pix);
     else if (act == PAI_ACT_TANH)
-        thin_store_chunk<PAI_ACT_TANH>(v, bias, slope, tile, lane, dst, row_off, row_ok);
+        thin_store_chunk<PAI_ACT_TANH>(v, slope, tile, lane, dst, pix0, ld, total_pix);
     else
-        thin_store_chunk<PAI_ACT_NONE>(v, bias, slope, tile, lane, dst, row_off, row_ok);
+        thin_store_chunk<PAI_ACT_NONE>(v, slope, tile, lane, dst, pix0, ld, total_pix);
 }
 
 //
@@ -118,6 +125,26 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
     for (int i = threadIdx.x; i < p.cout * 8; i += kThinFpropThreads) {
         const int row = i >> 3, c = i & 7;
         *reinterpret_cast<uint4*>(sB + sw128_off(row, c)) = __ldg(reinterpret_cast<const uint4*>(p.w) + i);
+    }
+    // The bias rides on the GEMM: K columns 16*CIN, 16*CIN+1 of every A row hold 1.0 and the same columns of the weight
+    // tile hold the bias split into two bf16 terms (hi + lo: 16 mantissa bits, error < 1e-5 relative) -- one more MMA
+    // k-step per tile instead of 64 loads + adds per row in the epilogue.  The constant A chunks are written once.
+    if (p.bias != nullptr) {
+        __syncthreads();
+        for (int co = threadIdx.x; co < p.cout; co += kThinFpropThreads) {
+            const float b = __ldg(p.bias + co);
+            const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+            const __nv_bfloat16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+            const uint32_t w0 = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+            *reinterpret_cast<uint4*>(sB + sw128_off(co, 2 * CIN)) = make_uint4(w0, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(sB + sw128_off(co, 2 * CIN + 1)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        for (int i = threadIdx.x; i < 2 * 128; i += kThinFpropThreads) {
+            uint8_t* a_tile = sA + (i >> 7) * 16384;
+            const int row = i & 127;
+            *reinterpret_cast<uint4*>(a_tile + sw128_off(row, 2 * CIN)) = make_uint4(0x3F803F80u, 0u, 0u, 0u);   // (1.0, 1.0)
+            *reinterpret_cast<uint4*>(a_tile + sw128_off(row, 2 * CIN + 1)) = make_uint4(0u, 0u, 0u, 0u);
+        }
     }
     fence_proxy_async_smem();
     if (warp == 4 && lane == 0) {
@@ -166,9 +193,9 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
                     TROLE_ADD(w_ring);
                 }
                 uint32_t words[8 * CIN];
+                float v[CIN][16];
 #pragma unroll
                 for (int j = 0; j < CIN; ++j) {
-                    float v[16];
 #pragma unroll
                     for (int ky = 0; ky < 4; ++ky) {
                         const int iy = 2 * a - 1 + ky;
@@ -183,21 +210,20 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
                             if (r > 0) lft = rp[2 * r - 1];
                             if (2 * r + 2 < kThinRowW) rgt = rp[2 * r + 2];
                         }
-                        v[ky * 4 + 0] = lft, v[ky * 4 + 1] = mid.x, v[ky * 4 + 2] = mid.y, v[ky * 4 + 3] = rgt;
+                        v[j][ky * 4 + 0] = lft, v[j][ky * 4 + 1] = mid.x, v[j][ky * 4 + 2] = mid.y, v[j][ky * 4 + 3] = rgt;
                     }
-                    if (CIN == 1) {
+                }
+                if (CIN == 1) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-                            words[q] = *reinterpret_cast<uint32_t*>(&h);
-                        }
-                    } else {
-                        // word q = (plane 0, plane 1) of tap q: plane 0 fills the low halves first, plane 1 the high ones
+                    for (int q = 0; q < 8; ++q) {
+                        __nv_bfloat162 h = __floats2bfloat162_rn(v[0][2 * q], v[0][2 * q + 1]);
+                        words[q] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                } else {
 #pragma unroll
-                        for (int q = 0; q < 16; ++q) {
-                            const uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[q]));
-                            words[q] = j == 0 ? hb : (words[q] | (hb << 16));
-                        }
+                    for (int q = 0; q < 16; ++q) {           // word q = (plane 0, plane 1) of tap q
+                        __nv_bfloat162 h = __floats2bfloat162_rn(v[0][q], v[CIN - 1][q]);
+                        words[q] = *reinterpret_cast<uint32_t*>(&h);
                     }
                 }
                 mbar_arrive(&ring_empty[gc % kThinRing]);           // granule a-1 is not needed after this tile
@@ -333,6 +359,7 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
                 const uint32_t td = tmem_base + s * acc_cols;
                 umma_bf16_ss(td, da0, db0, idesc, 0);
                 if (CIN == 2) umma_bf16_acc(td, da0 + 2, db0 + 2, idesc);
+                if (p.bias != nullptr) umma_bf16_acc(td, da0 + 2 * CIN, db0 + 2 * CIN, idesc);     // the bias k-step
                 umma_commit(&ps.a_empty[s]);
                 umma_commit(&ps.acc_full[s]);
             }
@@ -353,8 +380,6 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
         (void)ep_wait, (void)ep_work;
         for (int i = g; i < t_count; i += 2, ++k) {
             const long long tile = t_begin + (long long)i * t_step;
-            const long long pix = tile * 128 + r;
-            const bool row_ok = pix < p.total_pix;
             {
                 TROLE_T0();
                 mbar_wait(&ps.acc_full[g], (uint32_t)(k & 1));
@@ -371,10 +396,10 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
                 for (int j = 0; j < 4; ++j)
                     tmem_ld_16(td + (uint32_t)(c0 + 16 * j), *reinterpret_cast<uint32_t(*)[16]>(&v[16 * j]));
                 tmem_ld_wait();
-                const float* bias_c = p.bias != nullptr ? p.bias + c0 : nullptr;
-                thin_store_dispatch(v, bias_c, p.act1, p.slope, tile_buf, lane, p.out1 + c0, pix * p.ld1, row_ok);
+                const long long pix0 = tile * 128 + q * 32;          // first pixel of this warp's 32 rows
+                thin_store_dispatch(v, p.act1, p.slope, tile_buf, lane, p.out1 + c0, pix0, p.ld1, p.total_pix);
                 if (p.out2 != nullptr)
-                    thin_store_dispatch(v, bias_c, p.act2, p.slope, tile_buf, lane, p.out2 + c0, pix * p.ld2, row_ok);
+                    thin_store_dispatch(v, p.act2, p.slope, tile_buf, lane, p.out2 + c0, pix0, p.ld2, p.total_pix);
             }
             tc_fence_before();
             mbar_arrive(&ps.acc_empty[g]);
