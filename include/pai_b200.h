@@ -31,6 +31,11 @@ extern "C" {
 
 const char* pai_last_error(void);
 int pai_version(void);
+/* The tensor-core kernels are persistent: one CTA (195 KB of shared memory) per SM.  A collective that must run
+ * CONCURRENTLY with them (the NCCL gradient all-reduce overlapped with the backward pass, pai_b200/dp.py; Lightning DDP's
+ * bucketed overlap for main.py:123-135) needs SMs of its own, or its CTAs and ours wait for each other for the whole
+ * duration of a kernel.  pai_reserve_sms(n) makes every persistent launch of this process use (#SMs - n) CTAs. */
+int pai_reserve_sms(int n);
 
 /* ---------------------------------------------------------------------------------------------
  * 4x4 convolutions as tcgen05 implicit GEMM.
@@ -51,6 +56,13 @@ int pai_version(void);
 int pai_conv4x4_fprop(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
                       int cout_pad, int stride, const float* bias, int act, float slope, void* y, int y_ld,
                       int y_f32, int n_tile, float* splitk_ws, void* stream);
+
+/* The same convolution with TWO bf16 outputs of the same accumulator, each with its own activation and pixel stride
+ * (cout %% 64 == 0, no split-K): eval-mode encoder blocks whose BatchNorm is folded into the weights write the next
+ * encoder's LeakyReLU input AND the decoder's ReLU concat slot (models/pix2pix.py:62,98,212) from one GEMM. */
+int pai_conv4x4_fprop_dual(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
+                           int cout_pad, int stride, const float* bias, int act, float slope, void* y, int y_ld, void* y2,
+                           int y2_ld, int act2, int n_tile, void* stream);
 
 /* pai_convT4x4s2_fprop: nn.ConvTranspose2d(cin, cout, kernel_size=4, stride=2, padding=1)
  *   (models/pix2pix.py:99-105,186-192), run as 4 sub-pixel phases:
@@ -222,6 +234,15 @@ int pai_thin_convT4x4s2_plane(const void* x, int n, int h, int w, int c, int x_l
                               int act, float* out, void* stream);
 int pai_col2im4x4s1(const float* p, int ldp, int n, int h, int w, float* out, void* stream);
 
+/* report.py's image outputs on the device (report.py:122-141,220-233):
+ *   pai_to_uint8   torchvision ConvertImageDtype(torch.uint8) (models/utils.py:12): (x * 255.999) truncated; values outside
+ *                  [0, 1] wrap modulo 256 like the float -> int32 -> uint8 conversion of the x86 host the reference runs on
+ *   pai_afmhot_u8  matplotlib's "afmhot" colormap (r, g, b = clip(2v, 2v - 0.5, 2v - 1)) with its 256-entry look-up
+ *                  (index = min(int(x * 256), 255), entry i evaluated at v = i / 255) followed by pai_to_uint8:
+ *                  img [n, h*w] in [0, 1] -> out [n, 3, h*w] uint8 */
+int pai_to_uint8(const float* x, long long count, unsigned char* out, void* stream);
+int pai_afmhot_u8(const float* img, int n, long long hw, unsigned char* out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Optimizer step: torch.optim.Adam(lr=2e-4, betas=(0.5,0.999), eps=1e-7) of
  * UnetWrapper.configure_optimizers / training_step (models/wrapper.py:97-115,136,160), fused with
@@ -245,6 +266,11 @@ int pai_adam_multi(int count, float* const* params, const float* const* grads, f
                    float* const* exp_avg_sqs, const int* numels, float beta1, float beta2, float step_size,
                    float inv_bias_correction2_sqrt, float eps, const float* dyn, void* stream);
 int pai_adam_prepare(int* step, float lr, float beta1, float beta2, float* dyn, void* stream);
+/* Exponential moving average of the weights (callbacks/ema.py:24-34, torch_ema's rule, decay 0.9999 main.py:131):
+ * shadow_k <- shadow_k - one_minus_decay * (shadow_k - param_k) for `count` fp32 tensors in one launch (host arrays of
+ * device pointers; 12 B per parameter instead of three elementwise passes per tensor). */
+int pai_ema_multi(int count, float* const* shadows, const float* const* params, const int* numels, float one_minus_decay,
+                  void* stream);
 /* Weight gradient from the wgrad kernels' accumulation layout dw[16][ab] (tap-major, ab = A*B) to the parameter layout
  * grad[ab][16] (= [A, B, 4, 4], models/pix2pix.py:63,99); zero_src != 0 also zeroes dw for the next accumulation. */
 int pai_wgrad_finish(float* dw_tap_major, long long ab, float* grad, int zero_src, void* stream);

@@ -31,7 +31,7 @@ def _worker(rank, world, port, q):
     mx = dp.allreduce_max(float(rank), torch.device("cpu"))
     # overlapped exchange used by the fused backward nodes: a large gradient is averaged while "backward" continues,
     # and allreduce_gradients() afterwards must not average it a second time
-    os.environ["PAI_DP_OVERLAP"] = "1"              # opt-in (see dp.allreduce_async)
+    os.environ["PAI_DP_OVERLAP"] = "1"              # opt-in (see dp.overlap_enabled)
     big = torch.nn.Parameter(torch.zeros(1 << 18))
     small = torch.nn.Parameter(torch.zeros(5))
     big.grad = torch.full((1 << 18,), float(rank + 1))
@@ -40,9 +40,9 @@ def _worker(rank, world, port, q):
     n2 = dp.allreduce_gradients([big, small])
     assert float(big.grad[0]) == 1.5 and float(big.grad[-1]) == 1.5, big.grad[:3]
     assert float(small.grad[0]) == 15.0 and n2 == 5
-    del os.environ["PAI_DP_OVERLAP"]
+    os.environ["PAI_DP_OVERLAP"] = "0"
     big.grad = torch.full((1 << 18,), float(rank + 1))
-    dp.allreduce_async(big.grad)                    # off by default: a no-op, the grouped all-reduce averages it
+    dp.allreduce_async(big.grad)                    # switched off: a no-op, the grouped all-reduce averages it
     n3 = dp.allreduce_gradients([big])
     assert float(big.grad[7]) == 1.5 and n3 == 1 << 18
     q.put((rank, [t.numpy() for t in ref], [g.numpy() for g in local], [p.grad.numpy() for p in net.parameters()], n, mx))

@@ -7,9 +7,9 @@ image and not vendored: restated here from its documented behaviour, *unpinned* 
     num_updates += 1;  d = min(decay, (1 + num_updates) / (10 + num_updates))
     shadow <- shadow - (1 - d) * (shadow - param)          for every parameter that requires grad
 
-``update()`` runs as two multi-tensor launches over all parameters (``torch._foreach_sub`` / ``_foreach_add_``) instead
-of one small kernel triple per tensor -- the adjacent elementwise pass over the 54 M generator parameters of SURVEY.md
-8(f)-3.  The hooks have the reference's names and order, so ``pl.Trainer(callbacks=[EMACallback(0.9999)])`` works when
+``update()`` is ONE launch of the library's multi-tensor kernel (``pai_ema_multi``, csrc/optim.cu: 12 bytes per parameter)
+over all CUDA fp32 parameters -- the adjacent elementwise pass over the 54 M generator parameters of SURVEY.md 8(f)-3;
+parameters on the host take ``torch._foreach`` ops (plumbing, like FusedAdam's CPU path).  The hooks have the reference's names and order, so ``pl.Trainer(callbacks=[EMACallback(0.9999)])`` works when
 Lightning is installed; without it the class is a plain object with the same methods.
 """
 from __future__ import annotations
@@ -45,6 +45,17 @@ class ExponentialMovingAverage:
             decay = min(decay, (1 + self.num_updates) / (10 + self.num_updates))
         one_minus_decay = 1.0 - decay
         live = [p.detach() for p in self._params]
+        if live and all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and s.is_contiguous()
+                        for p, s in zip(live, self.shadow_params)):
+            import ctypes
+            from pai_b200 import lib
+            n = len(live)
+            arr = ctypes.c_void_p * n
+            with lib.on_device(live[0]):
+                lib.call("pai_ema_multi", n, arr(*[s.data_ptr() for s in self.shadow_params]),
+                         arr(*[p.data_ptr() for p in live]), (ctypes.c_int * n)(*[p.numel() for p in live]),
+                         one_minus_decay, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), kernels=(n + 47) // 48)
+            return
         diff = torch._foreach_sub(self.shadow_params, live)             # shadow - param
         torch._foreach_add_(self.shadow_params, diff, alpha=-one_minus_decay)
 

@@ -230,26 +230,31 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long m, int c, int ld, c
     const int cv = c >> 3;
     const int vec = threadIdx.x % cv;
     const long long ppb = kEwThreads / cv;
-    Vec8 sc, sh, mu, is;
+    // Few per-channel constants stay live in the loop (register pressure decides how many 16-byte loads a thread keeps
+    // in flight): z = sc * x + sh only supplies the activation masks; the x-hat terms are folded into
+    //   reduce: sum dz * xhat = invstd * (sum dz * x - mean * sum dz)          (finished after the loop)
+    //   apply : dx = k0 * dz + kA + kB * x,  k0 = gamma * invstd, kA = -k0 * (mean_dz - mean * invstd * mean_dzxhat),
+    //                                         kB = -k0 * invstd * mean_dzxhat
+    Vec8 sc, sh;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sc.v[i] = 1.f, sh.v[i] = 0.f, mu.v[i] = 0.f, is.v[i] = 1.f;
+    for (int i = 0; i < 8; ++i) sc.v[i] = 1.f, sh.v[i] = 0.f;
     if (BN) {
         sc = loadf8(ss + vec * 8);
         sh = loadf8(ss + c + vec * 8);
-        mu = loadf8(ss + 2 * c + vec * 8);
-        is = loadf8(ss + 3 * c + vec * 8);
     }
-    Vec8 k0, k1, k2;  // MODE 1 with BN: dx = k0 * dz + k1 + k2 * xhat
+    Vec8 k0, kA, kB;
     Vec8 s0, s1;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s0.v[i] = s1.v[i] = 0.f, k0.v[i] = 1.f, k1.v[i] = 0.f, k2.v[i] = 0.f;
+    for (int i = 0; i < 8; ++i) s0.v[i] = s1.v[i] = 0.f, k0.v[i] = 1.f, kA.v[i] = 0.f, kB.v[i] = 0.f;
     if (MODE == 1 && BN) {
+        const Vec8 mu = loadf8(ss + 2 * c + vec * 8), is = loadf8(ss + 3 * c + vec * 8);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float g = gamma != nullptr ? gamma[vec * 8 + i] : 1.f;
+            const float mdz = sums[vec * 8 + i] / (float)m, mdzx = sums[c + vec * 8 + i] / (float)m;
             k0.v[i] = g * is.v[i];
-            k1.v[i] = -k0.v[i] * sums[vec * 8 + i] / (float)m;
-            k2.v[i] = -k0.v[i] * sums[c + vec * 8 + i] / (float)m;
+            kB.v[i] = -k0.v[i] * is.v[i] * mdzx;
+            kA.v[i] = -k0.v[i] * mdz - kB.v[i] * mu.v[i];
         }
     }
     const long long stride = (long long)gridDim.x * ppb;
@@ -265,11 +270,10 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long m, int c, int ld, c
             float dz = a.v[i] * act_grad_t<ACT1>(z, slope);
             if (ACT2 >= 0) dz = fmaf(b.v[i], act_grad_t<(ACT2 >= 0 ? ACT2 : 0)>(z, slope), dz);
             if (BN) {
-                const float xh = (v.v[i] - mu.v[i]) * is.v[i];
                 if (MODE == 1)
-                    o.v[i] = fmaf(k0.v[i], dz, fmaf(k2.v[i], xh, k1.v[i]));
+                    o.v[i] = fmaf(k0.v[i], dz, fmaf(kB.v[i], v.v[i], kA.v[i]));
                 else
-                    s1.v[i] = fmaf(dz, xh, s1.v[i]);
+                    s1.v[i] = fmaf(dz, v.v[i], s1.v[i]);
             } else {
                 o.v[i] = dz;
             }
@@ -277,19 +281,20 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long m, int c, int ld, c
         }
         if (MODE != 0) store8(dx + pix * lddx + vec * 8, o);
     };
-    // 2 pixels (4-6 independent 16-byte loads) in flight per thread
+    // U pixels (2-3 independent 16-byte loads each) in flight per thread
+    constexpr int U = 4;
     long long pix = (long long)blockIdx.x * ppb + threadIdx.x / cv;
-    for (; pix + stride < m; pix += 2 * stride) {
-        const long long p1 = pix + stride;
-        const uint4 v0 = load_raw(x + pix * ld + vec * 8), v1 = load_raw(x + p1 * ld + vec * 8);
-        const uint4 a0 = load_raw(g1 + pix * ldg1 + vec * 8), a1 = load_raw(g1 + p1 * ldg1 + vec * 8);
-        uint4 b0 = make_uint4(0, 0, 0, 0), b1 = make_uint4(0, 0, 0, 0);
-        if (ACT2 >= 0) {
-            b0 = load_raw(g2 + pix * ldg2 + vec * 8);
-            b1 = load_raw(g2 + p1 * ldg2 + vec * 8);
+    for (; pix + (U - 1) * stride < m; pix += U * stride) {
+        uint4 rv[U], ra[U], rb[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long pp = pix + u * stride;
+            rv[u] = load_raw(x + pp * ld + vec * 8);
+            ra[u] = load_raw(g1 + pp * ldg1 + vec * 8);
+            rb[u] = ACT2 >= 0 ? load_raw(g2 + pp * ldg2 + vec * 8) : make_uint4(0, 0, 0, 0);
         }
-        body(v0, a0, b0, pix);
-        body(v1, a1, b1, p1);
+#pragma unroll
+        for (int u = 0; u < U; ++u) body(rv[u], ra[u], rb[u], pix + u * stride);
     }
     for (; pix < m; pix += stride) {
         const uint4 v0 = load_raw(x + pix * ld + vec * 8), a0 = load_raw(g1 + pix * ldg1 + vec * 8);
@@ -297,7 +302,14 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long m, int c, int ld, c
         if (ACT2 >= 0) b0 = load_raw(g2 + pix * ldg2 + vec * 8);
         body(v0, a0, b0, pix);
     }
-    if (MODE != 1) block_reduce_2x8(s0, s1, cv, c, sums);
+    if (MODE != 1) {
+        if (BN) {       // sum dz * xhat from sum dz * x and sum dz
+            const Vec8 mu = loadf8(ss + 2 * c + vec * 8), is = loadf8(ss + 3 * c + vec * 8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s1.v[i] = is.v[i] * (s1.v[i] - mu.v[i] * s0.v[i]);
+        }
+        block_reduce_2x8(s0, s1, cv, c, sums);
+    }
 }
 
 template <int MODE>
@@ -512,4 +524,51 @@ int pai_colsum(const void* x, long long m, int c, int ld, float* sums2c, void* s
     return 0;
 }
 
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// report.py image outputs (report.py:122-141,220-233)
+namespace pai {
+__device__ __forceinline__ unsigned char to_u8(float x) {
+    // torchvision F_t.convert_image_dtype float -> uint8: x * (255 + 1 - 1e-3), truncated; out-of-range values wrap like
+    // the host's float -> int32 -> uint8 cast
+    return (unsigned char)((int)(x * 255.999f) & 0xff);
+}
+__global__ void __launch_bounds__(256) to_uint8_kernel(const float* __restrict__ x, long long count, unsigned char* __restrict__ out) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < count; i += (long long)gridDim.x * 256) out[i] = to_u8(x[i]);
+}
+__global__ void __launch_bounds__(256) afmhot_u8_kernel(const float* __restrict__ img, int n, long long hw, unsigned char* __restrict__ out) {
+    const long long total = (long long)n * hw;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const long long b = i / hw, pix = i - b * hw;
+        int idx = (int)(img[i] * 256.f);
+        idx = idx < 0 ? 0 : (idx > 255 ? 255 : idx);
+        const float v = (float)idx / 255.f;                      // look-up table entry idx of 256
+        unsigned char* o = out + b * 3 * hw + pix;
+        o[0] = to_u8(fminf(fmaxf(2.f * v, 0.f), 1.f));
+        o[hw] = to_u8(fminf(fmaxf(2.f * v - 0.5f, 0.f), 1.f));
+        o[2 * hw] = to_u8(fminf(fmaxf(2.f * v - 1.f, 0.f), 1.f));
+    }
+}
+}  // namespace pai
+
+extern "C" {
+int pai_to_uint8(const float* x, long long count, unsigned char* out, void* stream) {
+    PAI_REQUIRE(x && out && count >= 0, "pai_to_uint8: bad arguments");
+    if (count == 0) return 0;
+    long long blocks = (count + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pai::to_uint8_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, count, out);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int pai_afmhot_u8(const float* img, int n, long long hw, unsigned char* out, void* stream) {
+    PAI_REQUIRE(img && out && n >= 0 && hw > 0, "pai_afmhot_u8: bad arguments");
+    if (n == 0) return 0;
+    long long blocks = ((long long)n * hw + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pai::afmhot_u8_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(img, n, hw, out);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 }  // extern "C"

@@ -685,7 +685,7 @@ int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFp
     if (p.kmma <= 0 || p.kmma > 4) p.kmma = 4;
     const size_t smem = stage_bytes * p.stages + 1024;
     static DeviceOnce once;
-    const int dev = current_device(), num_sms = sm_count(dev);
+    const int dev = current_device(), num_sms = persistent_ctas(dev);
     if (num_sms < 0) return -1;
     if (once.need(dev)) {
         PAI_CUDA_OK(cudaFuncSetAttribute(igemm_fprop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 194 * 1024));
@@ -766,7 +766,7 @@ int launch_igemm_wgrad(const CUtensorMap& tm_u, const CUtensorMap& tm_s, IgemmWg
     p.stages = pick_stages(stage_bytes, 196 * 1024);
     const size_t smem = stage_bytes * p.stages + 1024;
     static DeviceOnce once;
-    const int dev = current_device(), num_sms = sm_count(dev);
+    const int dev = current_device(), num_sms = persistent_ctas(dev);
     if (num_sms < 0) return -1;
     if (once.need(dev)) {
         PAI_CUDA_OK(cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

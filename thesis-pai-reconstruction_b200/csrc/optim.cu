@@ -176,11 +176,53 @@ adam_multi_kernel(const __grid_constant__ AdamTable t, AdamHyper hy0, const floa
     }
 }
 
+// ---- exponential moving average of the weights (callbacks/ema.py:24-34 -> torch_ema's update rule) ------------------
+// shadow <- shadow - (1 - d) * (shadow - param) for `count` tensors in one launch; the table reuses AdamTable
+// (p = shadow, g = live parameter).
+__global__ void __launch_bounds__(256)
+ema_multi_kernel(const __grid_constant__ AdamTable t, float one_minus_decay) {
+    for (int k = blockIdx.y; k < t.count; k += gridDim.y) {
+        float* sh = t.p[k];
+        const float* live = t.g[k];
+        const int n = t.n[k];
+        const int n4 = ((reinterpret_cast<uintptr_t>(sh) | reinterpret_cast<uintptr_t>(live)) & 15) == 0 ? n >> 2 : 0;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+            float4 s = reinterpret_cast<float4*>(sh)[i];
+            const float4 p = __ldg(reinterpret_cast<const float4*>(live) + i);
+            s.x -= one_minus_decay * (s.x - p.x), s.y -= one_minus_decay * (s.y - p.y);
+            s.z -= one_minus_decay * (s.z - p.z), s.w -= one_minus_decay * (s.w - p.w);
+            reinterpret_cast<float4*>(sh)[i] = s;
+        }
+        for (int i = 4 * n4 + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            sh[i] -= one_minus_decay * (sh[i] - live[i]);
+    }
+}
+
 }  // namespace pai
 
 using namespace pai;
 
 extern "C" {
+
+int pai_ema_multi(int count, float* const* shadows, const float* const* params, const int* numels, float one_minus_decay,
+                  void* stream) {
+    PAI_REQUIRE(count >= 0 && (count == 0 || (shadows && params && numels)), "pai_ema_multi: bad arguments");
+    for (int base = 0; base < count; base += kMaxTensors) {
+        AdamTable t;
+        t.count = count - base < kMaxTensors ? count - base : kMaxTensors;
+        int big = 0;
+        for (int i = 0; i < t.count; ++i) {
+            t.p[i] = shadows[base + i], t.g[i] = params[base + i], t.m[i] = nullptr, t.v[i] = nullptr, t.n[i] = numels[base + i];
+            if (t.n[i] > big) big = t.n[i];
+        }
+        int bx = (big / 4 + 255) / 256;
+        if (bx > 148 * 4) bx = 148 * 4;
+        if (bx < 1) bx = 1;
+        ema_multi_kernel<<<dim3(bx, t.count), 256, 0, (cudaStream_t)stream>>>(t, one_minus_decay);
+        PAI_CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
 
 int pai_adam_pack_conv4x4(float* w, const float* grad, float* exp_avg, float* exp_avg_sq, int a, int b, float beta1,
                           float beta2, float step_size, float inv_bias_correction2_sqrt, float eps, void* pack1,

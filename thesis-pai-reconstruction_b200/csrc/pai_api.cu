@@ -50,6 +50,16 @@ int sm_count(int dev) {
     return v;
 }
 
+static int g_reserved_sms = 0;
+
+int persistent_ctas(int dev) {
+    const int sms = sm_count(dev);
+    if (sms < 0) return sms;
+    int n = sms - __atomic_load_n(&g_reserved_sms, __ATOMIC_RELAXED);
+    if (n < 2) n = 2;
+    return n & ~1;          // CTA pairs
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (fn == nullptr) {
@@ -164,9 +174,16 @@ extern "C" {
 const char* pai_last_error(void) { return g_err; }
 int pai_version(void) { return 100; }
 
+int pai_reserve_sms(int n) {
+    PAI_REQUIRE(n >= 0 && n <= 64, "pai_reserve_sms: reservation must be in 0..64 (got %d)", n);
+    __atomic_store_n(&g_reserved_sms, n, __ATOMIC_RELAXED);
+    return 0;
+}
+
 static int conv4x4_fprop_impl(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
                               int cout_pad, int stride, const float* bias, int act, float slope, void* y, int y_ld,
-                              int y_f32, int n_tile, float* splitk_ws, float* bn_part, int bn_rows, void* stream) {
+                              int y_f32, int n_tile, float* splitk_ws, float* bn_part, int bn_rows, void* stream,
+                              void* y2 = nullptr, int y2_ld = 0, int act2 = PAI_ACT_NONE) {
     PAI_REQUIRE(x && w_packed && y, "pai_conv4x4_fprop: null pointer");
     PAI_REQUIRE(stride == 1 || stride == 2, "pai_conv4x4_fprop: stride must be 1 or 2 (got %d)", stride);
     PAI_REQUIRE(cin > 0 && cin % 64 == 0, "pai_conv4x4_fprop: cin must be a multiple of 64 (got %d)", cin);
@@ -229,7 +246,21 @@ static int conv4x4_fprop_impl(const void* x, int n, int h, int w, int cin, int x
     }
     p.out_sn = (long long)ho * wo * y_ld, p.out_sh = (long long)wo * y_ld, p.out_sw = y_ld;
     p.bias = bias, p.act = act, p.slope = slope, p.out_f32 = y_f32, p.out = y;
+    if (y2 != nullptr) {
+        PAI_REQUIRE(!y_f32 && y2_ld % 8 == 0 && aligned16(y2) && aligned16(y) && y_ld % 8 == 0 && cout % 64 == 0,
+                    "pai_conv4x4_fprop_dual: two bf16 outputs need cout %% 64 == 0 and 16 B aligned rows");
+        p.out2 = y2, p.act2 = act2;
+        p.out2_sn = (long long)ho * wo * y2_ld, p.out2_sh = (long long)wo * y2_ld, p.out2_sw = y2_ld;
+    }
     return launch_igemm_fprop(tm_a, tm_b, p, m_tiles, cout_pad / n_tile, 1, (cudaStream_t)stream);
+}
+
+int pai_conv4x4_fprop_dual(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,
+                           int cout_pad, int stride, const float* bias, int act, float slope, void* y, int y_ld, void* y2,
+                           int y2_ld, int act2, int n_tile, void* stream) {
+    PAI_REQUIRE(y2 != nullptr, "pai_conv4x4_fprop_dual: null second output");
+    return conv4x4_fprop_impl(x, n, h, w, cin, x_ld, w_packed, cout, cout_pad, stride, bias, act, slope, y, y_ld, 0, n_tile,
+                              nullptr, nullptr, 0, stream, y2, y2_ld, act2);
 }
 
 int pai_conv4x4_fprop(const void* x, int n, int h, int w, int cin, int x_ld, const void* w_packed, int cout,

@@ -36,6 +36,8 @@ struct DeviceOnce {
 // Current device ordinal and its SM count (cached per device); negative on a CUDA error (pai_last_error is set).
 int current_device();
 int sm_count(int dev);
+// SMs the persistent (one CTA per SM) kernels may occupy: sm_count minus the reservation of pai_reserve_sms()
+int persistent_ctas(int dev);
 
 // Encodes a bf16 tiled tensor map (rank <= 5, SWIZZLE_128B, zero OOB fill) through the driver
 // entry point fetched at run time, so the library loads on a box without libcuda.

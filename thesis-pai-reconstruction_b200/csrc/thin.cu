@@ -839,7 +839,7 @@ int pai_thin_conv4x4s2_fprop(const float* plane0, const float* plane1, int cin, 
     PAI_REQUIRE(p.total_pix < (1LL << 31) - 128, "pai_thin_conv4x4s2_fprop: tensor too large");
     p.tiles = (int)((p.total_pix + 127) / 128);
     p.fd_ow = make_fastdiv(p.ow), p.fd_oh = make_fastdiv(p.oh);
-    const int dev = current_device(), sms = sm_count(dev);
+    const int dev = current_device(), sms = persistent_ctas(dev);
     if (sms < 0) return -1;
     // 256-pixel wide images take the row-streaming form (bulk-copied input rows in a shared-memory ring)
     const bool stream = iw == kThinRowW && (reinterpret_cast<uintptr_t>(plane0) & 15) == 0 &&
@@ -889,7 +889,7 @@ int pai_thin_conv4x4s2_wgrad(const void* u, int u_ld, int c, const float* plane0
     uint32_t box[2] = {64, 64};
     int rc = encode_tmap_bf16(&tm_u, u, 2, dims, str, box);
     if (rc) return rc;
-    const int dev = current_device(), sms = sm_count(dev);
+    const int dev = current_device(), sms = persistent_ctas(dev);
     if (sms < 0) return -1;
     const size_t smem = (size_t)kThinWgradStages * (2 * 8192 + 4096) + 1024;
     static DeviceOnce once;
@@ -930,7 +930,7 @@ int pai_thin_convT4x4s2_plane(const void* x, int n, int h, int w, int c, int x_l
     if (rc) return rc;
     ThinPlaneParams p;
     p.n = n, p.h = h, p.c = c, p.kc = c / 64, p.bias = bias, p.act = act, p.out = out;
-    const int dev = current_device(), sms = sm_count(dev);
+    const int dev = current_device(), sms = persistent_ctas(dev);
     if (sms < 0) return -1;
     const size_t smem = 4 * 2048 + (size_t)kThinPlaneStages * 16384 + 1024;
     static DeviceOnce once;

@@ -28,9 +28,29 @@ def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         if backend == "nccl":
             torch.cuda.set_device(local)
+            if overlap_enabled():
+                # The all-reduce of layer k's weight gradient runs while the backward of layers k-1, k-2, ... continues.
+                # Our tensor-core kernels are persistent with one 195 KB-shared-memory CTA per SM: a NCCL CTA cannot share
+                # an SM with one, so without SMs of its own either side waits for the other for a whole kernel.  NCCL is
+                # held to RESERVED_SMS CTAs and the library launches (#SMs - RESERVED_SMS) persistent CTAs.
+                # (the reservation itself is switched on by the first all-reduce of a backward pass and off again by
+                # finish_async(): forward passes keep every SM)
+                os.environ.setdefault("NCCL_MAX_CTAS", str(RESERVED_SMS))
+                os.environ.setdefault("NCCL_MIN_CTAS", str(min(4, RESERVED_SMS)))
         dist.init_process_group(backend=backend, rank=rank, world_size=world)
     _enabled = world > 1
     return rank, local, world
+
+
+RESERVED_SMS = int(os.environ.get("PAI_DP_RESERVED_SMS", "8"))
+
+
+def overlap_enabled() -> bool:
+    """PAI_DP_OVERLAP=1: gradient all-reduces start inside the backward pass, on SMs reserved for NCCL.  Off by default:
+    measured on 2 B200s (round 2, batch 64) the overlapped step takes 9.07 ms against 8.97 ms for the single grouped
+    all-reduce after ``manual_backward`` (1 GPU: 8.35 ms) -- 20 separate collectives on 8 CTAs plus 5 % fewer SMs for the
+    backward GEMMs cost more than the 0.6 ms they hide."""
+    return os.environ.get("PAI_DP_OVERLAP", "0") == "1"
 
 
 def world_size() -> int:
@@ -52,15 +72,27 @@ def allreduce_async(t: torch.Tensor) -> None:
     in-place average over all ranks on NCCL's stream, so the exchange of layer k overlaps the dgrad / wgrad GEMMs of
     layers k-1, k-2, ... (the bucketed overlap DDP would give main.py:123-135).  ``finish_async`` joins them.
 
-    OFF unless PAI_DP_OVERLAP=1: measured on 2 B200s the overlap buys nothing (11.78 ms/step either way) -- the
-    implicit-GEMM kernels are persistent with one statically scheduled CTA per SM, so every SM an NCCL CTA occupies
-    delays its igemm CTA by the collective's duration.  It needs a dynamic (CLC) tile scheduler to pay off."""
-    if not active() or t.numel() < _BIG or not t.is_contiguous() or os.environ.get("PAI_DP_OVERLAP", "0") != "1":
+    Opt-in (PAI_DP_OVERLAP=1, see ``overlap_enabled``).  The persistent kernels leave RESERVED_SMS SMs to NCCL between the
+    first of these calls and ``finish_async`` (``pai_reserve_sms``), so the collectives and the GEMMs run side by side."""
+    if not active() or t.numel() < _BIG or not t.is_contiguous() or not overlap_enabled():
         return
     nccl = dist.get_backend() == "nccl"
+    if nccl and not _pending:
+        _reserve(RESERVED_SMS)         # from here to finish_async() the persistent kernels leave SMs to NCCL
     work = dist.all_reduce(t, op=dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM, async_op=True)
     _pending.append((work, t))
     _done.add(t.data_ptr())
+
+
+_reserved = 0
+
+
+def _reserve(n: int) -> None:
+    global _reserved
+    if n != _reserved:
+        from . import lib
+        lib.call("pai_reserve_sms", n, kernels=0)
+        _reserved = n
 
 
 def finish_async() -> None:
@@ -74,6 +106,7 @@ def finish_async() -> None:
         if not nccl:
             t.div_(world)
     _pending.clear()
+    _reserve(0)
 
 
 def allreduce_gradients(params) -> int:

@@ -153,6 +153,33 @@ def _thin_in_dgrad_pack(w, j):  # Conv2d weight [C, cin, 4, 4] -> bf16 [16, C]: 
     return _packs.get(f"thin_in_d{j}", w, lambda t: t[:, j].reshape(t.shape[0], 16).t().contiguous().bfloat16())
 
 
+FOLD_EVAL_BN = os.environ.get("PAI_NO_BN_FOLD") is None      # eval mode: BatchNorm folded into the GEMM operands
+
+
+def _folded(tag: str, conv, bn: "BNState", transposed: bool):
+    """-> (bf16 GEMM pack, fp32 bias) of an eval-mode ``conv -> BatchNorm`` pair folded into one affine convolution
+    (report.py:26-43 freezes the model, so BatchNorm is ``y * s + t`` with s = gamma / sqrt(running_var + eps),
+    t = beta - running_mean * s): W' = W * s[co], b' = b * s + t.  Cached on the conv weight (FusedAdam drops
+    ``_pai_aux`` after every update); the stamp also covers the BatchNorm tensors and the running statistics, which this
+    library updates through raw pointers (``_pai_stat_version``)."""
+    w = conv.weight
+    store = w.__dict__.setdefault("_pai_aux", {})
+    m = bn.mod
+    stamp = (w._version, w.data_ptr(), conv.bias._version, m.weight._version, m.bias._version, m.running_mean._version,
+             m.running_var._version, m.running_mean.data_ptr(), m.__dict__.get("_pai_stat_version", 0))
+    ent = store.get(tag)
+    if ent is None or ent[0] != stamp:
+        with torch.no_grad():
+            sc = m.weight.detach().float() * torch.rsqrt(m.running_var.float() + BN_EPS)
+            sh = m.bias.detach().float() - m.running_mean.float() * sc
+            wf = w.detach().float() * (sc.view(1, -1, 1, 1) if transposed else sc.view(-1, 1, 1, 1))
+            bf = (conv.bias.detach().float() * sc + sh).contiguous()
+            pack = ops.pack_convT_weight(wf) if transposed else ops.pack_conv_weight(wf)
+        ent = (stamp, (pack, bf))
+        store[tag] = ent
+    return ent[1]
+
+
 def _bf16(*shape, device):
     return torch.empty(*shape, dtype=torch.bfloat16, device=device)
 
@@ -183,6 +210,7 @@ def _batchnorm(raw, bn: BNState, training: bool, counters=None, partials=None):
     ss = ops.bn_finalize(sums, m, c, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
                          training=training, eps=BN_EPS, momentum=BN_MOMENTUM, nparts=nparts)
     if training:
+        bn.mod.__dict__["_pai_stat_version"] = bn.mod.__dict__.get("_pai_stat_version", 0) + 1   # running stats moved
         if counters is None:
             bn.num_batches_tracked.add_(1)
         else:
@@ -390,6 +418,14 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
         conv, bn = spec.enc_convs[i], spec.enc_bns[i]
         if i < L - 1:
             part = None
+            if (bn is not None and not training and not save and FOLD_EVAL_BN and ops.bn_fusable(n * hs[i] * ws[i], ch[i])):
+                # eval mode (report.py): BatchNorm folded into the weights, both consumers written by the GEMM epilogue --
+                # no raw tensor, no BatchNorm kernels
+                wp, bf = _folded("fold_f", conv, bn, transposed=False)
+                a_in[i + 1] = _bf16(n, hs[i], ws[i], ch[i], device=dev)
+                ops.conv4x4_fprop_dual(a_in[i], wp, ch[i], bf, a_in[i + 1], ACT_LEAKY, cat[L - 1 - i][..., ch[i]:], ACT_RELU,
+                                       slope=SLOPE)
+                continue
             if bn is not None and training and FUSE_BN_STATS and ops.bn_fusable(n * hs[i] * ws[i], ch[i]):
                 # BatchNorm statistics straight from the GEMM epilogue: no separate pass over the raw output
                 raw, part = ops.conv4x4_fprop_bnstats(a_in[i], _fprop_pack(conv.weight), ch[i], bias=conv.bias.detach())
@@ -415,6 +451,11 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
         co = spec.dec_out[j]
         part = None
         hj, wj = d_in.shape[1], d_in.shape[2]
+        if not training and not save and FOLD_EVAL_BN and ops.bn_fusable(4 * n * hj * wj, co):
+            wp, bf = _folded("fold_f", conv, bn, transposed=True)
+            ops.convT4x4s2_fprop(d_in, wp, co, bias=bf, act=ACT_RELU if j + 1 < L - 1 else ACT_NONE, out=cat[j + 1][..., :co])
+            d_in = cat[j + 1]
+            continue
         if training and FUSE_BN_STATS and ops.bn_fusable(4 * n * hj * wj, co):
             raw, part = ops.convT4x4s2_fprop_bnstats(d_in, _fpropT_pack(conv.weight), co, bias=conv.bias.detach())
         else:

@@ -17,6 +17,7 @@ c_int, c_float, c_void_p, c_ll = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, 
 # name -> argtypes, exactly the declarations of include/pai_b200.h
 SIGNATURES = {
     "pai_version": [],
+    "pai_reserve_sms": [c_int],
     "pai_conv4x4_fprop": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                           c_int, c_float, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p],
     "pai_convT4x4s2_fprop": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int,
@@ -104,7 +105,12 @@ SIGNATURES = {
                                  c_int, c_void_p, c_int, c_int, c_float, c_void_p],
     "pai_thin_conv4x4s2_wgrad": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "pai_thin_convT4x4s2_plane": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    "pai_conv4x4_fprop_dual": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int,
+                               c_float, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
+    "pai_to_uint8": [c_void_p, c_ll, c_void_p, c_void_p],
+    "pai_afmhot_u8": [c_void_p, c_int, c_ll, c_void_p, c_void_p],
     "pai_col2im4x4s1": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "pai_ema_multi": [c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p],
     "pai_adam_multi": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float,
                        c_float, c_void_p, c_void_p],
 }

@@ -127,6 +127,34 @@ def conv4x4_fprop(x, w_packed, cout, stride=2, bias=None, act=ACT_NONE, slope=0.
     return out
 
 
+def conv4x4_fprop_dual(x, w_packed, cout, bias, out1, act1, out2, act2, slope=0.2):
+    """Stride-2 4x4 convolution with two bf16 outputs of the same accumulator (eval-mode encoder with folded BatchNorm:
+    LeakyReLU input of the next encoder + ReLU concat slot of the decoder)."""
+    n, h, w, cin, ld = _nhwc(x)
+    cp = w_packed.shape[0]
+    assert tuple(out1.shape) == tuple(out2.shape) == (n, h // 2, w // 2, cout)
+    _igemm_call("pai_conv4x4_fprop_dual", 2.0 * n * (h // 2) * (w // 2) * cout * 16 * cin, _ptr(x), n, h, w, cin, ld,
+                _ptr(w_packed), cout, cp, 2, _ptr(bias), act1, float(slope), _ptr(out1), _nhwc(out1)[4], _ptr(out2),
+                _nhwc(out2)[4], act2, 0, _stream())
+
+
+def to_uint8(x):
+    """``models.utils.to_int`` (torchvision ConvertImageDtype(torch.uint8), models/utils.py:12) on the device."""
+    x = x.contiguous().float()
+    out = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    lib.call("pai_to_uint8", _ptr(x), x.numel(), _ptr(out), _stream())
+    return out
+
+
+def afmhot_uint8(img):
+    """``report.output_hot_image`` (report.py:220-233) up to the PNG encoder: ``[n, 1, h, w]`` in [0, 1] -> uint8 ``[n, 3, h, w]``."""
+    img = img.contiguous().float()
+    n, _, h, w = img.shape
+    out = torch.empty(n, 3, h, w, dtype=torch.uint8, device=img.device)
+    lib.call("pai_afmhot_u8", _ptr(img), n, h * w, _ptr(out), _stream())
+    return out
+
+
 BN_PART_ROWS = 160          # >= number of SMs (one partial-sum row per persistent CTA)
 
 

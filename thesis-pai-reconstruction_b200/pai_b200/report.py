@@ -16,15 +16,26 @@ from typing import Iterable, Tuple
 
 import torch
 
-from . import metrics
+from . import metrics, ops
 
 
 def _denormalize(x: torch.Tensor) -> torch.Tensor:          # models/utils.py:11
     return torch.clamp(x * 0.5 + 0.5, 0, 1)
 
 
-def _to_int(x: torch.Tensor) -> torch.Tensor:               # models/utils.py:12 (ConvertImageDtype(torch.uint8))
-    return x.mul(255.0 + 1.0 - 1e-3).to(torch.uint8)
+def _to_int(x: torch.Tensor) -> torch.Tensor:
+    """models/utils.py:12 (torchvision ConvertImageDtype(torch.uint8): ``x * 255.999`` truncated) on the device.  The
+    reference converts the RAW SSIM map (report.py:134-135), whose values may be negative: like the host conversion
+    it runs, out-of-range values wrap modulo 256 instead of being clamped."""
+    if x.is_cuda:
+        return ops.to_uint8(x)
+    return x.float().mul(255.0 + 1.0 - 1e-3).to(torch.int32).to(torch.uint8)
+
+
+def hot_images(preds: torch.Tensor) -> torch.Tensor:
+    """``output_hot_image`` (report.py:220-233) without the PNG encoder: matplotlib's "afmhot" colormap of every
+    denormalised prediction ``[n, 1, h, w]`` -> uint8 ``[n, 3, h, w]``, one kernel on the device."""
+    return ops.afmhot_uint8(preds)
 
 
 def depth_csv(depth_ssim: torch.Tensor) -> str:
@@ -61,7 +72,8 @@ def evaluate(model, batches: Iterable[Tuple[torch.Tensor, torch.Tensor]], want_m
         "ssim_stat": res["ssim_mean"], "psnr_stat": res["psnr_mean"], "rmse_stat": res["rmse"],
         "depth_ssim": res["depth_ssim"],
         "ssim_maps": res["ssim_maps"],
-        "ssim_maps_uint8": _to_int(res["ssim_maps"].clamp(0, 1)) if res["ssim_maps"] is not None else None,
+        "ssim_maps_uint8": _to_int(res["ssim_maps"]) if res["ssim_maps"] is not None else None,
+        "hot_images_uint8": hot_images(preds) if want_maps else None,
         "parameter_count": sum(p.numel() for p in model.parameters()) if isinstance(model, torch.nn.Module) else 0,
     }
     return out
