@@ -382,6 +382,15 @@ int pai_check_batchnorm_bwd_f32(const float* x, const float* g, int n, int c, in
                                 float* dx, float* dgamma, float* dbeta, void* stream);
 int pai_check_act_bwd_f32(const float* x, const float* g, long long count, int act, float slope, float* dx, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * dataset.py's per-image transform (dataset.py:51-61,126-134) for a batch of decoded grayscale uint8 images [n,ih,iw]:
+ * transforms.Resize((oh, ow), antialias=True) (ATen _upsample_bilinear2d_aa; round_u8 != 0 rounds back to uint8 levels
+ * as torchvision does for uint8 tensors) -> ConvertImageDtype(float32) -> Normalize(0.5, 0.5) (normalize != 0; applied
+ * to the ONE channel -- the reference passes 3-channel statistics and fails on GRAY images).
+ * out: fp32 [n,oh,ow].  Decoding PNG/JPEG files stays on the host. */
+int pai_resize_aa_normalize_u8(const unsigned char* img, int n, int ih, int iw, int oh, int ow, int normalize,
+                               int round_u8, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

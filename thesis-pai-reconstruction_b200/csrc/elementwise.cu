@@ -572,3 +572,67 @@ int pai_afmhot_u8(const float* img, int n, long long hw, unsigned char* out, voi
     return 0;
 }
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// dataset.py's per-image transform on the device (dataset.py:51-61,126-134): Resize((oh, ow), antialias=True) of a
+// uint8 grayscale image -> round back to uint8 levels -> ConvertImageDtype(float32) (/255) -> Normalize(0.5, 0.5).
+// The resampling is ATen's _upsample_bilinear2d_aa: triangle filter of half-width max(scale, 1) around the source
+// centre (o + 0.5) * scale, taps clipped to the image and renormalised.
+namespace pai {
+struct AaTaps {
+    int lo, n;
+    float center, invscale;
+};
+__device__ __forceinline__ AaTaps aa_taps(int o, int in, int out) {
+    const float scale = (float)in / (float)out;
+    const float support = scale >= 1.f ? scale : 1.f;
+    AaTaps t;
+    t.center = scale * ((float)o + 0.5f);
+    t.invscale = scale >= 1.f ? 1.f / scale : 1.f;
+    t.lo = max((int)(t.center - support + 0.5f), 0);
+    t.n = min((int)(t.center + support + 0.5f), in) - t.lo;
+    return t;
+}
+__device__ __forceinline__ float aa_weight(const AaTaps& t, int j) {
+    const float x = fabsf(((float)(j + t.lo) - t.center + 0.5f) * t.invscale);
+    return x < 1.f ? 1.f - x : 0.f;
+}
+__global__ void __launch_bounds__(256)
+resize_aa_norm_kernel(const unsigned char* __restrict__ img, int n, int ih, int iw, int oh, int ow, int normalize,
+                      int round_u8, float* __restrict__ out) {
+    const long long total = (long long)n * oh * ow;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int ox = (int)(i % ow), oy = (int)((i / ow) % oh);
+        const long long b = i / ((long long)ow * oh);
+        const AaTaps ty = aa_taps(oy, ih, oh), tx = aa_taps(ox, iw, ow);
+        float wy_sum = 0.f, wx_sum = 0.f;
+        for (int j = 0; j < ty.n; ++j) wy_sum += aa_weight(ty, j);
+        for (int j = 0; j < tx.n; ++j) wx_sum += aa_weight(tx, j);
+        const unsigned char* src = img + b * ih * iw;
+        // horizontal pass first, then vertical (the order ATen's separable implementation uses); each intermediate row
+        // value is kept in fp32
+        float acc = 0.f;
+        for (int jy = 0; jy < ty.n; ++jy) {
+            const unsigned char* row = src + (long long)(ty.lo + jy) * iw + tx.lo;
+            float r = 0.f;
+            for (int jx = 0; jx < tx.n; ++jx) r = fmaf(aa_weight(tx, jx) / wx_sum, (float)row[jx], r);
+            acc = fmaf(aa_weight(ty, jy) / wy_sum, r, acc);
+        }
+        if (round_u8) acc = fminf(fmaxf(rintf(acc), 0.f), 255.f);      // torchvision rounds back to uint8 after resizing
+        float v = acc / 255.f;                                       // ConvertImageDtype(torch.float32)
+        if (normalize) v = (v - 0.5f) / 0.5f;                        // Normalize(0.5, 0.5) for the single channel
+        out[i] = v;
+    }
+}
+}  // namespace pai
+
+extern "C" int pai_resize_aa_normalize_u8(const unsigned char* img, int n, int ih, int iw, int oh, int ow, int normalize,
+                                          int round_u8, float* out, void* stream) {
+    PAI_REQUIRE(img && out && n >= 0 && ih > 0 && iw > 0 && oh > 0 && ow > 0, "pai_resize_aa_normalize_u8: bad arguments");
+    if (n == 0) return 0;
+    long long blocks = ((long long)n * oh * ow + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    pai::resize_aa_norm_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(img, n, ih, iw, oh, ow, normalize, round_u8, out);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}

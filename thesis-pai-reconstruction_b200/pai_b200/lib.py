@@ -110,6 +110,7 @@ SIGNATURES = {
     "pai_to_uint8": [c_void_p, c_ll, c_void_p, c_void_p],
     "pai_afmhot_u8": [c_void_p, c_int, c_ll, c_void_p, c_void_p],
     "pai_col2im4x4s1": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "pai_resize_aa_normalize_u8": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "pai_ema_multi": [c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p],
     "pai_adam_multi": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float,
                        c_float, c_void_p, c_void_p],
