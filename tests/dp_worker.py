@@ -82,11 +82,25 @@ def main():
         both = [torch.empty_like(g) for _ in range(world)]
         dist.all_gather(both, g)
         expect[k] = (both[0] + both[1]) / 2
+    bf16_wire = dp.grad_exchange_dtype() == torch.bfloat16
     dp.allreduce_gradients(p for p in m2.unet.parameters())
     worst = 0.0
     for k, p in m2.unet.named_parameters():
-        assert torch.allclose(p.grad, expect[k], rtol=1e-5, atol=1e-8), f"all-reduced gradient {k} != mean of the local gradients"
+        if bf16_wire and p.grad.numel() >= dp._BIG:
+            # the large gradients travel as bf16: rounded once on the way in and once on the way out
+            err = (p.grad - expect[k]).abs().max().item()
+            assert err <= 2.0 ** -7 * expect[k].abs().max().item() + 1e-12, (k, err)
+        else:
+            assert torch.allclose(p.grad, expect[k], rtol=1e-5, atol=1e-8), f"all-reduced gradient {k} != mean of the local gradients"
         assert same_on_all_ranks(p.grad), f"averaged gradient {k} differs between ranks"
+    # ... and bit-exact fp32 averaging on request
+    os.environ["PAI_DP_GRAD_DTYPE"] = "fp32"
+    for k, p in m2.unet.named_parameters():
+        p.grad.copy_(local_g[k])
+    dp.allreduce_gradients(p for p in m2.unet.parameters())
+    for k, p in m2.unet.named_parameters():
+        assert torch.allclose(p.grad, expect[k], rtol=1e-5, atol=1e-8), f"fp32 all-reduced gradient {k} != mean of the local gradients"
+    del os.environ["PAI_DP_GRAD_DTYPE"]
     # (b) the path training uses: manual_backward = backward with the per-layer all-reduces started inside it
     # (dp.allreduce_async) + the grouped reduce of the rest.  Same data on both ranks: the result must be identical on
     # both ranks and equal a local backward up to the run-to-run noise of the bf16 network (two backward passes of the
@@ -94,13 +108,14 @@ def main():
     # values amplifies the flipped bf16 roundings)
     avg_g = g_backward(True)
     for k in local_g:
+        # (every rank must issue the same collectives: nothing rank-local may decide whether same_on_all_ranks runs)
+        assert same_on_all_ranks(avg_g[k]), f"averaged gradient {k} differs between ranks"
         a, b = local_g[k].double(), avg_g[k].double()
         if float(a.norm()) < 1e-6:
             continue
         rel = float((a - b).norm() / a.norm())
         worst = max(worst, rel)
         assert rel < 0.25, (k, rel)
-        assert same_on_all_ranks(avg_g[k]), f"averaged gradient {k} differs between ranks"
     torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:

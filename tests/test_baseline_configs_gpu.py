@@ -151,7 +151,7 @@ def test_two_rank_replicas_stay_identical_and_gradients_average():
     env.pop("PAI_DP_OVERLAP", None)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dp_worker.py")]
-    out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     print(out.stdout[-4000:])
     assert out.returncode == 0, out.stdout[-4000:]
     assert "dp_worker ok" in out.stdout
