@@ -119,8 +119,11 @@ def main():
     torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:
-        print(f"dp_worker ok (world {world}; worst averaged-vs-local gradient deviation {worst:.2e})")
-    dist.destroy_process_group()
+        print(f"dp_worker ok (world {world}; worst averaged-vs-local gradient deviation {worst:.2e})", flush=True)
+    # leave without tearing the communicator down: destroy_process_group() can block forever while captured CUDA graphs
+    # still reference the NCCL communicator (seen on 2 B200s); the process is done
+    sys.stdout.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":

@@ -1,7 +1,10 @@
 """GPU parity of the SSIM / PSNR / RMSE kernel (C-ABI pai_ssim_psnr_fwd / _bwd through
 pai_b200.metrics) against the oracle: the torchmetrics-0.11.4 restatement (oracle/torchmetrics_port.py),
-the independent fp64 C formulation (oracle/ssim_ref.c) and the fixtures produced by the real reference
-(tests/golden/metrics_ref.npz).  Tolerance for SSIM/PSNR: 1e-4 (BASELINE.json north_star)."""
+the independent fp64 C formulation (oracle/ssim_ref.c) and the fixtures of tests/golden/metrics_ref.npz.  Those fixtures
+were produced by the reference's own call sites (models/utils.py:38-47, report.py:78-96,188-217) running ON that same
+restatement (oracle/shim/torchmetrics; the real torchmetrics 0.11.4 cannot be installed here): they pin the kernel to the
+port, NOT to torchmetrics itself -- the metric half of the oracle stays "parity unpinned" (DESIGN.md section 2), backed by
+closed-form answers and the fp64 C formulation.  Tolerance for SSIM/PSNR: 1e-4 (BASELINE.json north_star)."""
 import ctypes
 import math
 import os
