@@ -143,20 +143,22 @@ def allreduce_gradients(params) -> int:
     big = [g for g in grads if g.numel() >= _BIG and g.is_contiguous()]
     small = [g for g in grads if not (g.numel() >= _BIG and g.is_contiguous())]
     # the large gradients (convolution weights, 229 MB fp32 for generator + PatchGAN)
-    if big and avg is not None and grad_exchange_dtype() == torch.bfloat16 and all(g.dtype == torch.float32 for g in big):
-        # travel as bf16 (115 MB instead of 229 MB; the all-reduce is bandwidth bound at this size):
-        # one multi-tensor cast into a flat buffer, ONE collective, one multi-tensor cast back.  Every element is rounded to
-        # bf16 once before and once after the sum (2^-9 relative); all ranks receive the same bits, so replicas stay identical.
-        n_big = sum(g.numel() for g in big)
-        flat = _flat_buffer(n_big, big[0].device)
+    if big and avg is not None and grad_exchange_dtype() == torch.bfloat16 and all(g.dtype == torch.float32 for g in grads):
+        # travel as bf16 (115 MB instead of 229 MB; at 8 GPUs the all-reduce is bandwidth bound:
+        # 9.12 vs 9.35 ms/step): one multi-tensor cast into a flat buffer, ONE collective for large and small gradients
+        # alike, one multi-tensor cast back.  Every element is rounded to bf16 once before and once after the sum (2^-9
+        # relative); all ranks receive the same bits, so replicas stay identical.
+        every = big + small
+        n_all = sum(g.numel() for g in every)
+        flat = _flat_buffer(n_all, every[0].device)
         views, off = [], 0
-        for g in big:
-            views.append(flat[off:off + g.numel()].view_as(g))
+        for g in every:
+            views.append(flat[off:off + g.numel()].view(g.shape))
             off += g.numel()
-        torch._foreach_copy_(views, big)
+        torch._foreach_copy_(views, [g.contiguous() for g in every])
         dist.all_reduce(flat, op=avg)
-        torch._foreach_copy_(big, views)
-        total += n_big
+        torch._foreach_copy_(every, views)
+        return n_all
     elif big:
         # averaged in place by ONE grouped NCCL launch (ncclGroupStart/End around the per-tensor all-reduces) -- no
         # flatten / copy-back passes and no per-tensor launch latency
