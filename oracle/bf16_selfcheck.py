@@ -4,7 +4,7 @@ import sys
 import os; sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 import pix2pix_port as port
-n=2
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 sd = port.init_state(3, 1, 1, loss_type="ssim+psnr")
 x, target = port.synthetic_pairs(n, seed=50 + n)
 def run(autocast):
@@ -17,6 +17,6 @@ def run(autocast):
 a, ya = run(False); b, yb = run(True)
 print("ydiff", (ya-yb).abs().max().item())
 for k in a.g_keys:
-    if not k.endswith("weight") or ".2." in k: continue
+    if not k.endswith("weight") or "code.2." in k: continue   # BatchNorm affine
     g, go = b.sd[k].grad.double(), a.sd[k].grad.double()
     print(f"{k:40s} cos {float((g*go).sum()/(g.norm()*go.norm())):.4f} ratio {float(g.norm()/go.norm()):.4f}")

@@ -18,7 +18,7 @@ for r in rows[1:]:
     val = float(r[idx["Metric Value"]].replace(",", ""))
     unit = r[idx["Metric Unit"]]
     name = r[idx["Metric Name"]]
-    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "usecond": 1.0, "msecond": 1e3, "nsecond": 1e-3, "second": 1e6, "%": 1.0}.get(unit, 1.0)
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "usecond": 1.0, "msecond": 1e3, "nsecond": 1e-3, "ns": 1e-3, "us": 1.0, "ms": 1e3, "second": 1e6, "%": 1.0}.get(unit, 1.0)
     d[name] = val * scale
 launches = [d for _, d in sorted(per.items(), key=lambda kv: int(kv[0]))]
 tot_b = sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in launches)

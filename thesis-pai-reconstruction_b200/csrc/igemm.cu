@@ -95,7 +95,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&ps.acc_full[a], 1);
-            mbar_init(&ps.acc_empty[a], PAIR ? 512 : 256);
+            mbar_init(&ps.acc_empty[a], PAIR ? 16 : 8);       // one arrival per epilogue warp (and CTA)
         }
         mbar_fence_init();
     }
@@ -316,15 +316,18 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             // fused activation backward: the saved activations of this warp's first chunk are fetched while the MMAs of
             // the tile are still running, those of the next chunk while the current one is packed and stored
             const bool masked = p.mask_src != nullptr && fast;
-            uint4 mreg[8];
-            auto mask_fetch = [&](int c) {
+            // two chunk buffers: both of this warp's chunks of a 256-column (phase-fused) tile are in flight before the
+            // accumulator is waited for -- a DRAM round trip is longer than packing and storing one chunk
+            uint4 mreg[2][8];
+            auto mask_fetch = [&](int c, uint4 (&dst)[8]) {
                 const long long coff = fused ? p.out_phase_off[c >> 6] : 0;
                 const __nv_bfloat16* mrow = reinterpret_cast<const __nv_bfloat16*>(p.mask_src) + off + coff + (fused ? 0 : c);
 #pragma unroll
                 for (int ch = 0; ch < 8; ++ch)
-                    mreg[ch] = row_ok ? __ldg(reinterpret_cast<const uint4*>(mrow) + ch) : make_uint4(0, 0, 0, 0);
+                    dst[ch] = row_ok ? __ldg(reinterpret_cast<const uint4*>(mrow) + ch) : make_uint4(0, 0, 0, 0);
             };
-            if (masked && 64 * half < acc_n) mask_fetch(64 * half);
+            if (masked && 64 * half < acc_n) mask_fetch(64 * half, mreg[0]);
+            if (masked && 64 * half + 128 < acc_n) mask_fetch(64 * half + 128, mreg[1]);
             {
                 ROLE_T0();
                 mbar_wait(&ps.acc_full[a], acc_phase);
@@ -357,8 +360,14 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         const float* bias_c = p.bias != nullptr ? p.bias + col0 + oc : nullptr;
                         // activation / bias dispatch hoisted out of the 64-element loop
                         if (masked && which == 0) {
-                            mask_pack(v, mreg, p.mask_slope, tile, lane);
-                            if (c + 128 < acc_n) mask_fetch(c + 128);      // this warp's next chunk (n_out == 1)
+                            // this warp's chunks are c = 64 * half + 128 * k (n_out == 1): buffer k & 1
+                            if (((c >> 7) & 1) == 0) {
+                                mask_pack(v, mreg[0], p.mask_slope, tile, lane);
+                                if (c + 256 < acc_n) mask_fetch(c + 256, mreg[0]);
+                            } else {
+                                mask_pack(v, mreg[1], p.mask_slope, tile, lane);
+                                if (c + 256 < acc_n) mask_fetch(c + 256, mreg[1]);
+                            }
                         } else if (act == PAI_ACT_LEAKY)
                             bias_act_pack<PAI_ACT_LEAKY>(v, bias_c, p.slope, tile, lane);
                         else if (act == PAI_ACT_RELU)
@@ -464,12 +473,14 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                                       vec_ok && col0 + cc + 16 <= p.cout, p.cout - (col0 + cc));
                 }
             }
-            __syncwarp();
             tc_fence_before();
-            if (PAIR)
-                mbar_arrive_leader(&ps.acc_empty[a]);   // 2 x 256 arrivals (both CTAs) release the accumulator pair
-            else
-                mbar_arrive(&ps.acc_empty[a]);          // 256 arrivals release the accumulator to the MMA warp
+            __syncwarp();
+            if (lane == 0) {                            // (every lane fenced its TMEM reads before the __syncwarp)
+                if (PAIR)
+                    mbar_arrive_leader(&ps.acc_empty[a]);   // 2 x 8 warps (both CTAs) release the accumulator pair
+                else
+                    mbar_arrive(&ps.acc_empty[a]);          // 8 warps release the accumulator to the MMA warp
+            }
 #ifdef PAI_PROFILE_ROLES
             prof_total += clock64() - twork;
 #endif
@@ -532,7 +543,7 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_consta
             mbar_init(&ps.empty[s], 1);
         }
         mbar_init(&ps.acc_full[0], 1);
-        mbar_init(&ps.acc_empty[0], 128);
+        mbar_init(&ps.acc_empty[0], 4);
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc(&ps.tmem_base, tmem_cols);
@@ -645,9 +656,9 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_consta
                     }
                 }
             }
-            __syncwarp();
             tc_fence_before();
-            mbar_arrive(&ps.acc_empty[0]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ps.acc_empty[0]);
             ++seg;
         }
     }

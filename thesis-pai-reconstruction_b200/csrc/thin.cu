@@ -149,15 +149,16 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
     fence_proxy_async_smem();
     if (warp == 4 && lane == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&ps.a_full[s], 128);
+            // one arrival per WARP (lane 0 after __syncwarp): 128 per-thread arrivals on one mbarrier serialise
+            mbar_init(&ps.a_full[s], 4);
             mbar_init(&ps.a_empty[s], 1);
             mbar_init(&ps.acc_full[s], 1);
-            mbar_init(&ps.acc_empty[s], 128);
+            mbar_init(&ps.acc_empty[s], 4);
         }
         if (STREAM)
             for (int s = 0; s < kThinRing; ++s) {
-                mbar_init(&ring_full[s], 1);
-                mbar_init(&ring_empty[s], 128);
+                mbar_init(&ring_full[s], CIN);           // one arrival (with its byte count) per plane loader
+                mbar_init(&ring_empty[s], 4);
             }
         mbar_fence_init();
     }
@@ -170,6 +171,9 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
     if (warp < 4 && STREAM) {
         // ---------------- producers (streaming): thread r <-> output column r of the CTA's current output row
         const int r = warp * 32 + lane;
+        const uint32_t ring_s = smem_u32(ring);
+        const uint32_t col_b = (uint32_t)(2 * r) * 4;                 // byte offset of input column 2r inside a row
+        const uint32_t lft_b = r > 0 ? 4u : 0u, rgt_b = r < 127 ? 8u : 0u;   // neighbours 2r-1 / 2r+2 (clamped at the image edge)
         int gc = 0;                                   // granule counter of this CTA (same sequence as the loader's)
         int i = 0;
         long long row = t_begin;
@@ -194,23 +198,26 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
                 }
                 uint32_t words[8 * CIN];
                 float v[CIN][16];
+                // shared-space loads with immediate offsets: one base register per granule, the plane / row-of-granule
+                // offsets are compile-time constants (this warp is alone on its scheduler: the loop is a chain of dependent
+                // instructions, so every address computation it does not need counts)
+                const uint32_t base_lo = ring_s + (uint32_t)((gc % kThinRing) * CIN) * (2 * kThinRowW * 4) + col_b;
+                const uint32_t base_hi = ring_s + (uint32_t)((g1 % kThinRing) * CIN) * (2 * kThinRowW * 4) + col_b;
+                const bool top_ok = a > 0, bot_ok = 2 * a + 2 < p.ih;       // input rows 2a-1 / 2a+2 inside the image
 #pragma unroll
                 for (int j = 0; j < CIN; ++j) {
 #pragma unroll
                     for (int ky = 0; ky < 4; ++ky) {
-                        const int iy = 2 * a - 1 + ky;
-                        const bool rok = iy >= 0 && iy < p.ih;
-                        const int gsl = (ky < 2 ? gc : g1) % kThinRing;
-                        // granule rows: ky 0 -> row 2(a-1)+1 (first row of granule a-1), ky 1 -> its second, ky 2, 3 -> granule a
-                        const float* rp = ring + ((size_t)(gsl * CIN + j) * 2 + (ky & 1)) * kThinRowW;
-                        float2 mid = make_float2(0.f, 0.f);
-                        float lft = 0.f, rgt = 0.f;
-                        if (rok) {
-                            mid = *reinterpret_cast<const float2*>(rp + 2 * r);
-                            if (r > 0) lft = rp[2 * r - 1];
-                            if (2 * r + 2 < kThinRowW) rgt = rp[2 * r + 2];
-                        }
-                        v[j][ky * 4 + 0] = lft, v[j][ky * 4 + 1] = mid.x, v[j][ky * 4 + 2] = mid.y, v[j][ky * 4 + 3] = rgt;
+                        const uint32_t addr = (ky < 2 ? base_lo : base_hi) + (uint32_t)(j * 2 + (ky & 1)) * (kThinRowW * 4);
+                        float m0, m1, lf, rg;
+                        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m0), "=f"(m1) : "r"(addr));
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lf) : "r"(addr - lft_b));
+                        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(rg) : "r"(addr + rgt_b));
+                        const bool rok = ky == 0 ? top_ok : (ky == 3 ? bot_ok : true);
+                        v[j][ky * 4 + 0] = (rok && r > 0) ? lf : 0.f;
+                        v[j][ky * 4 + 1] = rok ? m0 : 0.f;
+                        v[j][ky * 4 + 2] = rok ? m1 : 0.f;
+                        v[j][ky * 4 + 3] = (rok && r < 127) ? rg : 0.f;
                     }
                 }
                 if (CIN == 1) {
@@ -226,7 +233,8 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
                         words[q] = *reinterpret_cast<uint32_t*>(&h);
                     }
                 }
-                mbar_arrive(&ring_empty[gc % kThinRing]);           // granule a-1 is not needed after this tile
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ring_empty[gc % kThinRing]);   // granule a-1 is not needed after this tile
                 const int s = i & 1;
                 {
                     TROLE_T0();
@@ -239,9 +247,11 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
                     *reinterpret_cast<uint4*>(a_tile + sw128_off(r, c)) =
                         make_uint4(words[4 * c], words[4 * c + 1], words[4 * c + 2], words[4 * c + 3]);
                 fence_proxy_async_smem();
-                mbar_arrive(&ps.a_full[s]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ps.a_full[s]);
             }
-            mbar_arrive(&ring_empty[gc % kThinRing]);               // last granule of the segment
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ring_empty[gc % kThinRing]);       // last granule of the segment
             ++gc;
             row = (long long)img * p.oh + a_hi;
         }
@@ -250,9 +260,13 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
             printf("[thin roles] producer: total %lld cyc, waiting for input rows %lld, for a free A slot %lld, tiles %d\n",
                    clock64() - tstart, w_ring, w_slot, i);
 #endif
-    } else if (warp == 5 && STREAM) {
-        // ---------------- loader: bulk async copies of the input rows into the granule ring
+    } else if ((warp == 5 || (CIN == 2 && warp == 6)) && STREAM) {
+        // ---------------- loaders: bulk async copies of the input rows into the granule ring, one thread per plane (an
+        // elected thread needs ~250 cycles per cp.async.bulk: with one loader and four 1 KB copies per granule the
+        // 2-plane layer was loader-bound).  The two rows of a granule are adjacent in memory: one 2 KB copy when both exist.
         if (elect_one()) {
+            const int j = warp - 5;                                  // plane of this loader
+            const float* plane = j == 0 ? p.p0 : p.p1;
             int gc = 0;
             long long row = t_begin;
             const long long row_end = t_begin + t_count;
@@ -261,16 +275,18 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
                 const int a_lo = (int)(row - (long long)img * p.oh);
                 const long long img_end = (long long)(img + 1) * p.oh;
                 const int a_hi = (int)((img_end < row_end ? img_end : row_end) - (long long)img * p.oh);
+                const float* src = plane + (size_t)img * p.ih * p.iw;
                 for (int g = a_lo - 1; g < a_hi; ++g, ++gc) {
                     const int sl = gc % kThinRing;
                     mbar_wait(&ring_empty[sl], (uint32_t)(((gc / kThinRing) & 1) ^ 1));
                     const int r0 = 2 * g + 1, r1 = 2 * g + 2;
                     const bool ok0 = r0 >= 0, ok1 = r1 < p.ih;
-                    mbar_expect_tx(&ring_full[sl], (uint32_t)(((ok0 ? 1 : 0) + (ok1 ? 1 : 0)) * CIN * kThinRowW * 4));
-#pragma unroll
-                    for (int j = 0; j < CIN; ++j) {
-                        const float* src = (j == 0 ? p.p0 : p.p1) + (size_t)img * p.ih * p.iw;
-                        float* dst = ring + (size_t)(sl * CIN + j) * 2 * kThinRowW;
+                    float* dst = ring + (size_t)(sl * CIN + j) * 2 * kThinRowW;
+                    if (ok0 && ok1) {
+                        mbar_expect_tx(&ring_full[sl], 2 * kThinRowW * 4);
+                        bulk_g2s(dst, src + (size_t)r0 * p.iw, 2 * kThinRowW * 4, &ring_full[sl]);
+                    } else {
+                        mbar_expect_tx(&ring_full[sl], kThinRowW * 4);
                         if (ok0) bulk_g2s(dst, src + (size_t)r0 * p.iw, kThinRowW * 4, &ring_full[sl]);
                         if (ok1) bulk_g2s(dst + kThinRowW, src + (size_t)r1 * p.iw, kThinRowW * 4, &ring_full[sl]);
                     }
@@ -329,7 +345,8 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
                 *reinterpret_cast<uint4*>(a_tile + sw128_off(r, c)) =
                     make_uint4(words[4 * c], words[4 * c + 1], words[4 * c + 2], words[4 * c + 3]);
             fence_proxy_async_smem();
-            mbar_arrive(&ps.a_full[s]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ps.a_full[s]);
         }
     } else if (warp == 4) {
         // ---------------- MMA issuer
@@ -402,7 +419,8 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
                     thin_store_dispatch(v, p.act2, p.slope, tile_buf, lane, p.out2 + c0, pix0, p.ld2, p.total_pix);
             }
             tc_fence_before();
-            mbar_arrive(&ps.acc_empty[g]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ps.acc_empty[g]);
 #ifdef PAI_PROFILE_ROLES
             ep_work += clock64() - tw0;
 #endif
@@ -461,7 +479,7 @@ thin_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const ThinWgradParam
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tm_u);
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kThinWgradStages; ++s) {
-            mbar_init(&ps.full[s], 129);      // 128 column-producer threads + the TMA thread's expect_tx arrival
+            mbar_init(&ps.full[s], 5);        // 4 column-producer warps (lane 0 after __syncwarp) + the TMA thread's expect_tx arrival
             mbar_init(&ps.empty[s], 1);
         }
         mbar_init(&ps.acc_full, 1);
@@ -560,7 +578,8 @@ thin_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const ThinWgradParam
                                                      (uint32_t)((((qp >> 2) ^ (k & 7)) << 4) + ((qp & 3) << 2))) = words[kx * CIN + j];
                     }
                 fence_proxy_async_smem();
-                mbar_arrive(&ps.full[stage]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ps.full[stage]);
                 if (++stage == kThinWgradStages) stage = 0, phase ^= 1;
             }
         }
@@ -642,7 +661,7 @@ thin_convT_plane_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&ps.acc_full[a], 1);
-            mbar_init(&ps.acc_empty[a], 128);
+            mbar_init(&ps.acc_empty[a], 4);
         }
         mbar_init(&ps.w_full, 1);
         mbar_fence_init();
@@ -740,7 +759,8 @@ thin_convT_plane_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
                     tmem_ld_16(tmem_base + acc * 16 + ((uint32_t)(q * 32) << 16), v);
                     tmem_ld_wait();
                     tc_fence_before();
-                    mbar_arrive(&ps.acc_empty[acc]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&ps.acc_empty[acc]);
                     ++cnt;
 #pragma unroll
                     for (int t = 0; t < 16; ++t) ring[sc][t][b] = __uint_as_float(v[t]);
