@@ -252,6 +252,9 @@ int pai_afmhot_u8(const float* img, int n, long long hw, unsigned char* out, voi
  *                          Adam update in place (skipped when grad == NULL: pack only), then
  *                          pack1[a, (ky*4+kx)*b + b'] and pack2[py*2+px, b', (ty*2+tx)*a + a'] (either may
  *                          be NULL; pack2 has b_pad rows per phase; padding rows are left untouched)
+ *   pai_adam_pack_conv4x4_multi  the same for `count` weights in ONE launch (host arrays, one entry per weight;
+ *                          grads are required): a launch per weight keeps every small layer at the latency of one
+ *                          thread block
  *   pai_adam_multi         the same update for `count` small dense tensors in one launch (host arrays of
  *                          device pointers)
  *   pai_adam_prepare       device-side step counter for CUDA-graph capture of the training step: ++*step and
@@ -262,6 +265,10 @@ int pai_afmhot_u8(const float* img, int n, long long hw, unsigned char* out, voi
 int pai_adam_pack_conv4x4(float* w, const float* grad, float* exp_avg, float* exp_avg_sq, int a, int b, float beta1,
                           float beta2, float step_size, float inv_bias_correction2_sqrt, float eps, void* pack1,
                           void* pack2, int b_pad, const float* dyn, void* stream);
+int pai_adam_pack_conv4x4_multi(int count, float* const* ws, const float* const* grads, float* const* exp_avgs,
+                                float* const* exp_avg_sqs, const int* as, const int* bs, void* const* pack1s,
+                                void* const* pack2s, const int* b_pads, float beta1, float beta2, float step_size,
+                                float inv_bias_correction2_sqrt, float eps, const float* dyn, void* stream);
 int pai_adam_multi(int count, float* const* params, const float* const* grads, float* const* exp_avgs,
                    float* const* exp_avg_sqs, const int* numels, float beta1, float beta2, float step_size,
                    float inv_bias_correction2_sqrt, float eps, const float* dyn, void* stream);

@@ -32,3 +32,10 @@ print("gaps >2us:", sum(1 for g in gaps if g > 2)/steps, "per step, total", sum(
 agg = collections.Counter(); cnt = collections.Counter()
 for a, b, n in ks: agg[n[:90]] += (b - a); cnt[n[:90]] += 1
 for n, t in agg.most_common(60): print(f"{t/steps/1e3:8.3f} ms/step  x{cnt[n]/steps:6.1f}  {n}")
+# per-kernel-name table (time per step, launches per step)
+agg = collections.defaultdict(lambda: [0.0, 0])
+for a, b, name in ks:
+    agg[name][0] += b - a; agg[name][1] += 1
+print("\nper kernel (us/step, launches/step):")
+for name, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+    print(f"{t/steps:9.1f} us  x{n/steps:5.1f}  {name[:150]}")

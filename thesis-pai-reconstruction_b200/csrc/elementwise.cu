@@ -68,6 +68,29 @@ __device__ __forceinline__ float act_grad(float z, int act, float slope) {
 
 // Block-level reduction of per-thread 8-channel partial sums (two quantities) followed by one
 // atomicAdd per channel: threads with equal (threadIdx.x % cv) own the same channels.
+// Grid of the streaming kernels below: ONE wave -- as many blocks as are resident at once (occupancy x SMs), never
+// more than the rows need.  The former fixed 148 x 8 blocks ran as 1.6 - 2.7 waves of 3 - 5 resident blocks: every wave
+// pays the cold-load latency and (reduce kernels) the block-reduction + atomics tail again, and the last wave is partly
+// empty (bn_stats of 16.8 MB took 20 us).
+template <auto Kernel>
+static int wave_grid(long long m, int c) {
+    static int per_sm[64] = {};
+    const int dev = current_device();
+    if (dev < 0) return 1;
+    int nb = __atomic_load_n(&per_sm[dev & 63], __ATOMIC_RELAXED);
+    if (nb == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, Kernel, kEwThreads, 0) != cudaSuccess || nb < 1) nb = 2;
+        (void)cudaGetLastError();
+        __atomic_store_n(&per_sm[dev & 63], nb, __ATOMIC_RELAXED);
+    }
+    const long long ppb = kEwThreads / (c >> 3);
+    long long blocks = (m + ppb - 1) / ppb;
+    const long long cap = (long long)sm_count(dev) * nb;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
 __device__ __forceinline__ void block_reduce_2x8(const Vec8& a, const Vec8& b, int cv, int c, float* out) {
     __shared__ float red[kEwThreads * 16];
     float* mine = red + threadIdx.x * 16;
@@ -313,11 +336,11 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long m, int c, int ld, c
 }
 
 template <int MODE>
-static int bn_bwd_dispatch(int grid, cudaStream_t st, const __nv_bfloat16* x, long long m, int c, int ld, const float* ss,
+static int bn_bwd_dispatch(cudaStream_t st, const __nv_bfloat16* x, long long m, int c, int ld, const float* ss,
                            const __nv_bfloat16* g1, int ldg1, int act1, const __nv_bfloat16* g2, int ldg2, int act2,
                            float slope, float* sums, const float* gamma, __nv_bfloat16* dx, int lddx) {
 #define PAI_BWD(A1, A2, BNF)                                                                                        \
-    bn_bwd_kernel<A1, A2, BNF, MODE><<<grid, kEwThreads, 0, st>>>(x, m, c, ld, ss, g1, ldg1, g2, ldg2, slope, sums, \
+    bn_bwd_kernel<A1, A2, BNF, MODE><<<wave_grid<bn_bwd_kernel<A1, A2, BNF, MODE>>(m, c), kEwThreads, 0, st>>>(x, m, c, ld, ss, g1, ldg1, g2, ldg2, slope, sums, \
                                                                    gamma, dx, lddx)
 #define PAI_BWD_A2(A1, BNF)                                            \
     do {                                                               \
@@ -398,14 +421,6 @@ colsum_wide_kernel(const __nv_bfloat16* __restrict__ x, long long m, int c, int 
     for (int i = 0; i < 8; ++i) atomicAdd(sums + vec * 8 + i, s.v[i]);
 }
 
-static int ew_grid(long long m, int c) {
-    const long long ppb = kEwThreads / (c >> 3);
-    long long blocks = (m + ppb - 1) / ppb;
-    const long long cap = 148LL * 8;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    return (int)blocks;
-}
 static bool ew_ok(int c, const void* p, int ld) {
     const int cv = c >> 3;
     return c > 0 && c % 8 == 0 && cv <= kEwThreads && kEwThreads % cv == 0 && ld % 8 == 0 &&
@@ -424,7 +439,7 @@ int pai_bn_stats(const void* x, long long m, int c, int ld, float* sums, void* s
     PAI_REQUIRE(ew_ok(c, x, ld), "pai_bn_stats: c=%d ld=%d must be multiples of 8 with (c/8) | 256, x 16 B aligned", c, ld);
     cudaStream_t st = (cudaStream_t)stream;
     PAI_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, st));
-    bn_stats_kernel<<<ew_grid(m, c), kEwThreads, 0, st>>>((const bf16*)x, m, c, ld, sums);
+    bn_stats_kernel<<<wave_grid<bn_stats_kernel>(m, c), kEwThreads, 0, st>>>((const bf16*)x, m, c, ld, sums);
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -451,10 +466,9 @@ int pai_bn_apply_act(const void* x, long long m, int c, int ld, const float* sca
     PAI_REQUIRE(x && out1 && m > 0, "pai_bn_apply_act: null pointer / empty input");
     PAI_REQUIRE(ew_ok(c, x, ld) && ew_ok(c, out1, ld1) && (out2 == nullptr || ew_ok(c, out2, ld2)),
                 "pai_bn_apply_act: bad channel count / stride / alignment (c=%d)", c);
-    const int grid = ew_grid(m, c);
     cudaStream_t st = (cudaStream_t)stream;
 #define PAI_APPLY(A1, A2) \
-    bn_apply_act_kernel<A1, A2><<<grid, kEwThreads, 0, st>>>((const bf16*)x, m, c, ld, scale_shift, (bf16*)out1, ld1, (bf16*)out2, ld2, slope)
+    bn_apply_act_kernel<A1, A2><<<wave_grid<bn_apply_act_kernel<A1, A2>>(m, c), kEwThreads, 0, st>>>((const bf16*)x, m, c, ld, scale_shift, (bf16*)out1, ld1, (bf16*)out2, ld2, slope)
 #define PAI_APPLY_A2(A1)                                               \
     do {                                                               \
         if (out2 == nullptr) PAI_APPLY(A1, -1);                        \
@@ -479,7 +493,7 @@ int pai_bn_bwd_reduce(const void* x, long long m, int c, int ld, const float* sc
                 "pai_bn_bwd_reduce: bad channel count / stride / alignment (c=%d)", c);
     cudaStream_t st = (cudaStream_t)stream;
     PAI_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, st));
-    return bn_bwd_dispatch<0>(ew_grid(m, c), st, (const bf16*)x, m, c, ld, scale_shift, (const bf16*)g1, ldg1, act1,
+    return bn_bwd_dispatch<0>(st, (const bf16*)x, m, c, ld, scale_shift, (const bf16*)g1, ldg1, act1,
                               (const bf16*)g2, ldg2, act2, slope, sums, nullptr, nullptr, 0);
 }
 
@@ -490,7 +504,7 @@ int pai_bn_bwd_apply(const void* x, long long m, int c, int ld, const float* sca
                 "pai_bn_bwd_apply: null pointer / empty input");
     PAI_REQUIRE(ew_ok(c, x, ld) && ew_ok(c, g1, ldg1) && (g2 == nullptr || ew_ok(c, g2, ldg2)) && ew_ok(c, dx, lddx),
                 "pai_bn_bwd_apply: bad channel count / stride / alignment (c=%d)", c);
-    return bn_bwd_dispatch<1>(ew_grid(m, c), (cudaStream_t)stream, (const bf16*)x, m, c, ld, scale_shift, (const bf16*)g1,
+    return bn_bwd_dispatch<1>((cudaStream_t)stream, (const bf16*)x, m, c, ld, scale_shift, (const bf16*)g1,
                               ldg1, act1, (const bf16*)g2, ldg2, act2, slope, const_cast<float*>(sums), gamma, (bf16*)dx,
                               lddx);
 }
@@ -502,7 +516,7 @@ int pai_act_bwd(const void* x, long long m, int c, int ld, const void* g1, int l
                 "pai_act_bwd: bad channel count / stride / alignment (c=%d)", c);
     cudaStream_t st = (cudaStream_t)stream;
     PAI_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, st));
-    return bn_bwd_dispatch<2>(ew_grid(m, c), st, (const bf16*)x, m, c, ld, nullptr, (const bf16*)g1, ldg1, act1,
+    return bn_bwd_dispatch<2>(st, (const bf16*)x, m, c, ld, nullptr, (const bf16*)g1, ldg1, act1,
                               (const bf16*)g2, ldg2, act2, slope, sums, nullptr, (bf16*)dx, lddx);
 }
 
@@ -519,7 +533,7 @@ int pai_colsum(const void* x, long long m, int c, int ld, float* sums2c, void* s
         return 0;
     }
     PAI_CUDA_OK(cudaMemsetAsync(sums2c, 0, sizeof(float) * 2 * c, st));
-    colsum_kernel<<<ew_grid(m, c), kEwThreads, 0, st>>>((const bf16*)x, m, c, ld, sums2c);
+    colsum_kernel<<<wave_grid<colsum_kernel>(m, c), kEwThreads, 0, st>>>((const bf16*)x, m, c, ld, sums2c);
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -49,16 +49,14 @@ __device__ __forceinline__ float adam_update(float p, float g, float& m, float& 
 
 static constexpr int kTA = 32, kTB = 32, kPackThreads = 256;
 
-// grid (ceil(B/32), ceil(A/32)); smem: s1[16][32 a][32 b] and s2[16][32 b][32 a] bf16 (2 x 32 KB)
-__global__ void __launch_bounds__(kPackThreads)
-adam_pack_conv4x4_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
-                         float* __restrict__ v, int A, int B, AdamHyper hy0, const float* __restrict__ dyn,
-                         __nv_bfloat16* __restrict__ p1, __nv_bfloat16* __restrict__ p2, int b_pad) {
+// one 32 x 32 (a, b) tile of one weight; smem: s1[16][32 a][32 b] and s2[16][32 b][32 a] bf16 (2 x 32 KB)
+__device__ __forceinline__ void adam_pack_tile(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
+                                               float* __restrict__ v, int A, int B, const AdamHyper& hy,
+                                               __nv_bfloat16* __restrict__ p1, __nv_bfloat16* __restrict__ p2, int b_pad,
+                                               int a0, int b0) {
     extern __shared__ __nv_bfloat16 pk_smem[];
-    const AdamHyper hy = adam_dyn(hy0, dyn);
     __nv_bfloat16* s1 = pk_smem;                       // [tap][a][b]
     __nv_bfloat16* s2 = pk_smem + 16 * kTA * kTB;      // [tap][b][a]
-    const int a0 = blockIdx.y * kTA, b0 = blockIdx.x * kTB;
     const int tid = threadIdx.x;
     // ---- pass 1: float4 = 4 taps of one (a, b); a row of the tile is 32 b x 16 taps = 128 float4
     // (four iterations = 16 independent 16-byte loads in flight per thread)
@@ -126,6 +124,40 @@ adam_pack_conv4x4_kernel(float* __restrict__ w, const float* __restrict__ g, flo
             }
         }
     }
+}
+
+// grid (ceil(B/32), ceil(A/32))
+__global__ void __launch_bounds__(kPackThreads)
+adam_pack_conv4x4_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
+                         float* __restrict__ v, int A, int B, AdamHyper hy0, const float* __restrict__ dyn,
+                         __nv_bfloat16* __restrict__ p1, __nv_bfloat16* __restrict__ p2, int b_pad) {
+    adam_pack_tile(w, g, m, v, A, B, adam_dyn(hy0, dyn), p1, p2, b_pad, blockIdx.y * kTA, blockIdx.x * kTB);
+}
+
+// All 4x4 convolution weights of an optimizer in ONE launch: block -> (weight, tile) through the prefix of tile counts.
+// One launch per weight left the small layers (8 .. 128 tiles) at the ~20 us latency of a single block each, 8 of the 17
+// launches of a step.
+static constexpr int kMaxPackWeights = 24;
+struct AdamPackTable {
+    float* w[kMaxPackWeights];
+    const float* g[kMaxPackWeights];
+    float* m[kMaxPackWeights];
+    float* v[kMaxPackWeights];
+    __nv_bfloat16* p1[kMaxPackWeights];
+    __nv_bfloat16* p2[kMaxPackWeights];
+    int A[kMaxPackWeights], B[kMaxPackWeights], b_pad[kMaxPackWeights];
+    int first_tile[kMaxPackWeights + 1];
+    int count;
+};
+
+__global__ void __launch_bounds__(kPackThreads)
+adam_pack_multi_kernel(const __grid_constant__ AdamPackTable t, AdamHyper hy0, const float* __restrict__ dyn) {
+    int k = 0;
+    while (k + 1 < t.count && (int)blockIdx.x >= t.first_tile[k + 1]) ++k;
+    const int tile = blockIdx.x - t.first_tile[k];
+    const int tiles_b = (t.B[k] + kTB - 1) / kTB;
+    adam_pack_tile(t.w[k], t.g[k], t.m[k], t.v[k], t.A[k], t.B[k], adam_dyn(hy0, dyn), t.p1[k], t.p2[k], t.b_pad[k],
+                   (tile / tiles_b) * kTA, (tile % tiles_b) * kTB);
 }
 
 // ---- weight gradient: GEMM layout -> parameter layout ----------------------------------------------------------
@@ -248,6 +280,48 @@ int pai_adam_pack_conv4x4(float* w, const float* grad, float* exp_avg, float* ex
     adam_pack_conv4x4_kernel<<<grid, kPackThreads, smem, (cudaStream_t)stream>>>(
         w, grad, exp_avg, exp_avg_sq, a, b, hy, dyn, (__nv_bfloat16*)pack1, (__nv_bfloat16*)pack2, b_pad);
     PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pai_adam_pack_conv4x4_multi(int count, float* const* ws, const float* const* grads, float* const* exp_avgs,
+                                float* const* exp_avg_sqs, const int* as, const int* bs, void* const* pack1s,
+                                void* const* pack2s, const int* b_pads, float beta1, float beta2, float step_size,
+                                float inv_bias_correction2_sqrt, float eps, const float* dyn, void* stream) {
+    PAI_REQUIRE(count >= 0 && (count == 0 || (ws && grads && exp_avgs && exp_avg_sqs && as && bs && pack1s && pack2s && b_pads)),
+                "pai_adam_pack_conv4x4_multi: null table");
+    static DeviceOnce attr_once;
+    const int attr_dev = current_device();
+    if (attr_dev < 0) return -1;
+    const int smem = 2 * 16 * kTA * kTB * (int)sizeof(__nv_bfloat16);
+    if (attr_once.need(attr_dev)) {
+        PAI_CUDA_OK(cudaFuncSetAttribute(adam_pack_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_once.mark(attr_dev);
+    }
+    AdamHyper hy = {1.f - beta1, beta2, 1.f - beta2, step_size, inv_bias_correction2_sqrt, eps};
+    for (int base = 0; base < count; base += kMaxPackWeights) {
+        AdamPackTable t;
+        t.count = count - base < kMaxPackWeights ? count - base : kMaxPackWeights;
+        int tiles = 0;
+        for (int i = 0; i < t.count; ++i) {
+            const int k = base + i;
+            PAI_REQUIRE(ws[k] && grads[k] && exp_avgs[k] && exp_avg_sqs[k] && as[k] > 0 && bs[k] > 0,
+                        "pai_adam_pack_conv4x4_multi: bad entry %d", k);
+            PAI_REQUIRE(((reinterpret_cast<uintptr_t>(ws[k]) | reinterpret_cast<uintptr_t>(grads[k]) |
+                          reinterpret_cast<uintptr_t>(exp_avgs[k]) | reinterpret_cast<uintptr_t>(exp_avg_sqs[k]) |
+                          reinterpret_cast<uintptr_t>(pack1s[k]) | reinterpret_cast<uintptr_t>(pack2s[k])) & 15) == 0,
+                        "pai_adam_pack_conv4x4_multi: entry %d: pointers must be 16 B aligned", k);
+            PAI_REQUIRE(pack2s[k] == nullptr || b_pads[k] >= bs[k], "pai_adam_pack_conv4x4_multi: entry %d: b_pad %d < b %d",
+                        k, b_pads[k], bs[k]);
+            t.w[i] = ws[k], t.g[i] = grads[k], t.m[i] = exp_avgs[k], t.v[i] = exp_avg_sqs[k];
+            t.p1[i] = (__nv_bfloat16*)pack1s[k], t.p2[i] = (__nv_bfloat16*)pack2s[k];
+            t.A[i] = as[k], t.B[i] = bs[k], t.b_pad[i] = b_pads[k];
+            t.first_tile[i] = tiles;
+            tiles += ((as[k] + kTA - 1) / kTA) * ((bs[k] + kTB - 1) / kTB);
+        }
+        t.first_tile[t.count] = tiles;
+        adam_pack_multi_kernel<<<tiles, kPackThreads, smem, (cudaStream_t)stream>>>(t, hy, dyn);
+        PAI_CUDA_OK(cudaGetLastError());
+    }
     return 0;
 }
 

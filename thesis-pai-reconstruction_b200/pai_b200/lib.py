@@ -112,6 +112,8 @@ SIGNATURES = {
     "pai_col2im4x4s1": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "pai_resize_aa_normalize_u8": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "pai_ema_multi": [c_int, c_void_p, c_void_p, c_void_p, c_float, c_void_p],
+    "pai_adam_pack_conv4x4_multi": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p],
     "pai_adam_multi": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float,
                        c_float, c_void_p, c_void_p],
 }

@@ -5,7 +5,7 @@ The reference builds ``torch.optim.Adam(params, lr=2e-4, betas=(0.5, 0.999), eps
 constructor, ``state_dict`` layout (``step``, ``exp_avg``, ``exp_avg_sq`` per parameter) and arithmetic,
 but runs the whole step in a handful of launches:
 
-* every 4x4 convolution weight ``[A, B, 4, 4]`` is updated by ONE kernel that also rewrites the two bf16
+* all 4x4 convolution weights ``[A, B, 4, 4]`` are updated by ONE launch that also rewrites the two bf16
   GEMM-operand packs the implicit-GEMM kernels read (``engine`` pack cache) -- no separate repack pass;
 * all remaining tensors (biases, BatchNorm affine, thin layers) share one multi-tensor launch.
 
@@ -78,7 +78,7 @@ class FusedAdam(torch.optim.Adam):
         return st
 
     def _launch(self, items, beta1, beta2, step_size, inv_bc2, eps, dyn, stream):
-        small = []
+        small, fused = [], []
         for p, g, st in items:
             p.__dict__.pop("_pai_aux", None)            # packs the kernels below do not rewrite
             packs = engine.fused_pack_targets(p)
@@ -86,11 +86,21 @@ class FusedAdam(torch.optim.Adam):
                 p.__dict__.pop("_pai_packs", None)      # thin-layer packs are rebuilt lazily
                 small.append((p, g, st))
                 continue
-            p1, p2, b_pad = packs
-            lib.call("pai_adam_pack_conv4x4", _ptr(p), _ptr(g), _ptr(st["exp_avg"]), _ptr(st["exp_avg_sq"]),
-                     p.shape[0], p.shape[1], beta1, beta2, step_size, inv_bc2, eps, _ptr(p1), _ptr(p2),
-                     b_pad, _ptr(dyn), stream)
-            engine.restamp_packs(p)
+            fused.append((p, g, st, packs))
+        if fused:
+            n = len(fused)
+            arr, ints = ctypes.c_void_p * n, ctypes.c_int * n
+            lib.call("pai_adam_pack_conv4x4_multi", n,
+                     arr(*[p.data_ptr() for p, _, _, _ in fused]), arr(*[g.data_ptr() for _, g, _, _ in fused]),
+                     arr(*[s["exp_avg"].data_ptr() for _, _, s, _ in fused]),
+                     arr(*[s["exp_avg_sq"].data_ptr() for _, _, s, _ in fused]),
+                     ints(*[p.shape[0] for p, _, _, _ in fused]), ints(*[p.shape[1] for p, _, _, _ in fused]),
+                     arr(*[0 if k[0] is None else k[0].data_ptr() for _, _, _, k in fused]),
+                     arr(*[0 if k[1] is None else k[1].data_ptr() for _, _, _, k in fused]),
+                     ints(*[k[2] for _, _, _, k in fused]),
+                     beta1, beta2, step_size, inv_bc2, eps, _ptr(dyn), stream, kernels=(n + 23) // 24)
+            for p, _, _, _ in fused:
+                engine.restamp_packs(p)
         if small:
             n = len(small)
             arr = ctypes.c_void_p * n
