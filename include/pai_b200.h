@@ -165,6 +165,22 @@ int pai_bn_bwd_apply(const void* x, long long m, int c, int ld, const float* sca
 int pai_act_bwd(const void* x, long long m, int c, int ld, const void* g1, int ldg1, int act1, const void* g2, int ldg2,
                 int act2, float slope, float* sums2c, void* dx, int lddx, void* stream);
 int pai_colsum(const void* x, long long m, int c, int ld, float* sums2c, void* stream);
+/* Small layers (the <= 8x8 levels: m * 16 B per operand must fit 200 KB of shared memory, pai_bn_small_ok): one block
+ * per 8 channels holds its slice of ALL pixels, so the whole training-mode BatchNorm is one launch.
+ *   pai_bn_small_fwd  = pai_bn_stats + pai_bn_finalize (running statistics, scale_shift[4c]) + pai_bn_apply_act, and
+ *                       the Dropout2d scaling of models/pix2pix.py:107 on out1 when `mask` [n][c] (fp32, 0 or 1/(1-p))
+ *                       is given (pixels_per_image = h*w of the layer)
+ *   pai_bn_small_bwd  = pai_scale_channels (Dropout2d backward on g1, when `mask` is given) + pai_bn_bwd_reduce +
+ *                       pai_bn_bwd_apply; sums[2c] as in pai_bn_bwd_reduce (plain 2c floats, written not accumulated)
+ *   operands of pai_bn_small_ok: 1 for fwd, 2 (+1 with g2) for bwd */
+int pai_bn_small_ok(long long m, int c, int operands);
+int pai_bn_small_fwd(const void* x, long long m, int c, int ld, const float* gamma, const float* beta, float eps,
+                     float momentum, float* running_mean, float* running_var, float* scale_shift, void* out1, int ld1,
+                     int act1, void* out2, int ld2, int act2, float slope, const float* mask, int pixels_per_image,
+                     void* stream);
+int pai_bn_small_bwd(const void* x, long long m, int c, int ld, const float* scale_shift, const void* g1, int ldg1,
+                     int act1, const void* g2, int ldg2, int act2, float slope, const float* mask, int pixels_per_image,
+                     const float* gamma, float* sums, void* dx, int lddx, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * The four degenerate (1- or 2-channel-wide, HBM-bound) layers: enc0 Conv2d(1,64,4,2,1)

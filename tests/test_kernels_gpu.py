@@ -311,3 +311,53 @@ def test_dropout2d_layer_node_scales_whole_channels():
     g = x.grad.float().reshape(4, 64, 64).mean(1)
     assert torch.allclose(g, per_plane.round(), atol=1e-2)
     assert L.dropout2d(x, mod.eval()) is x
+
+
+@pytest.mark.parametrize("n,h,w,c,drop", [(64, 8, 8, 512, True), (8, 2, 2, 512, False), (3, 5, 7, 256, True), (64, 4, 4, 64, False)])
+def test_small_layer_batchnorm_one_launch_equals_the_separate_kernels(n, h, w, c, drop):
+    """pai_bn_small_fwd / pai_bn_small_bwd (one block per 8 channels, everything in one launch) against the chain they
+    replace: bn_stats -> bn_finalize -> bn_apply_act (-> scale_channels) and scale_channels -> bn_bwd_reduce ->
+    bn_bwd_apply.  Same arithmetic, different summation order: outputs equal to a bf16 ulp, sums to fp32 rounding."""
+    ops = _ops()
+    x = _rand((n, h, w, c), 11, 2.0) + 0.5
+    gamma = torch.rand(c, device="cuda") + 0.5
+    beta = torch.randn(c, device="cuda")
+    mask = ops.dropout2d_mask(n, c, 0.5, x.device) if drop else None
+    m = n * h * w
+    assert ops.bn_small_ok(x, 3)
+    # separate kernels
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    ss = ops.bn_finalize(ops.bn_stats(x), m, c, gamma, beta, rm, rv, training=True)
+    wide = torch.zeros(n, h, w, 2 * c, dtype=torch.bfloat16, device="cuda")
+    o1 = torch.empty_like(x)
+    ops.bn_apply_act(x, ss, o1, ops.ACT_LEAKY, wide[..., c:], ops.ACT_RELU, slope=0.2)
+    if drop:
+        ops.scale_channels(o1, mask, out=o1)
+    # one launch
+    rm2, rv2 = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    wide2 = torch.zeros_like(wide)
+    p1 = torch.empty_like(x)
+    ss2 = ops.bn_small_fwd(x, gamma, beta, rm2, rv2, p1, ops.ACT_LEAKY, wide2[..., c:], ops.ACT_RELU, slope=0.2, mask=mask)
+    assert torch.allclose(ss2, ss, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(rm2, rm, rtol=1e-5, atol=1e-6) and torch.allclose(rv2, rv, rtol=1e-5, atol=1e-6)
+    for got, want in ((p1, o1), (wide2, wide)):
+        d = (got.float() - want.float()).abs()
+        assert (d > 2.0 ** -7 * want.float().abs()).float().mean().item() < 1e-4      # at most a bf16 ulp, and rarely
+        assert d.max().item() <= 2.0 ** -6 * want.float().abs().max().item()
+    # backward: two gradients (encoder) and one gradient + dropout (decoder)
+    g1 = _rand((n, h, w, c), 12)
+    g2 = _rand((n, h, w, 2 * c), 13)[..., c:]
+    for two in (True, False):
+        ga = g1.clone()
+        if not two and drop:
+            ops.scale_channels(ga, mask, out=ga)
+        a2, t2 = (g2, ops.ACT_RELU) if two else (None, ops.ACT_NONE)
+        s_ref = ops.bn_bwd_reduce(x, ss, ga, ops.ACT_LEAKY, a2, t2, slope=0.2)
+        dx_ref = torch.empty_like(x)
+        ops.bn_bwd_apply(x, ss, ga, ops.ACT_LEAKY, a2, t2, s_ref, gamma, dx_ref, slope=0.2)
+        dx = torch.empty_like(x)
+        s_got = ops.bn_small_bwd(x, ss, g1, ops.ACT_LEAKY, a2, t2, gamma, dx, slope=0.2, mask=None if two else mask)
+        scale = s_ref.abs().max().item()
+        assert torch.allclose(s_got, s_ref, rtol=1e-3, atol=1e-4 * scale)
+        d = (dx.float() - dx_ref.float()).abs()
+        assert d.max().item() <= 2.0 ** -6 * dx_ref.float().abs().max().item() + 1e-6

@@ -335,6 +335,180 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long m, int c, int ld, c
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small layers (<= 8x8 at batch 64: a few MB, every pass over them is launch latency): BatchNorm is per channel, so ONE
+// block that owns 8 channels over ALL pixels needs no grid-wide reduction.  It keeps its [m][8] slice in shared memory
+// and does statistics -> finalize (running statistics, scale_shift) -> normalise + activation (+ Dropout2d mask) in
+// one launch instead of memset + bn_stats + bn_finalize + bn_apply_act + scale_channels; the backward twin replaces
+// scale_channels + memset + bn_bwd_reduce + bn_bwd_apply.  Same arithmetic as those kernels.
+static constexpr int kSmallThreads = 1024;      // forward: 4 pixels per thread at 8x8 x batch 64, one batch of loads
+static constexpr int kSmallBwdThreads = 512;    // backward keeps ~50 values per thread live
+
+__device__ __forceinline__ void block_sum16(float (&acc)[16], float (*red)[16], float* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        float v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        float v = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w][threadIdx.x];
+        total[threadIdx.x] = v;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kSmallThreads)
+bn_small_fwd_kernel(const __nv_bfloat16* __restrict__ x, int m, int c, int ld, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                    float* __restrict__ running_var, float* __restrict__ ss, __nv_bfloat16* __restrict__ o1, int ld1,
+                    int act1, __nv_bfloat16* __restrict__ o2, int ld2, int act2, float slope,
+                    const float* __restrict__ mask, int ppi) {
+    extern __shared__ uint4 small_vals[];
+    __shared__ float red[kSmallThreads / 32][16];
+    __shared__ float total[16], coef[16];
+    const int ch0 = blockIdx.x * 8;
+    // the 8 finishing threads fetch their per-channel parameters now: the latency hides under the statistics pass
+    float pg = 1.f, pb = 0.f, prm = 0.f, prv = 0.f;
+    if (threadIdx.x < 8) {
+        const int ch = ch0 + threadIdx.x;
+        if (gamma != nullptr) pg = gamma[ch];
+        if (beta != nullptr) pb = beta[ch];
+        if (running_mean != nullptr) prm = running_mean[ch], prv = running_var[ch];
+    }
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll 4
+    for (int pix = threadIdx.x; pix < m; pix += kSmallThreads) {
+        const uint4 r = load_raw(x + (size_t)pix * ld + ch0);
+        small_vals[pix] = r;
+        const Vec8 v = unpack8(r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            acc[i] += v.v[i];
+            acc[8 + i] = fmaf(v.v[i], v.v[i], acc[8 + i]);
+        }
+    }
+    block_sum16(acc, red, total);
+    if (threadIdx.x < 8) {
+        const int ch = ch0 + threadIdx.x;
+        const float mean = total[threadIdx.x] / (float)m;
+        const float var = fmaxf(total[8 + threadIdx.x] / (float)m - mean * mean, 0.f);
+        if (running_mean != nullptr) {
+            const float unbiased = m > 1 ? var * ((float)m / (float)(m - 1)) : var;
+            running_mean[ch] = (1.f - momentum) * prm + momentum * mean;
+            running_var[ch] = (1.f - momentum) * prv + momentum * unbiased;
+        }
+        const float invstd = rsqrtf(var + eps);
+        const float g = pg, b = pb;
+        ss[ch] = coef[threadIdx.x] = g * invstd;
+        ss[c + ch] = coef[8 + threadIdx.x] = b - mean * g * invstd;
+        ss[2 * c + ch] = mean;
+        ss[3 * c + ch] = invstd;
+    }
+    __syncthreads();
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sc[i] = coef[i], sh[i] = coef[8 + i];
+#pragma unroll 2
+    for (int pix = threadIdx.x; pix < m; pix += kSmallThreads) {
+        const Vec8 v = unpack8(small_vals[pix]);
+        Vec8 mk;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mk.v[i] = 1.f;
+        if (mask != nullptr) mk = loadf8(mask + (size_t)(pix / ppi) * c + ch0);
+        Vec8 a, b;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float z = fmaf(v.v[i], sc[i], sh[i]);
+            a.v[i] = act_fwd(z, act1, slope) * mk.v[i];
+            b.v[i] = act_fwd(z, act2, slope);
+        }
+        store8(o1 + (size_t)pix * ld1 + ch0, a);
+        if (o2 != nullptr) store8(o2 + (size_t)pix * ld2 + ch0, b);
+    }
+}
+
+// smem: x slice, g1 slice and (g2 != NULL) g2 slice, [m] uint4 each
+__global__ void __launch_bounds__(kSmallBwdThreads)
+bn_small_bwd_kernel(const __nv_bfloat16* __restrict__ x, int m, int c, int ld, const float* __restrict__ ss,
+                    const __nv_bfloat16* __restrict__ g1, int ldg1, int act1, const __nv_bfloat16* __restrict__ g2,
+                    int ldg2, int act2, float slope, const float* __restrict__ mask, int ppi,
+                    const float* __restrict__ gamma, float* __restrict__ sums, __nv_bfloat16* __restrict__ dx, int lddx) {
+    extern __shared__ uint4 small_vals[];
+    __shared__ float red[kSmallBwdThreads / 32][16];
+    __shared__ float total[16], coef[24];
+    uint4* xs = small_vals;
+    uint4* g1s = small_vals + m;
+    uint4* g2s = small_vals + 2 * m;
+    const int ch0 = blockIdx.x * 8;
+    const Vec8 sc = loadf8(ss + ch0), sh = loadf8(ss + c + ch0);
+    // dz of one pixel from the staged operands (the Dropout2d mask scales g1: d(mask * relu(z)))
+    auto dz_of = [&](int pix, const Vec8& v) {
+        const Vec8 a = unpack8(g1s[pix]);
+        Vec8 mk, b, dz;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mk.v[i] = 1.f, b.v[i] = 0.f;
+        if (mask != nullptr) mk = loadf8(mask + (size_t)(pix / ppi) * c + ch0);
+        if (g2 != nullptr) b = unpack8(g2s[pix]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float z = fmaf(v.v[i], sc.v[i], sh.v[i]);
+            // g1 * mask is rounded to bf16 like the in-place scale_channels pass this kernel replaces
+            const float ga = mask != nullptr ? __bfloat162float(__float2bfloat16_rn(a.v[i] * mk.v[i])) : a.v[i];
+            dz.v[i] = ga * act_grad(z, act1, slope);
+            if (g2 != nullptr) dz.v[i] = fmaf(b.v[i], act_grad(z, act2, slope), dz.v[i]);
+        }
+        return dz;
+    };
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+#pragma unroll 2
+    for (int pix = threadIdx.x; pix < m; pix += kSmallBwdThreads) {
+        const uint4 rx = load_raw(x + (size_t)pix * ld + ch0);
+        const uint4 ra = load_raw(g1 + (size_t)pix * ldg1 + ch0);
+        xs[pix] = rx;
+        g1s[pix] = ra;
+        if (g2 != nullptr) g2s[pix] = load_raw(g2 + (size_t)pix * ldg2 + ch0);
+        const Vec8 v = unpack8(rx);
+        const Vec8 dz = dz_of(pix, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            acc[i] += dz.v[i];
+            acc[8 + i] = fmaf(dz.v[i], v.v[i], acc[8 + i]);
+        }
+    }
+    block_sum16(acc, red, total);
+    if (threadIdx.x < 8) {
+        const int ch = ch0 + threadIdx.x;
+        const float mu = ss[2 * c + ch], is = ss[3 * c + ch];
+        const float s0 = total[threadIdx.x], s1 = is * (total[8 + threadIdx.x] - mu * s0);
+        sums[ch] = s0;
+        sums[c + ch] = s1;
+        const float g = gamma != nullptr ? gamma[ch] : 1.f;
+        const float k0 = g * is, kB = -k0 * is * (s1 / (float)m), kA = -k0 * (s0 / (float)m) - kB * mu;
+        coef[threadIdx.x] = k0, coef[8 + threadIdx.x] = kA, coef[16 + threadIdx.x] = kB;
+    }
+    __syncthreads();
+    float k0[8], kA[8], kB[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) k0[i] = coef[i], kA[i] = coef[8 + i], kB[i] = coef[16 + i];
+    for (int pix = threadIdx.x; pix < m; pix += kSmallBwdThreads) {
+        const Vec8 v = unpack8(xs[pix]);
+        const Vec8 dz = dz_of(pix, v);
+        Vec8 o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] = fmaf(k0[i], dz.v[i], fmaf(kB[i], v.v[i], kA[i]));
+        store8(dx + (size_t)pix * lddx + ch0, o);
+    }
+}
+
 template <int MODE>
 static int bn_bwd_dispatch(cudaStream_t st, const __nv_bfloat16* x, long long m, int c, int ld, const float* ss,
                            const __nv_bfloat16* g1, int ldg1, int act1, const __nv_bfloat16* g2, int ldg2, int act2,
@@ -518,6 +692,59 @@ int pai_act_bwd(const void* x, long long m, int c, int ld, const void* g1, int l
     PAI_CUDA_OK(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * c, st));
     return bn_bwd_dispatch<2>(st, (const bf16*)x, m, c, ld, nullptr, (const bf16*)g1, ldg1, act1,
                               (const bf16*)g2, ldg2, act2, slope, sums, nullptr, (bf16*)dx, lddx);
+}
+
+static const size_t kSmallSmemMax = 200 * 1024;
+
+int pai_bn_small_ok(long long m, int c, int operands) {
+    return m > 0 && c > 0 && c % 8 == 0 && operands >= 1 && operands <= 3 && (size_t)m * 16 * operands <= kSmallSmemMax;
+}
+
+int pai_bn_small_fwd(const void* x, long long m, int c, int ld, const float* gamma, const float* beta, float eps,
+                     float momentum, float* running_mean, float* running_var, float* scale_shift, void* out1, int ld1,
+                     int act1, void* out2, int ld2, int act2, float slope, const float* mask, int pixels_per_image,
+                     void* stream) {
+    PAI_REQUIRE(x && scale_shift && out1 && m > 0, "pai_bn_small_fwd: null pointer / empty input");
+    PAI_REQUIRE(pai_bn_small_ok(m, c, 1), "pai_bn_small_fwd: m=%lld c=%d does not fit one block per 8 channels", m, c);
+    PAI_REQUIRE(ew_ok(8, x, ld) && ew_ok(8, out1, ld1) && (out2 == nullptr || ew_ok(8, out2, ld2)),
+                "pai_bn_small_fwd: bad stride / alignment (c=%d)", c);
+    PAI_REQUIRE(act1 != PAI_ACT_TANH && act2 != PAI_ACT_TANH, "pai_bn_small_fwd: tanh is not a BatchNorm consumer");
+    PAI_REQUIRE(mask == nullptr || pixels_per_image > 0, "pai_bn_small_fwd: mask needs pixels_per_image");
+    static DeviceOnce once;
+    const int dev = current_device();
+    if (dev < 0) return -1;
+    if (once.need(dev)) {
+        PAI_CUDA_OK(cudaFuncSetAttribute(bn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmemMax));
+        once.mark(dev);
+    }
+    bn_small_fwd_kernel<<<c / 8, kSmallThreads, (size_t)m * 16, (cudaStream_t)stream>>>(
+        (const bf16*)x, (int)m, c, ld, gamma, beta, eps, momentum, running_mean, running_var, scale_shift, (bf16*)out1, ld1,
+        act1, (bf16*)out2, ld2, act2, slope, mask, pixels_per_image > 0 ? pixels_per_image : 1);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int pai_bn_small_bwd(const void* x, long long m, int c, int ld, const float* scale_shift, const void* g1, int ldg1,
+                     int act1, const void* g2, int ldg2, int act2, float slope, const float* mask, int pixels_per_image,
+                     const float* gamma, float* sums, void* dx, int lddx, void* stream) {
+    PAI_REQUIRE(x && scale_shift && g1 && sums && dx && m > 0, "pai_bn_small_bwd: null pointer / empty input");
+    const int operands = g2 != nullptr ? 3 : 2;
+    PAI_REQUIRE(pai_bn_small_ok(m, c, operands), "pai_bn_small_bwd: m=%lld c=%d does not fit one block per 8 channels", m, c);
+    PAI_REQUIRE(ew_ok(8, x, ld) && ew_ok(8, g1, ldg1) && (g2 == nullptr || ew_ok(8, g2, ldg2)) && ew_ok(8, dx, lddx),
+                "pai_bn_small_bwd: bad stride / alignment (c=%d)", c);
+    PAI_REQUIRE(mask == nullptr || pixels_per_image > 0, "pai_bn_small_bwd: mask needs pixels_per_image");
+    static DeviceOnce once;
+    const int dev = current_device();
+    if (dev < 0) return -1;
+    if (once.need(dev)) {
+        PAI_CUDA_OK(cudaFuncSetAttribute(bn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmemMax));
+        once.mark(dev);
+    }
+    bn_small_bwd_kernel<<<c / 8, kSmallBwdThreads, (size_t)m * 16 * operands, (cudaStream_t)stream>>>(
+        (const bf16*)x, (int)m, c, ld, scale_shift, (const bf16*)g1, ldg1, act1, (const bf16*)g2, ldg2, act2, slope, mask,
+        pixels_per_image > 0 ? pixels_per_image : 1, gamma, sums, (bf16*)dx, lddx);
+    PAI_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 int pai_colsum(const void* x, long long m, int c, int ld, float* sums2c, void* stream) {

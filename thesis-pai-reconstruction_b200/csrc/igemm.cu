@@ -74,7 +74,11 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     const int cta_n = PAIR ? n_tile / 2 : n_tile;           // weight-tile rows staged by this CTA
     const uint32_t a_bytes = 128 * 128;
     const uint32_t b_bytes = (uint32_t)cta_n * 128;
-    const uint32_t stage_bytes = a_bytes + (fused ? 4 : 1) * b_bytes;
+    // A pipeline stage holds p.ksub (1 or 2) 64-channel K blocks, each [A box | weight box(es)]: the MMA-issuing thread
+    // pays its per-stage costs (barrier wait, fence, commit, loop) once per 8 MMAs instead of once per 4
+    const int ksub = p.ksub;
+    const uint32_t sub_bytes = a_bytes + (fused ? 4 : 1) * b_bytes;
+    const uint32_t stage_bytes = (uint32_t)ksub * sub_bytes;
     const int stages = p.stages;
     const int num_kb = (fused ? 9 : p.ntaps) * p.kc_per_tap;
     const int acc_n = fused ? 4 * n_tile : n_tile;          // accumulator columns per tile
@@ -113,8 +117,8 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = ps.tmem_base;
 
-    long long prof_wait = 0, prof_wait2 = 0, prof_total = 0;
-    (void)prof_wait, (void)prof_wait2, (void)prof_total;
+    long long prof_wait = 0, prof_wait2 = 0, prof_total = 0, prof_fence = 0, prof_issue = 0, prof_commit = 0;
+    (void)prof_wait, (void)prof_wait2, (void)prof_total, (void)prof_fence, (void)prof_issue, (void)prof_commit;
     // TMA producers: warps 0, 2 and 3 deal the k-blocks round-robin.  One elected thread needs ~250 cycles per
     // cp.async.bulk.tensor (coordinate set-up, barrier wait, issue) -- measured with -DPAI_PROFILE_ROLES: a single
     // producer was busy 78 % of the kernel and the MMA thread waited on it -- while an N = 128 k-block is only 256 cycles
@@ -142,49 +146,65 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
                 const int col0 = nt * n_tile;
                 const int kb_begin = num_kb * ks / p.splitk, kb_end = num_kb * (ks + 1) / p.splitk;
-                const int g_end = g + (kb_end - kb_begin);
+                const int g_end = g + (kb_end - kb_begin) / ksub;        // stages of this tile (host: ksub | k-blocks)
                 for (; mine < g_end; mine += P) {
-                    const int kb = kb_begin + (mine - g);
-                    int tap, kc;
-                    p.fd_kc.divmod(kb, tap, kc);                // fused: tap = box index 0..8
+                    const int kb0 = kb_begin + (mine - g) * ksub;
                     {
                         ROLE_T0();
                         mbar_wait(&ps.empty[stage], phase ^ 1);
                         ROLE_ADD(prof_wait);
                     }
-                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                    uint8_t* sb = sa + a_bytes;
-                    if (fused) {
-                        int nu = 0;
-                        while (nu < 4 && p.box_users[tap][nu] >= 0) ++nu;
-                        if (PAIR) {
-                            if (rank == 0) mbar_expect_tx(&ps.full[stage], 2 * (a_bytes + nu * b_bytes));
-                            tma_load_5d_pair(sa, &tm_a, &ps.full[stage], kc * 64, w0 + p.box_w[tap], 0, h0 + p.box_h[tap], n0);
-                        } else {
-                            mbar_expect_tx(&ps.full[stage], a_bytes + nu * b_bytes);
-                            tma_load_5d(sa, &tm_a, &ps.full[stage], kc * 64, w0 + p.box_w[tap], 0, h0 + p.box_h[tap], n0);
-                        }
-                        for (int u = 0; u < nu; ++u) {
-                            const int pt = p.box_users[tap][u], ph = pt >> 2, tp = pt & 3;
+                    uint8_t* st = smem + (size_t)stage * stage_bytes;
+                    int tap, kc;
+                    p.fd_kc.divmod(kb0, tap, kc);                // fused: tap = box index 0..8 (ksub | kc_per_tap)
+                    const int nu = fused ? p.box_nu[tap] : 1;
+                    const uint32_t tx = (uint32_t)ksub * (a_bytes + nu * b_bytes);
+                    if (!PAIR || rank == 0) mbar_expect_tx(&ps.full[stage], PAIR ? 2 * tx : tx);
+                    for (int j = 0; j < ksub; ++j) {
+                        uint8_t* sa = st + (size_t)j * sub_bytes;
+                        uint8_t* sb = sa + a_bytes;
+                        const int kb = kb0 + j;
+                        if (fused) {
+                            const int kcj = kc + j;
                             if (PAIR)
-                                tma_load_2d_pair(sb + u * b_bytes, &tm_b, &ps.full[stage], (tp * p.kc_per_tap + kc) * 64,
-                                                 ph * p.b_rows_per_phase + brow);
+                                tma_load_5d_pair(sa, &tm_a, &ps.full[stage], kcj * 64, w0 + p.box_w[tap], 0, h0 + p.box_h[tap], n0);
                             else
-                                tma_load_2d(sb + u * b_bytes, &tm_b, &ps.full[stage], (tp * p.kc_per_tap + kc) * 64,
-                                            ph * p.b_rows_per_phase);
-                        }
-                    } else {
-                        const int ti = phase_idx * p.ntaps + tap;
-                        if (PAIR) {
-                            if (rank == 0) mbar_expect_tx(&ps.full[stage], 2 * stage_bytes);
-                            tma_load_5d_pair(sa, &tm_a, &ps.full[stage], p.tap_c[ti] + kc * 64, w0 + p.tap_w[ti], p.tap_p[ti],
-                                             h0 + p.tap_h[ti], n0);
-                            tma_load_2d_pair(sb, &tm_b, &ps.full[stage], kb * 64, phase_idx * p.b_rows_per_phase + col0 + brow);
+                                tma_load_5d(sa, &tm_a, &ps.full[stage], kcj * 64, w0 + p.box_w[tap], 0, h0 + p.box_h[tap], n0);
+                            if (PAIR && p.box_merge[tap]) {
+                                // one MMA of N = 64 * nu: the N dimension of a cta_group::2 tile is split [first half |
+                                // second half] between the two CTAs, so this CTA stages the WHOLE 64-row weight boxes of
+                                // its half of the users (two 32-row loads each) instead of half of every box
+                                const int per = nu >> 1;
+                                for (int v = 0; v < per; ++v) {
+                                    const int pt = p.box_users[tap][(int)rank * per + v], ph = pt >> 2, tp = pt & 3;
+                                    for (int hr = 0; hr < 2; ++hr)
+                                        tma_load_2d_pair(sb + (2 * v + hr) * b_bytes, &tm_b, &ps.full[stage],
+                                                         (tp * p.kc_per_tap + kcj) * 64, ph * p.b_rows_per_phase + hr * cta_n);
+                                }
+                            } else {
+                                for (int u = 0; u < nu; ++u) {
+                                    const int pt = p.box_users[tap][u], ph = pt >> 2, tp = pt & 3;
+                                    if (PAIR)
+                                        tma_load_2d_pair(sb + u * b_bytes, &tm_b, &ps.full[stage], (tp * p.kc_per_tap + kcj) * 64,
+                                                         ph * p.b_rows_per_phase + brow);
+                                    else
+                                        tma_load_2d(sb + u * b_bytes, &tm_b, &ps.full[stage], (tp * p.kc_per_tap + kcj) * 64,
+                                                    ph * p.b_rows_per_phase);
+                                }
+                            }
                         } else {
-                            mbar_expect_tx(&ps.full[stage], stage_bytes);
-                            tma_load_5d(sa, &tm_a, &ps.full[stage], p.tap_c[ti] + kc * 64, w0 + p.tap_w[ti], p.tap_p[ti],
-                                        h0 + p.tap_h[ti], n0);
-                            tma_load_2d(sb, &tm_b, &ps.full[stage], kb * 64, phase_idx * p.b_rows_per_phase + col0);
+                            int tapj, kcj;
+                            p.fd_kc.divmod(kb, tapj, kcj);
+                            const int ti = phase_idx * p.ntaps + tapj;
+                            if (PAIR) {
+                                tma_load_5d_pair(sa, &tm_a, &ps.full[stage], p.tap_c[ti] + kcj * 64, w0 + p.tap_w[ti], p.tap_p[ti],
+                                                 h0 + p.tap_h[ti], n0);
+                                tma_load_2d_pair(sb, &tm_b, &ps.full[stage], kb * 64, phase_idx * p.b_rows_per_phase + col0 + brow);
+                            } else {
+                                tma_load_5d(sa, &tm_a, &ps.full[stage], p.tap_c[ti] + kcj * 64, w0 + p.tap_w[ti], p.tap_p[ti],
+                                            h0 + p.tap_h[ti], n0);
+                                tma_load_2d(sb, &tm_b, &ps.full[stage], kb * 64, phase_idx * p.b_rows_per_phase + col0);
+                            }
                         }
                     }
                     stage += P;
@@ -197,8 +217,22 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 #endif
         }
     } else if (warp == 1) {
-        if (rank == 0 && elect_one()) {
+        if (rank == 0) {
+            // MMA issuer.  The WHOLE warp walks the loops -- warp-uniform control flow lets the compiler keep the stage
+            // counter, barrier addresses and descriptor words in uniform registers -- and one elected lane issues.  The
+            // issuing thread is the critical path of every N <= 128 layer (a lone warp pays the full latency of each
+            // dependent instruction: -DPAI_PROFILE_ROLES showed ~290 cycles per stage outside the MMAs against 256
+            // cycles of tensor work, and 700 per stage in the phase-fused mode), so everything that does not depend on
+            // the stage is computed once per tile or per box and the per-stage work is: wait, fence, two 32-bit
+            // descriptor words, the MMAs, the commit.
             const uint32_t idesc = umma_idesc_bf16(PAIR ? 256 : 128, n_tile, 0, 0);
+            const uint32_t idesc_n2 = umma_idesc_bf16(PAIR ? 256 : 128, fused ? 2 * n_tile : n_tile, 0, 0);
+            const uint32_t idesc_n4 = umma_idesc_bf16(PAIR ? 256 : 128, fused ? 4 * n_tile : n_tile, 0, 0);
+            const uint32_t full0 = smem_u32(&ps.full[0]), empty0 = smem_u32(&ps.empty[0]);
+            const uint32_t acc_full0 = smem_u32(&ps.acc_full[0]), acc_empty0 = smem_u32(&ps.acc_empty[0]);
+            const uint32_t a_lo0 = umma_desc_lo_kmajor(smem_u32(smem));
+            const uint32_t stage_units = stage_bytes >> 4, sub_units = sub_bytes >> 4, a_units = a_bytes >> 4, b_units = b_bytes >> 4;
+            const int kmma = p.kmma, kc_per_tap = p.kc_per_tap, splitk = p.splitk;
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -210,75 +244,98 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 const uint32_t acc_phase = (it >> 1) & 1;
                 {
                     ROLE_T0();
-                    mbar_wait(&ps.acc_empty[a], acc_phase ^ 1);   // epilogue has drained this accumulator
+                    mbar_wait_u32(acc_empty0 + 8 * a, acc_phase ^ 1);   // epilogue has drained this accumulator
                     ROLE_ADD(prof_wait2);
                 }
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + a * acc_cols;
-                const int ks = t - p.fd_splitk.quot(t) * p.splitk;
-                const int kb_begin = num_kb * ks / p.splitk, kb_end = num_kb * (ks + 1) / p.splitk;
-                uint32_t started = 0;      // fused: phases whose accumulator already holds a partial sum
-                for (int kb = kb_begin; kb < kb_end; ++kb) {
-                    {
-                        ROLE_T0();
-                        mbar_wait(&ps.full[stage], phase);
-                        ROLE_ADD(prof_wait);
-                    }
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t sb = sa + a_bytes;
-                    // descriptors: the 14-bit start-address field counts 16-byte units, so stepping K by 16
-                    // elements (32 B) or moving to the next B tile is a plain add on the base descriptor (the
-                    // single issuing thread is the bottleneck of the narrow-N layers: keep its chain short)
-                    const uint64_t da0 = umma_desc_kmajor_sw128(sa), db0 = umma_desc_kmajor_sw128(sb);
-                    if (fused) {
-                        const int box = kb / p.kc_per_tap;
-                        for (int u = 0; u < 4 && p.box_users[box][u] >= 0; ++u) {
-                            const int ph = p.box_users[box][u] >> 2;
-                            const uint64_t dbu = db0 + (uint64_t)u * (b_bytes >> 4);
-                            const uint32_t td = tmem_d + ph * n_tile;
-                            if (PAIR) {
-                                umma_bf16_ss_pair(td, da0, dbu, idesc, (started >> ph) & 1);
-                                umma_bf16_acc_pair(td, da0 + 2, dbu + 2, idesc);
-                                umma_bf16_acc_pair(td, da0 + 4, dbu + 4, idesc);
-                                umma_bf16_acc_pair(td, da0 + 6, dbu + 6, idesc);
-                            } else {
-                                umma_bf16_ss(td, da0, dbu, idesc, (started >> ph) & 1);
-                                umma_bf16_acc(td, da0 + 2, dbu + 2, idesc);
-                                umma_bf16_acc(td, da0 + 4, dbu + 4, idesc);
-                                umma_bf16_acc(td, da0 + 6, dbu + 6, idesc);
+                if (fused) {
+                    // 9 boxes x kc_per_tap channel blocks, box-major (the producers' order); the centre box comes first
+                    // and starts all four accumulators, so everything after its first channel block accumulates
+                    for (int box = 0; box < 9; ++box) {
+                        const int nu = p.box_nu[box];
+                        const bool merged = p.box_merge[box] != 0;
+                        const int groups = merged ? 1 : nu;
+                        const uint32_t idesc_u = merged ? (nu == 2 ? idesc_n2 : idesc_n4) : idesc;
+                        const uint32_t td0 = tmem_d + p.box_col[box][0] * n_tile, td1 = tmem_d + p.box_col[box][1] * n_tile;
+                        const uint32_t td2 = tmem_d + p.box_col[box][2] * n_tile, td3 = tmem_d + p.box_col[box][3] * n_tile;
+                        for (int kc = 0; kc < kc_per_tap; kc += ksub) {
+                            {
+                                ROLE_T0();
+                                mbar_wait_u32(full0 + 8 * stage, phase);
+                                ROLE_ADD(prof_wait);
                             }
-                            started |= 1u << ph;
+                            tc_fence_after();
+                            if (elect_one()) {
+                                for (int j = 0; j < ksub; ++j) {
+                                    const uint32_t a_lo = a_lo0 + stage * stage_units + j * sub_units, b_lo = a_lo + a_units;
+                                    const uint32_t acc = (box | kc | j) != 0;
+                                    umma_kblock_lo<PAIR, 4>(td0, a_lo, b_lo, idesc_u, acc);
+                                    if (groups > 1) umma_kblock_lo<PAIR, 4>(td1, a_lo, b_lo + b_units, idesc_u, acc);
+                                    if (groups > 2) {      // only with PAI_NO_PHASE_MERGE: the centre box as 4 N = 64 MMAs
+                                        umma_kblock_lo<PAIR, 4>(td2, a_lo, b_lo + 2 * b_units, idesc_u, acc);
+                                        umma_kblock_lo<PAIR, 4>(td3, a_lo, b_lo + 3 * b_units, idesc_u, acc);
+                                    }
+                                }
+                                umma_commit_u32<PAIR>(empty0 + 8 * stage);     // frees the stage (in both CTAs)
+                            }
+                            if (++stage == stages) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
                         }
-                    } else if (PAIR) {
-                        umma_bf16_ss_pair(tmem_d, da0, db0, idesc, kb != kb_begin);
-                        if (p.kmma > 1) umma_bf16_acc_pair(tmem_d, da0 + 2, db0 + 2, idesc);
-                        if (p.kmma > 2) umma_bf16_acc_pair(tmem_d, da0 + 4, db0 + 4, idesc);
-                        if (p.kmma > 3) umma_bf16_acc_pair(tmem_d, da0 + 6, db0 + 6, idesc);
-                    } else {
-                        umma_bf16_ss(tmem_d, da0, db0, idesc, kb != kb_begin);
-                        if (p.kmma > 1) umma_bf16_acc(tmem_d, da0 + 2, db0 + 2, idesc);
-                        if (p.kmma > 2) umma_bf16_acc(tmem_d, da0 + 4, db0 + 4, idesc);
-                        if (p.kmma > 3) umma_bf16_acc(tmem_d, da0 + 6, db0 + 6, idesc);
                     }
-                    if (PAIR)
-                        umma_commit_pair(&ps.empty[stage]);     // frees the stage in both CTAs
-                    else
-                        umma_commit(&ps.empty[stage]);
-                    if (++stage == stages) {
-                        stage = 0;
-                        phase ^= 1;
+                } else {
+                    const int ks = t - p.fd_splitk.quot(t) * splitk;
+                    const int kb_begin = num_kb * ks / splitk, kb_end = num_kb * (ks + 1) / splitk;
+                    if (kmma == 4) {
+                        for (int kb = kb_begin; kb < kb_end; kb += ksub) {
+                            {
+                                ROLE_T0();
+                                mbar_wait_u32(full0 + 8 * stage, phase);
+                                ROLE_ADD(prof_wait);
+                            }
+                            tc_fence_after();
+                            const uint32_t a_lo = a_lo0 + stage * stage_units, b_lo = a_lo + a_units;
+                            if (elect_one()) {
+                                umma_kblock_lo<PAIR, 4>(tmem_d, a_lo, b_lo, idesc, kb != kb_begin);
+                                if (ksub > 1) umma_kblock_lo<PAIR, 4>(tmem_d, a_lo + sub_units, b_lo + sub_units, idesc, 1u);
+                                umma_commit_u32<PAIR>(empty0 + 8 * stage);
+                            }
+                            if (++stage == stages) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
+                    } else {
+                        // thin im2col operands: one K block of which only the first 16 * kmma columns hold data (ksub == 1)
+                        for (int kb = kb_begin; kb < kb_end; ++kb) {
+                            mbar_wait_u32(full0 + 8 * stage, phase);
+                            tc_fence_after();
+                            const uint32_t a_lo = a_lo0 + stage * stage_units, b_lo = a_lo + a_units;
+                            if (elect_one()) {
+                                const uint32_t acc = kb != kb_begin;
+                                if (kmma == 1)
+                                    umma_kblock_lo<PAIR, 1>(tmem_d, a_lo, b_lo, idesc, acc);
+                                else if (kmma == 2)
+                                    umma_kblock_lo<PAIR, 2>(tmem_d, a_lo, b_lo, idesc, acc);
+                                else
+                                    umma_kblock_lo<PAIR, 3>(tmem_d, a_lo, b_lo, idesc, acc);
+                                umma_commit_u32<PAIR>(empty0 + 8 * stage);
+                            }
+                            if (++stage == stages) {
+                                stage = 0;
+                                phase ^= 1;
+                            }
+                        }
                     }
                 }
-                if (PAIR)
-                    umma_commit_pair(&ps.acc_full[a]);          // both epilogues
-                else
-                    umma_commit(&ps.acc_full[a]);
+                if (elect_one()) umma_commit_u32<PAIR>(acc_full0 + 8 * a);      // the epilogue(s) may read the tile
             }
 #ifdef PAI_PROFILE_ROLES
-            if (blockIdx.x == 0)
-                printf("[roles] mma: total %lld cyc, waiting for full stages %lld, for a drained accumulator %lld, tiles %d, k-blocks/tile %d\n",
-                       clock64() - tstart, prof_wait, prof_wait2, it, num_kb / p.splitk);
+            if (blockIdx.x == 0 && elect_one())
+                printf("[roles] mma: total %lld cyc, waiting for full stages %lld, for a drained accumulator %lld, tiles %d, k-blocks/tile %d; unfused: fence %lld issue %lld commit %lld\n",
+                       clock64() - tstart, prof_wait, prof_wait2, it, num_kb / p.splitk, prof_fence, prof_issue, prof_commit);
 #endif
         }
     } else if (warp >= 4) {
@@ -690,10 +747,20 @@ bool igemm_fprop_use_pair(int n_tile, long long m_tiles, int n_tiles, int phases
 int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFpropParams p, int m_tiles,
                        int n_tiles, int phases, cudaStream_t stream) {
     const bool pair = p.pair != 0;
-    const size_t stage_bytes = 128 * 128 + (size_t)(p.fused_phases ? 4 : 1) * (pair ? p.n_tile / 2 : p.n_tile) * 128;
+    const size_t sub_bytes = 128 * 128 + (size_t)(p.fused_phases ? 4 : 1) * (pair ? p.n_tile / 2 : p.n_tile) * 128;
+    if (p.kmma <= 0 || p.kmma > 4) p.kmma = 4;
+    if (p.splitk < 1) p.splitk = 1;
+    // two K blocks per pipeline stage when every tile (and split-K slice) has an even number of them and at least three
+    // such stages fit: halves the per-stage work of the MMA-issuing thread.  PAI_IGEMM_KSUB=1 forces single blocks.
+    {
+        static const char* env = getenv("PAI_IGEMM_KSUB");
+        const int num_kb = (p.fused_phases ? 9 : p.ntaps) * p.kc_per_tap;
+        const bool even = p.fused_phases ? p.kc_per_tap % 2 == 0 : num_kb % (2 * p.splitk) == 0;
+        p.ksub = (even && p.kmma == 4 && 3 * 2 * sub_bytes <= 192 * 1024 && !(env && env[0] == '1')) ? 2 : 1;
+    }
+    const size_t stage_bytes = sub_bytes * p.ksub;
     p.stages = pick_stages(stage_bytes, 192 * 1024);
     p.m_tiles = pair ? (m_tiles + 1) / 2 : m_tiles, p.n_tiles = n_tiles, p.phases = phases;
-    if (p.kmma <= 0 || p.kmma > 4) p.kmma = 4;
     const size_t smem = stage_bytes * p.stages + 1024;
     static DeviceOnce once;
     const int dev = current_device(), num_sms = persistent_ctas(dev);

@@ -331,17 +331,34 @@ static int convT4x4s2_fprop_impl(const void* x, int n, int h, int w, int cin, in
         for (int px = 0; px < 2; ++px) p.out_phase_off[py * 2 + px] = (py * wo + px) * ld;
     if (fuse) {
         p.fused_phases = 1;
-        for (int bx = 0; bx < 9; ++bx) {
+        static const int col_of_phase[4] = {0, 1, 3, 2};      // 3 of the 4 two-phase boxes get adjacent column blocks
+        static const int box_order[9] = {4, 0, 1, 2, 3, 5, 6, 7, 8};   // centre (dy = dx = 0) first
+        const bool merge_ok = getenv("PAI_NO_PHASE_MERGE") == nullptr;
+        for (int bi = 0; bi < 9; ++bi) {
+            const int bx = box_order[bi];
             const int dy = bx / 3 - 1, dx = bx % 3 - 1;
-            p.box_h[bx] = dy, p.box_w[bx] = dx;
+            p.box_h[bi] = dy, p.box_w[bi] = dx;
             int nu = 0;
-            for (int py = 0; py < 2; ++py)
-                for (int ty = 0; ty < 2; ++ty)
-                    for (int px = 0; px < 2; ++px)
+            for (int col = 0; col < 4; ++col)            // users in column order
+                for (int ph = 0; ph < 4; ++ph) {
+                    if (col_of_phase[ph] != col) continue;
+                    const int py = ph >> 1, px = ph & 1;
+                    for (int ty = 0; ty < 2; ++ty)
                         for (int tx = 0; tx < 2; ++tx)
-                            if (kTd[py][ty] == dy && kTd[px][tx] == dx) p.box_users[bx][nu++] = (py * 2 + px) * 4 + ty * 2 + tx;
-            for (; nu < 4; ++nu) p.box_users[bx][nu] = -1;
+                            if (kTd[py][ty] == dy && kTd[px][tx] == dx) {
+                                p.box_users[bi][nu] = ph * 4 + ty * 2 + tx;
+                                p.box_col[bi][nu] = col;
+                                ++nu;
+                            }
+                }
+            p.box_nu[bi] = nu;
+            bool consecutive = nu > 1;
+            for (int u = 1; u < nu; ++u) consecutive = consecutive && p.box_col[bi][u] == p.box_col[bi][u - 1] + 1;
+            p.box_merge[bi] = merge_ok && consecutive;
+            for (; nu < 4; ++nu) p.box_users[bi][nu] = -1, p.box_col[bi][nu] = 0;
         }
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) p.out_phase_off[col_of_phase[py * 2 + px]] = (py * wo + px) * ld;
         p.bias = bias, p.act = act, p.slope = slope, p.out_f32 = 0, p.out = y;
         return launch_igemm_fprop(tm_a, tm_b, p, m_tiles, 1, 1, (cudaStream_t)stream);
     }

@@ -249,6 +249,85 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
         : "memory");
 }
 
+// ---- lean forms for the MMA-issuing warp (igemm fprop).  Measured with -DPAI_PROFILE_ROLES: the issuing thread spent
+// ~290 cycles per pipeline stage outside the MMAs (64-bit descriptor arithmetic, generic->shared conversions, register ->
+// uniform-register moves), more than the 256 cycles of tensor work of an N = 128 stage.  Here barriers are addressed by
+// their 32-bit shared address and descriptors by their LOW word only: the high word of every K-major SWIZZLE_128B
+// descriptor is the constant kDescHiSw128 (SBO 1024 B, version 1, SWIZZLE_128B), and stepping K by 16 elements or moving
+// to another tile never carries out of the 14-bit address field of the low word.
+static constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo_kmajor(uint32_t saddr) { return ((saddr & 0x3FFFF) >> 4) | (1u << 16); }
+
+__device__ __forceinline__ bool mbar_try_wait_u32(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_u32(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait_u32(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("pai: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+                   threadIdx.x);
+            __trap();
+        }
+    }
+}
+// KSTEPS MMAs over one 64-wide K block (16 elements = 2 descriptor units per step); `accumulate` applies to the first.
+template <bool PAIR, int KSTEPS>
+__device__ __forceinline__ void umma_kblock_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                               uint32_t accumulate) {
+#pragma unroll
+    for (int k = 0; k < KSTEPS; ++k) {
+#ifdef PAI_EXP_FEWER_MMA   // timing experiment only (wrong results): 1 of 4 k-steps, to tell issue-bound from tensor-bound
+        if (k > 0) break;
+#endif
+        if (PAIR)
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                ".reg .b64 da, db;\n"
+                "setp.ne.b32 p, %4, 0;\n"
+                "mov.b64 da, {%1, %5};\n"
+                "mov.b64 db, {%2, %5};\n"
+                "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n"
+                "}\n" ::"r"(tmem_d),
+                "r"(a_lo + 2 * k), "r"(b_lo + 2 * k), "r"(idesc), "r"(k == 0 ? accumulate : 1u), "r"(kDescHiSw128)
+                : "memory");
+        else
+            asm volatile(
+                "{\n"
+                ".reg .pred p;\n"
+                ".reg .b64 da, db;\n"
+                "setp.ne.b32 p, %4, 0;\n"
+                "mov.b64 da, {%1, %5};\n"
+                "mov.b64 db, {%2, %5};\n"
+                "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+                "}\n" ::"r"(tmem_d),
+                "r"(a_lo + 2 * k), "r"(b_lo + 2 * k), "r"(idesc), "r"(k == 0 ? accumulate : 1u), "r"(kDescHiSw128)
+                : "memory");
+    }
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_commit_u32(uint32_t bar) {
+    if (PAIR)
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+            "h"((uint16_t)3)
+            : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 // Shared-memory matrix descriptors for SWIZZLE_128B tiles whose rows are 128 B (64 bf16) wide and
 // whose 8-row groups are 1024 B apart (exactly what a TMA box with a 64-element inner dimension
 // writes).  K-major: rows are M/N, the 128 B row holds 64 K-values.  MN-major: rows are K, the

@@ -38,6 +38,7 @@ struct IgemmFpropParams {
     int cout;                  // valid output channels
     int kc_per_tap, ntaps;     // 64-channel K blocks per tap, taps per phase
     int stages;
+    int ksub;                  // 64-channel K blocks per pipeline stage (1 or 2), chosen by launch_igemm_fprop
     int m_tiles, n_tiles, phases;  // tile grid walked by the persistent CTAs
     int tap_c[16], tap_w[16], tap_p[16], tap_h[16];  // per (phase * ntaps + tap): A-box coordinate offsets
     int b_rows_per_phase;      // rows of the packed weight matrix per phase (cout_pad)
@@ -58,7 +59,12 @@ struct IgemmFpropParams {
     // feeds the 1, 2 or 4 (phase, tap) MMAs that read it (instead of 16 separate box loads)
     int fused_phases;
     int box_w[9], box_h[9];            // box coordinate offsets
-    int box_users[9][4];               // phase * 4 + tap of every MMA fed by the box, -1 terminated
+    int box_users[9][4];               // phase * 4 + tap of every MMA fed by the box, -1 terminated, in column order
+    // The accumulator of phase ph sits in TMEM column block box_col = {0, 1, 3, 2}[ph] (out_phase_off is indexed by
+    // column block).  A box whose users occupy CONSECUTIVE column blocks feeds ONE MMA of N = 64 * users (box_merge):
+    // an N = 64 SS-mode MMA reads 6 KB of operands for 32 clocks of tensor work -- more than shared memory delivers --
+    // while N = 256 reads 12 KB for 128 clocks.  The centre box (all 4 phases) comes first, so every later MMA accumulates.
+    int box_nu[9], box_col[9][4], box_merge[9];
     int kmma;                  // MMA k-steps (16 channels each) issued per 64-channel K block: 4, or fewer when only the
                                // first 16 * kmma columns of the (single) K block hold data (thin im2col operands)
     // BatchNorm statistics from the epilogue (coalesced bf16 path only): every CTA adds the per-channel sum and sum of

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from pai_b200 import dp, engine, lib, metrics
+from pai_b200 import dp, engine, lib, metrics, ops
 from pai_b200.optim import FusedAdam
 
 from ._lightning import LightningModule
@@ -113,6 +113,10 @@ class UnetWrapper(LightningModule):
             self.log(name, value, prog_bar=True)
 
     def _training_step_eager(self, batch, batch_idx):
+        with ops.zero_pool(batch[0].device):        # one fill for the step's small zeroed temporaries
+            return self._training_step_body(batch, batch_idx)
+
+    def _training_step_body(self, batch, batch_idx):
         x, target = batch
         if self.loss_type == "gan":
             opt_d = self.optimizers()[1]

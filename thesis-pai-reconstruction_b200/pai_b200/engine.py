@@ -218,6 +218,26 @@ def _batchnorm(raw, bn: BNState, training: bool, counters=None, partials=None):
     return ss
 
 
+def _batchnorm_act(raw, bn: BNState, training, counters, partials, out1, act1, out2=None, act2=ACT_NONE, mask=None):
+    """BatchNorm + activation(s) of ``raw`` into ``out1`` (and ``out2``); ``mask`` = Dropout2d scaling of ``out1``.
+    Small layers in training mode take ONE launch (``ops.bn_small_fwd``); the rest is statistics (or the partial sums of
+    the GEMM epilogue) -> ``bn_finalize`` -> ``bn_apply_act`` (-> ``scale_channels``).  -> scale_shift."""
+    if training and partials is None and ops.bn_small_ok(raw):
+        ss = ops.bn_small_fwd(raw, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, out1, act1, out2,
+                              act2, slope=SLOPE, mask=mask, eps=BN_EPS, momentum=BN_MOMENTUM)
+        bn.mod.__dict__["_pai_stat_version"] = bn.mod.__dict__.get("_pai_stat_version", 0) + 1
+        if counters is None:
+            bn.num_batches_tracked.add_(1)
+        else:
+            counters.append(bn.num_batches_tracked)
+        return ss
+    ss = _batchnorm(raw, bn, training, counters, partials)
+    ops.bn_apply_act(raw, ss, out1, act1, out2, act2, slope=SLOPE)
+    if mask is not None:
+        ops.scale_channels(out1, mask, out=out1)
+    return ss
+
+
 # ------------------------------------------------------------------------------------------ fp32 check path
 _check = False
 
@@ -431,12 +451,13 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
                 raw, part = ops.conv4x4_fprop_bnstats(a_in[i], _fprop_pack(conv.weight), ch[i], bias=conv.bias.detach())
             else:
                 raw = ops.conv4x4_fprop(a_in[i], _fprop_pack(conv.weight), ch[i], stride=2, bias=conv.bias.detach())
+            a_in[i + 1] = _bf16(n, hs[i], ws[i], ch[i], device=dev)
             if bn is not None:
-                ss = _batchnorm(raw, bn, training, counters, part)
+                ss = _batchnorm_act(raw, bn, training, counters, part, a_in[i + 1], ACT_LEAKY, cat[L - 1 - i][..., ch[i]:],
+                                    ACT_RELU)
             else:
                 ss = None
-            a_in[i + 1] = _bf16(n, hs[i], ws[i], ch[i], device=dev)
-            ops.bn_apply_act(raw, ss, a_in[i + 1], ACT_LEAKY, cat[L - 1 - i][..., ch[i]:], ACT_RELU, slope=SLOPE)
+                ops.bn_apply_act(raw, None, a_in[i + 1], ACT_LEAKY, cat[L - 1 - i][..., ch[i]:], ACT_RELU, slope=SLOPE)
             raw_e[i], ss_e[i] = raw, ss
         else:
             # bottleneck: Identity norm (models/pix2pix.py:157), only consumer is decoder 0's ReLU
@@ -460,14 +481,13 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
             raw, part = ops.convT4x4s2_fprop_bnstats(d_in, _fpropT_pack(conv.weight), co, bias=conv.bias.detach())
         else:
             raw = ops.convT4x4s2_fprop(d_in, _fpropT_pack(conv.weight), co, bias=conv.bias.detach())
-        ss = _batchnorm(raw, bn, training, counters, part)
         slot = cat[j + 1][..., :co]
-        ops.bn_apply_act(raw, ss, slot, ACT_RELU if j + 1 < L - 1 else ACT_NONE)
         if training and spec.dec_dropout[j] > 0:
             # Dropout2d sits between the BatchNorm and the next block's ReLU; the mask is non-negative, so it commutes
             # with the ReLU already applied: relu(mask * z) == mask * relu(z)
             drop_masks[j] = ops.dropout2d_mask(n, co, spec.dec_dropout[j], dev)
-            ops.scale_channels(slot, drop_masks[j], out=slot)
+        ss = _batchnorm_act(raw, bn, training, counters, part, slot, ACT_RELU if j + 1 < L - 1 else ACT_NONE,
+                            mask=drop_masks[j])
         raw_d[j], ss_d[j] = raw, ss
         d_in = cat[j + 1]
     last = spec.dec_convs[L - 1]
@@ -522,18 +542,23 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
         enc_i = L - 2 - j                       # encoder whose skip sits in cat[j+1]
         dskip[enc_i] = dcat[..., co:]
         g1 = dcat[..., :co]
-        if s.drop_masks[j] is not None:
-            ops.scale_channels(g1, s.drop_masks[j], out=g1)          # Dropout2d backward, in place on the fresh dgrad
         raw, ss = s.raw_d[j], s.ss_d[j]
         act_out = ACT_RELU if j + 1 < L - 1 else ACT_NONE     # consumer of this decoder's output
-        sums = ops.bn_bwd_reduce(raw, ss, g1, act_out)
         d_raw = _bf16(*raw.shape, device=dev)
-        ops.bn_bwd_apply(raw, ss, g1, act_out, None, ACT_NONE, sums, bn.weight.detach(), d_raw)
+        if ops.bn_small_ok(raw, 2):
+            # Dropout2d backward + BatchNorm backward (reduce + apply) in one launch
+            sums = ops.bn_small_bwd(raw, ss, g1, act_out, None, ACT_NONE, bn.weight.detach(), d_raw, slope=SLOPE,
+                                    mask=s.drop_masks[j])
+        else:
+            if s.drop_masks[j] is not None:
+                ops.scale_channels(g1, s.drop_masks[j], out=g1)      # Dropout2d backward, in place on the fresh dgrad
+            sums = ops.bn_bwd_reduce(raw, ss, g1, act_out)
+            ops.bn_bwd_apply(raw, ss, g1, act_out, None, ACT_NONE, sums, bn.weight.detach(), d_raw)
         d_in = s.cat[j] if j > 0 else s.dec_in0
         cin = conv.weight.shape[0]
         gw = ops.wgrad_finish(ops.convT4x4s2_wgrad(d_in, d_raw))   # [cin, co, 4, 4]
         dp.allreduce_async(gw)                    # data-parallel: the exchange overlaps the rest of the backward
-        grads[(1, j)] = (gw, torch.zeros(co, device=dev), sums[co:], sums[:co])
+        grads[(1, j)] = (gw, ops.zeros_f32(co, device=dev), sums[co:], sums[:co])
         dcat = ops.conv4x4_fprop(d_raw, _dgradT_pack(conv.weight), cin, stride=2)   # grad w.r.t. decoder input
     # ---- bottleneck encoder L-1: dec_in0 = relu(conv + bias)
     i = L - 1
@@ -548,14 +573,17 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
     for i in range(L - 2, 0, -1):
         conv, bn = spec.enc_convs[i], spec.enc_bns[i]
         raw, ss = s.raw_e[i], s.ss_e[i]
-        sums = ops.bn_bwd_reduce(raw, ss, d_a, ACT_LEAKY, dskip[i], ACT_RELU, slope=SLOPE)
         d_raw = _bf16(*raw.shape, device=dev)
-        ops.bn_bwd_apply(raw, ss, d_a, ACT_LEAKY, dskip[i], ACT_RELU, sums, None if bn is None else bn.weight.detach(),
-                         d_raw, slope=SLOPE)
+        if bn is not None and ops.bn_small_ok(raw, 3):
+            sums = ops.bn_small_bwd(raw, ss, d_a, ACT_LEAKY, dskip[i], ACT_RELU, bn.weight.detach(), d_raw, slope=SLOPE)
+        else:
+            sums = ops.bn_bwd_reduce(raw, ss, d_a, ACT_LEAKY, dskip[i], ACT_RELU, slope=SLOPE)
+            ops.bn_bwd_apply(raw, ss, d_a, ACT_LEAKY, dskip[i], ACT_RELU, sums, None if bn is None else bn.weight.detach(),
+                             d_raw, slope=SLOPE)
         gw = ops.wgrad_finish(ops.conv4x4_wgrad(s.a_in[i], d_raw, stride=2))
         dp.allreduce_async(gw)
         if bn is not None:
-            grads[(0, i)] = (gw, torch.zeros(ch[i], device=dev), sums[ch[i]:], sums[:ch[i]])
+            grads[(0, i)] = (gw, ops.zeros_f32(ch[i], device=dev), sums[ch[i]:], sums[:ch[i]])
         else:
             grads[(0, i)] = (gw, sums[:ch[i]].clone())
         d_a = ops.convT4x4s2_fprop(d_raw, _dgrad_pack(conv.weight), ch[i - 1])

@@ -42,6 +42,10 @@ SIGNATURES = {
     "pai_act_bwd": [c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p,
                     c_void_p, c_int, c_void_p],
     "pai_colsum": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p],
+    "pai_bn_small_fwd": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                         c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p, c_int, c_void_p],
+    "pai_bn_small_bwd": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float,
+                         c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p],
     "pai_smallc_conv_fprop": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                               c_void_p, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_float, c_void_p],
     "pai_smallc_conv_wgrad": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
@@ -117,7 +121,8 @@ SIGNATURES = {
     "pai_adam_multi": [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float,
                        c_float, c_void_p, c_void_p],
 }
-RESTYPES = {"pai_ssim_bwd_workspace_bytes": (ctypes.c_longlong, [c_int, c_int, c_int])}
+RESTYPES = {"pai_ssim_bwd_workspace_bytes": (ctypes.c_longlong, [c_int, c_int, c_int]),
+            "pai_bn_small_ok": (c_int, [c_ll, c_int, c_int])}
 
 _lib = None
 launches = 0  # number of kernels this process asked the library to launch (bench.py reports it)

@@ -7,12 +7,14 @@ are required).  PyTorch owns every buffer; the library only enqueues kernels on 
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
 from . import lib
 
 ACT_NONE, ACT_LEAKY, ACT_RELU, ACT_TANH = 0, 1, 2, 3
+BN_SMALL_OFF = os.environ.get("PAI_NO_BN_SMALL", "0") == "1"
 # ConvTranspose2d(4,2,1) sub-pixel phases: T[parity] = ((k, d), (k, d))
 _T_K = ((1, 3), (0, 2))
 
@@ -100,6 +102,71 @@ def pack_convT_weight(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# ------------------------------------------------------------------------------------------ zeroed temporaries
+class _ZeroPool:
+    """One fill per training step for the SMALL zero-initialised fp32 temporaries (split-K workspaces, BatchNorm partial
+    sums, zero bias gradients): ~50 of the step's 88 fill kernels were 2 us launches of a few KB each.  While a pool is
+    open, ``zeros_f32`` hands out slices of one buffer sized by the previous step's demand; whatever does not fit falls
+    back to ``torch.zeros``.  The buffer is a fresh allocation per step (views keep it alive; nothing is recycled under
+    a live tensor), also under CUDA-graph capture.  The weight-gradient accumulators are NOT pooled: their fill right in
+    front of the wgrad kernel leaves the lines in L2 for its reductions."""
+    MAX_ELEMS = 4 << 20                      # larger requests keep their own fill
+
+    def __init__(self):
+        self.capacity = 0
+        self.buf = None
+        self.cursor = 0
+        self.demand = 0
+        self.depth = 0
+
+
+_zero_pools = {}
+
+
+class zero_pool:
+    """``with ops.zero_pool(device):`` around one training step (models/wrapper.py)."""
+
+    def __init__(self, device):
+        on = device.type == "cuda" and os.environ.get("PAI_NO_ZERO_POOL", "0") != "1"
+        self.pool = _zero_pools.setdefault((device.type, device.index), _ZeroPool()) if on else None
+        self.device = device
+
+    def __enter__(self):
+        pl = self.pool
+        if pl is None:
+            return self
+        pl.depth += 1
+        if pl.depth == 1:
+            pl.cursor = pl.demand = 0
+            pl.buf = torch.zeros(pl.capacity, dtype=torch.float32, device=self.device) if pl.capacity else None
+        return self
+
+    def __exit__(self, *exc):
+        pl = self.pool
+        if pl is None:
+            return False
+        pl.depth -= 1
+        if pl.depth == 0:
+            pl.capacity, pl.buf = pl.demand, None
+        return False
+
+
+def zeros_f32(*shape, device) -> torch.Tensor:
+    pl = _zero_pools.get((device.type, device.index))
+    n = 1
+    for d in shape:
+        n *= int(d)
+    if pl is None or pl.depth == 0 or n > _ZeroPool.MAX_ELEMS or n == 0:
+        return torch.zeros(*shape, dtype=torch.float32, device=device)
+    padded = (n + 63) & ~63                  # 256-byte slices
+    pl.demand += padded
+    if pl.buf is None or pl.cursor + padded > pl.buf.numel():
+        return torch.zeros(*shape, dtype=torch.float32, device=device)
+    out = pl.buf[pl.cursor:pl.cursor + n].view(*shape)
+    pl.cursor += padded
+    return out
+
+
 # ------------------------------------------------------------------------------------------ fprop / dgrad
 SPLITK_MAX_PIXELS = 74 * 128     # more output pixels than this always fill the GPU with tiles
 
@@ -109,7 +176,7 @@ def _splitk_ws(pixels: int, cout: int, device):
     (the library decides the split factor, include/pai_b200.h)."""
     if pixels > SPLITK_MAX_PIXELS or cout < 16:
         return None
-    return torch.zeros(pixels, cout, dtype=torch.float32, device=device)
+    return zeros_f32(pixels, cout, device=device)
 
 
 def conv4x4_fprop(x, w_packed, cout, stride=2, bias=None, act=ACT_NONE, slope=0.2, out=None, out_f32=False,
@@ -169,7 +236,7 @@ def conv4x4_fprop_bnstats(x, w_packed, cout, bias=None):
     n, h, w, cin, ld = _nhwc(x)
     cp = w_packed.shape[0]
     out = torch.empty(n, h // 2, w // 2, cout, dtype=torch.bfloat16, device=x.device)
-    part = torch.zeros(BN_PART_ROWS, 2 * cout, dtype=torch.float32, device=x.device)
+    part = zeros_f32(BN_PART_ROWS, 2 * cout, device=x.device)
     _igemm_call("pai_conv4x4_fprop_bnstats", 2.0 * n * (h // 2) * (w // 2) * cout * 16 * cin, _ptr(x), n, h, w, cin, ld,
                 _ptr(w_packed), cout, cp, 2, _ptr(bias), _ptr(out), cout, 0, _ptr(part), BN_PART_ROWS, _stream())
     return out, part
@@ -179,7 +246,7 @@ def convT4x4s2_fprop_bnstats(x, w_packed, cout, bias=None):
     n, h, w, cin, ld = _nhwc(x)
     cp = w_packed.shape[1]
     out = torch.empty(n, 2 * h, 2 * w, cout, dtype=torch.bfloat16, device=x.device)
-    part = torch.zeros(BN_PART_ROWS, 2 * cout, dtype=torch.float32, device=x.device)
+    part = zeros_f32(BN_PART_ROWS, 2 * cout, device=x.device)
     _igemm_call("pai_convT4x4s2_fprop_bnstats", 2.0 * n * h * w * cout * 16 * cin, _ptr(x), n, h, w, cin, ld,
                 _ptr(w_packed), cout, cp, _ptr(bias), _ptr(out), cout, 0, _ptr(part), BN_PART_ROWS, _stream())
     return out, part
@@ -193,7 +260,7 @@ def conv4x4_dgrad_act(gy, w_packed_dgrad, cin, saved_act, slope=0.2, want_colsum
     sn, sh, sw, sc, sld = _nhwc(saved_act)
     assert (sn, sh, sw, sc) == (n, 2 * h, 2 * w, cin) and sld == cin
     out = torch.empty(n, 2 * h, 2 * w, cin, dtype=torch.bfloat16, device=gy.device)
-    part = torch.zeros(BN_PART_ROWS, 2 * cin, dtype=torch.float32, device=gy.device) if want_colsum else None
+    part = zeros_f32(BN_PART_ROWS, 2 * cin, device=gy.device) if want_colsum else None
     _igemm_call("pai_conv4x4_dgrad_act", 2.0 * n * h * w * cin * 16 * cout, _ptr(gy), n, h, w, cout, ld,
                 _ptr(w_packed_dgrad), cin, cp, _ptr(saved_act), float(slope), _ptr(out), cin, 0, _ptr(part), BN_PART_ROWS,
                 _stream())
@@ -322,6 +389,44 @@ def bn_bwd_apply(x, ss, g1, act1, g2, act2, sums, gamma, dx, slope=0.2):
     lib.call("pai_bn_bwd_apply", _ptr(x), m, c, ld, _ptr(ss), _ptr(g1), ldg1, act1, _ptr(g2), ldg2, act2,
              float(slope), _ptr(sums), _ptr(gamma), _ptr(dx), lddx, _stream())
     return dx
+
+
+def bn_small_ok(x, operands: int = 1) -> bool:
+    """Does ``x`` ([m, c] view) fit the one-launch BatchNorm of the small layers (one block per 8 channels holding all
+    pixels of ``operands`` bf16 tensors in shared memory)?  [PAI_NO_BN_SMALL=1 switches the path off]"""
+    if BN_SMALL_OFF:
+        return False
+    m, c, _ = _mat(x)
+    return bool(lib.load().pai_bn_small_ok(m, c, operands))
+
+
+def bn_small_fwd(x, gamma, beta, running_mean, running_var, out1, act1, out2=None, act2=ACT_NONE, slope=0.2, mask=None,
+                 eps=1e-5, momentum=0.1):
+    """Training-mode BatchNorm + activation(s) (+ Dropout2d mask on ``out1``) of a small layer in ONE launch;
+    -> scale_shift ``[4c]`` like ``bn_finalize``."""
+    m, c, ld = _mat(x)
+    _, _, ld1 = _mat(out1)
+    ld2 = _mat(out2)[2] if out2 is not None else 0
+    ss = torch.empty(4 * c, dtype=torch.float32, device=x.device)
+    ppi = m // mask.shape[0] if mask is not None else 0
+    lib.call("pai_bn_small_fwd", _ptr(x), m, c, ld, _ptr(gamma), _ptr(beta), float(eps), float(momentum),
+             _ptr(running_mean), _ptr(running_var), _ptr(ss), _ptr(out1), ld1, act1, _ptr(out2), ld2, act2, float(slope),
+             _ptr(mask), ppi, _stream())
+    return ss
+
+
+def bn_small_bwd(x, ss, g1, act1, g2, act2, gamma, dx, slope=0.2, mask=None):
+    """``scale_channels`` (Dropout2d backward on ``g1``) + ``bn_bwd_reduce`` + ``bn_bwd_apply`` of a small layer in ONE
+    launch; -> sums ``[2c]`` (dbeta | dgamma)."""
+    m, c, ld = _mat(x)
+    _, _, ldg1 = _mat(g1)
+    ldg2 = _mat(g2)[2] if g2 is not None else 0
+    _, _, lddx = _mat(dx)
+    sums = torch.empty(2 * c, dtype=torch.float32, device=x.device)
+    ppi = m // mask.shape[0] if mask is not None else 0
+    lib.call("pai_bn_small_bwd", _ptr(x), m, c, ld, _ptr(ss), _ptr(g1), ldg1, act1, _ptr(g2), ldg2, act2, float(slope),
+             _ptr(mask), ppi, _ptr(gamma), _ptr(sums), _ptr(dx), lddx, _stream())
+    return sums
 
 
 def act_bwd(x, g1, act1, g2, act2, dx, slope=0.2):
