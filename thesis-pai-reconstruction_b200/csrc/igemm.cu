@@ -147,6 +147,18 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                 const int col0 = nt * n_tile;
                 const int kb_begin = num_kb * ks / p.splitk, kb_end = num_kb * (ks + 1) / p.splitk;
                 const int g_end = g + (kb_end - kb_begin) / ksub;        // stages of this tile (host: ksub | k-blocks)
+                // this worker's next tile: its activation boxes are prefetched into L2 box by box alongside the loads
+                int pw0 = 0, ph0 = 0, pn0 = 0, pphase = 0;
+                const bool pf = p.prefetch_taps != 0 && t + workers < total_tiles;
+                if (pf) {
+                    int r2, m2, tw2, th2, tn2;
+                    p.fd_n_tiles.divmod(p.fd_splitk.quot(t + workers), r2, tn2);
+                    p.fd_m_tiles.divmod(r2, pphase, m2);
+                    if (PAIR) m2 = 2 * m2 + (int)rank;
+                    p.fd_tiles_w.divmod(m2, m2, tw2);
+                    p.fd_tiles_h.divmod(m2, tn2, th2);
+                    pw0 = tw2 * p.bw, ph0 = th2 * p.bh, pn0 = tn2 * p.bn;
+                }
                 for (; mine < g_end; mine += P) {
                     const int kb0 = kb_begin + (mine - g) * ksub;
                     {
@@ -170,6 +182,8 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                                 tma_load_5d_pair(sa, &tm_a, &ps.full[stage], kcj * 64, w0 + p.box_w[tap], 0, h0 + p.box_h[tap], n0);
                             else
                                 tma_load_5d(sa, &tm_a, &ps.full[stage], kcj * 64, w0 + p.box_w[tap], 0, h0 + p.box_h[tap], n0);
+                            if (pf && ((p.prefetch_taps >> tap) & 1u))
+                                tma_prefetch_5d(&tm_a, kcj * 64, pw0 + p.box_w[tap], 0, ph0 + p.box_h[tap], pn0);
                             if (PAIR && p.box_merge[tap]) {
                                 // one MMA of N = 64 * nu: the N dimension of a cta_group::2 tile is split [first half |
                                 // second half] between the two CTAs, so this CTA stages the WHOLE 64-row weight boxes of
@@ -196,6 +210,10 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                             int tapj, kcj;
                             p.fd_kc.divmod(kb, tapj, kcj);
                             const int ti = phase_idx * p.ntaps + tapj;
+                            if (pf && ((p.prefetch_taps >> tapj) & 1u)) {
+                                const int tj = pphase * p.ntaps + tapj;
+                                tma_prefetch_5d(&tm_a, p.tap_c[tj] + kcj * 64, pw0 + p.tap_w[tj], p.tap_p[tj], ph0 + p.tap_h[tj], pn0);
+                            }
                             if (PAIR) {
                                 tma_load_5d_pair(sa, &tm_a, &ps.full[stage], p.tap_c[ti] + kcj * 64, w0 + p.tap_w[ti], p.tap_p[ti],
                                                  h0 + p.tap_h[ti], n0);
@@ -395,11 +413,27 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 #endif
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + a * acc_cols + ((uint32_t)(q * 32) << 16);
+            // The accumulator is handed back as soon as this warp's LAST chunk sits in registers -- before its bias /
+            // statistics / store work -- with a relaxed arrival (2 x 8 warps release a pair's accumulators, 8 otherwise).
+            bool released = false;
+            auto release_acc = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {                        // (every lane fenced its TMEM reads before the __syncwarp)
+                    if (PAIR)
+                        mbar_arrive_leader_relaxed(&ps.acc_empty[a]);
+                    else
+                        mbar_arrive_relaxed(&ps.acc_empty[a]);
+                }
+                released = true;
+            };
             if (fast) {
                 // ---- coalesced path: 64 channels of 32 rows are transposed through a swizzled smem tile so
                 // that 8 lanes write one full 128-byte row segment (4 rows per store instruction)
                 uint4* tile = stage_buf[warp - 4];
                 int item = 0;
+                const int n_items = (acc_n >> 6) * n_out;
+                const int last_item = ((n_items - 1) & 1) == half ? n_items - 1 : n_items - 2;   // of this warp (< 0: none)
                 for (int c = 0; c < acc_n; c += 64) {
                     // fused phases: chunk c is phase c/64 of the same 64 output channels
                     const long long coff = fused ? p.out_phase_off[c >> 6] : 0;
@@ -411,6 +445,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         for (int j = 0; j < 4; ++j)
                             tmem_ld_16(tmem_d + (uint32_t)(c + 16 * j), *reinterpret_cast<uint32_t(*)[16]>(&v[16 * j]));
                         tmem_ld_wait();
+                        if (item == last_item) release_acc();
                         __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(which == 0 ? p.out : p.out2);
                         const int act = which == 0 ? p.act : p.act2;
                         const long long my_off = which == 0 ? off : off2;
@@ -530,14 +565,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                                       vec_ok && col0 + cc + 16 <= p.cout, p.cout - (col0 + cc));
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {                            // (every lane fenced its TMEM reads before the __syncwarp)
-                if (PAIR)
-                    mbar_arrive_leader(&ps.acc_empty[a]);   // 2 x 8 warps (both CTAs) release the accumulator pair
-                else
-                    mbar_arrive(&ps.acc_empty[a]);          // 8 warps release the accumulator to the MMA warp
-            }
+            if (!released) release_acc();
 #ifdef PAI_PROFILE_ROLES
             prof_total += clock64() - twork;
 #endif
@@ -715,7 +743,7 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&ps.acc_empty[0]);
+            if (lane == 0) mbar_arrive_relaxed(&ps.acc_empty[0]);   // relaxed: must not wait for the reductions above
             ++seg;
         }
     }
@@ -760,6 +788,18 @@ int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFp
     }
     const size_t stage_bytes = sub_bytes * p.ksub;
     p.stages = pick_stages(stage_bytes, 192 * 1024);
+    p.prefetch_taps = 0;
+    if (getenv("PAI_NO_L2_PREFETCH") == nullptr && p.splitk == 1) {
+        if (p.fused_phases) {
+            p.prefetch_taps = 1u;                       // the centre box
+        } else {
+            for (int t = 0; t < p.ntaps && t < 32; ++t) {
+                bool first = true;                      // first tap of its (channel offset, parity) class
+                for (int u = 0; u < t; ++u) first = first && !(p.tap_c[u] == p.tap_c[t] && p.tap_p[u] == p.tap_p[t]);
+                if (first) p.prefetch_taps |= 1u << t;
+            }
+        }
+    }
     p.m_tiles = pair ? (m_tiles + 1) / 2 : m_tiles, p.n_tiles = n_tiles, p.phases = phases;
     const size_t smem = stage_bytes * p.stages + 1024;
     static DeviceOnce once;

@@ -119,6 +119,13 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, u
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
+// L2 prefetch of a 5-D box (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -206,6 +213,16 @@ __device__ __forceinline__ void tma_load_5d_pair(void* dst, const CUtensorMap* m
         : "memory");
 }
 // arrive (count 1) on the LEADER CTA's copy of `bar`, from either CTA of the pair
+// Relaxed arrivals for the accumulator hand-off: the TMEM reads being released are ordered by tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync, so the arrival need not wait for the epilogue's outstanding global stores and
+// reductions the way the default .release form does (measured: +10 .. +50 us per layer with the release form).
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader_relaxed(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPairLeaderMask)
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPairLeaderMask) : "memory");
 }

@@ -413,14 +413,18 @@ __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(c
                 for (int j = 0; j < 4; ++j)
                     tmem_ld_16(td + (uint32_t)(c0 + 16 * j), *reinterpret_cast<uint32_t(*)[16]>(&v[16 * j]));
                 tmem_ld_wait();
+                if (c0 + 64 >= p.cout) {
+                    // last chunk in registers: the accumulator goes back to the MMA warp now, with a relaxed arrival (the
+                    // default release form would wait for the stores below)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_relaxed(&ps.acc_empty[g]);
+                }
                 const long long pix0 = tile * 128 + q * 32;          // first pixel of this warp's 32 rows
                 thin_store_dispatch(v, p.act1, p.slope, tile_buf, lane, p.out1 + c0, pix0, p.ld1, p.total_pix);
                 if (p.out2 != nullptr)
                     thin_store_dispatch(v, p.act2, p.slope, tile_buf, lane, p.out2 + c0, pix0, p.ld2, p.total_pix);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ps.acc_empty[g]);
 #ifdef PAI_PROFILE_ROLES
             ep_work += clock64() - tw0;
 #endif
@@ -760,7 +764,7 @@ thin_convT_plane_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
                     tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&ps.acc_empty[acc]);
+                    if (lane == 0) mbar_arrive_relaxed(&ps.acc_empty[acc]);
                     ++cnt;
 #pragma unroll
                     for (int t = 0; t < 16; ++t) ring[sc][t][b] = __uint_as_float(v[t]);
