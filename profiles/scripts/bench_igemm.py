@@ -34,7 +34,7 @@ def rnd(*shape):
 LAYERS = [("enc1", "conv", 128, 64, 128), ("enc2", "conv", 64, 128, 256), ("enc3", "conv", 32, 256, 512),
           ("enc4", "conv", 16, 512, 512), ("dec3", "convT", 8, 1024, 512), ("dec4", "convT", 16, 1024, 256),
           ("dec5", "convT", 32, 512, 128), ("dec6", "convT", 64, 256, 64),
-          ("D1dgrad", "dgrad_act", 64, 128, 64), ("D2dgrad", "dgrad_act", 32, 256, 128), ("D3dgrad", "dgrad_act", 16, 512, 256),
+          ("D1dgrad", "dgrad_act", 64, 128, 64), ("D1dgrad-ns", "dgrad_act_nosum", 64, 128, 64), ("D2dgrad", "dgrad_act", 32, 256, 128), ("D3dgrad", "dgrad_act", 16, 512, 256),
           ("dec4dgrad", "conv", 32, 256, 1024), ("dec5dgrad", "conv", 64, 128, 512), ("dec6dgrad", "conv", 128, 64, 256)]
 for name, kind, hin, cin, cout in LAYERS:
     if only and name not in only:
@@ -53,7 +53,8 @@ for name, kind, hin, cin, cout in LAYERS:
         wp = ops.pack_convT_weight(torch.randn(cin, cout, 4, 4, device=dev) * 0.05)
         saved = rnd(N, 2 * hin, 2 * hin, cout)
         fl = 2.0 * N * hin ** 2 * cout * 16 * cin
-        fn = lambda: ops.conv4x4_dgrad_act(x, wp, cout, saved)
+        fn = (lambda: ops.conv4x4_dgrad_act(x, wp, cout, saved)) if kind == "dgrad_act" else (
+            lambda: ops.conv4x4_dgrad_act(x, wp, cout, saved, want_colsum=False))
     us = timeit(fn)
     print(f"{name:10s} {kind:9s} {cin:5d}->{cout:4d} @{hin:3d}  {fl / 1e9:7.1f} GFLOP {us:8.1f} us {fl / us / 1e6:8.1f} TFLOP/s", flush=True)
     del x, wp

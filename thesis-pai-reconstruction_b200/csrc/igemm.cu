@@ -58,7 +58,7 @@ struct __align__(8) PipeSmem {
 // per FLOP (the large layers are L2 -> SM bound, profiles/r1_igemm_fprop_step_summary.txt) and one instruction stream
 // drives two tensor cores.  `full` barriers live in the leader (both CTAs' TMA loads complete on them), `empty` /
 // `acc_full` are signalled in both CTAs by multicast commits, both epilogues release the leader's `acc_empty`.
-template <bool PAIR>
+template <bool PAIR, bool MASKED>
 __global__ void __launch_bounds__(kFpropThreads, 1)
 igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const IgemmFpropParams p) {
@@ -366,6 +366,52 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         const int hi = (r / p.bw) % p.bh;
         const int ni = r / (p.bw * p.bh);
         const int n_out = p.out2 != nullptr ? 2 : 1;
+        // Rows this lane STORES on the coalesced path: row i * 4 + lane / 8 of the warp's 32, chunk lane % 8.  Their
+        // position inside the pixel box is packed once (w | h << 8 | n << 16); the per-tile offset is plain integer
+        // arithmetic -- the earlier form fetched offset and validity of every stored row with three shuffles, and the
+        // shuffles / shared-memory loads of the epilogue are what slows the main loop (they share the MIO pipe with
+        // the barrier traffic of the producer and MMA warps: without them the N <= 128 layers run 20-40 % faster).
+        int spack[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rs = q * 32 + i * 4 + (lane >> 3);
+            spack[i] = (rs % p.bw) | (((rs / p.bw) % p.bh) << 8) | ((rs / (p.bw * p.bh)) << 16);
+        }
+        // BatchNorm / bias-gradient column sums: this lane's 8 channels (chunk lane % 8) of the rows it stores, carried
+        // in registers ACROSS tiles and reduced over the 4 row groups + added to the CTA's partial row only when the
+        // warp moves to other columns or runs out of tiles (before: 32 shared-memory loads and 4 reductions per chunk)
+        // (only where the warp stays on ONE 64-channel block -- N <= 128 or the phase-fused tiles -- and outside the
+        // register-bound masked instantiation; elsewhere the chunk's sums are reduced and added right after its stores)
+        const bool st_persist = !MASKED && (fused || acc_n <= 128);
+        float st_sum[8], st_sq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) st_sum[j] = st_sq[j] = 0.f;
+        int st_col = -1;                               // first channel of the 64 the accumulators belong to
+        // reduce over the 4 row groups (lanes l, l^8, l^16, l^24 hold the same channels) and add to the CTA's partial row
+        auto reduce_add = [&](float (&su)[8], float (&sq)[8], int col) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                su[j] += __shfl_xor_sync(0xffffffffu, su[j], 8);
+                su[j] += __shfl_xor_sync(0xffffffffu, su[j], 16);
+                sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], 8);
+                sq[j] += __shfl_xor_sync(0xffffffffu, sq[j], 16);
+            }
+            if (lane < 8) {
+                float* bp = p.bn_part + (size_t)blockIdx.x * (2 * p.cout) + col + lane * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    atomicAdd(bp + j, su[j]);
+                    atomicAdd(bp + p.cout + j, sq[j]);
+                }
+            }
+        };
+        auto flush_stats = [&]() {
+            if (st_col < 0) return;
+            reduce_add(st_sum, st_sq, st_col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) st_sum[j] = st_sq[j] = 0.f;
+            st_col = -1;
+        };
         int it = 0;
         for (int t = worker; t < total_tiles; t += workers, ++it) {
             int nt, rr, mt, phase_idx, tw, th, tn;
@@ -390,10 +436,10 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             // (the fused-phase mode is only launched when this holds: cout == n_tile == 64, bf16 output)
             // fused activation backward: the saved activations of this warp's first chunk are fetched while the MMAs of
             // the tile are still running, those of the next chunk while the current one is packed and stored
-            const bool masked = p.mask_src != nullptr && fast;
+            const bool masked = MASKED && p.mask_src != nullptr && fast;   // (MASKED: the instantiation of pai_conv4x4_dgrad_act)
             // two chunk buffers: both of this warp's chunks of a 256-column (phase-fused) tile are in flight before the
             // accumulator is waited for -- a DRAM round trip is longer than packing and storing one chunk
-            uint4 mreg[2][8];
+            uint4 mreg[MASKED ? 2 : 1][8];
             auto mask_fetch = [&](int c, uint4 (&dst)[8]) {
                 const long long coff = fused ? p.out_phase_off[c >> 6] : 0;
                 const __nv_bfloat16* mrow = reinterpret_cast<const __nv_bfloat16*>(p.mask_src) + off + coff + (fused ? 0 : c);
@@ -402,7 +448,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                     dst[ch] = row_ok ? __ldg(reinterpret_cast<const uint4*>(mrow) + ch) : make_uint4(0, 0, 0, 0);
             };
             if (masked && 64 * half < acc_n) mask_fetch(64 * half, mreg[0]);
-            if (masked && 64 * half + 128 < acc_n) mask_fetch(64 * half + 128, mreg[1]);
+            if (masked && 64 * half + 128 < acc_n) mask_fetch(64 * half + 128, mreg[MASKED ? 1 : 0]);
             {
                 ROLE_T0();
                 mbar_wait(&ps.acc_full[a], acc_phase);
@@ -453,12 +499,13 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         // activation / bias dispatch hoisted out of the 64-element loop
                         if (masked && which == 0) {
                             // this warp's chunks are c = 64 * half + 128 * k (n_out == 1): buffer k & 1
+                            // this warp's chunks are c = 64 * half + 128 * k (n_out == 1): buffer k & 1
                             if (((c >> 7) & 1) == 0) {
                                 mask_pack(v, mreg[0], p.mask_slope, tile, lane);
                                 if (c + 256 < acc_n) mask_fetch(c + 256, mreg[0]);
                             } else {
-                                mask_pack(v, mreg[1], p.mask_slope, tile, lane);
-                                if (c + 256 < acc_n) mask_fetch(c + 256, mreg[1]);
+                                mask_pack(v, mreg[MASKED ? 1 : 0], p.mask_slope, tile, lane);
+                                if (c + 256 < acc_n) mask_fetch(c + 256, mreg[MASKED ? 1 : 0]);
                             }
                         } else if (act == PAI_ACT_LEAKY)
                             bias_act_pack<PAI_ACT_LEAKY>(v, bias_c, p.slope, tile, lane);
@@ -469,51 +516,108 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         else
                             bias_act_pack<PAI_ACT_NONE>(v, bias_c, p.slope, tile, lane);
                         __syncwarp();
-                        if (p.bn_part != nullptr && which == 0) {
-                            // BatchNorm statistics of exactly what is stored: lane <-> channels 2*lane, 2*lane + 1 of
-                            // the chunk, summed over the valid rows of the 32 x 64 bf16 tile (conflict-free words)
-                            const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
-                            const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
-                            const int chunk = lane >> 2, word = lane & 3;
-                            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-                            // all 32 shared-memory loads are issued before the first add (a per-row `continue` kept the
-                            // loop a chain of load -> use round trips: 35 cycles x 32 rows per chunk)
-                            uint32_t u[32];
+                        if constexpr (MASKED) {
+                            // register-bound instantiation (64 registers of prefetched activation masks): statistics from
+                            // the staged tile, offsets of the stored rows by shuffle (the 8 packed row positions of the other path spill here)
+                            if (p.bn_part != nullptr && which == 0) {
+                                // BatchNorm statistics of exactly what is stored: lane <-> channels 2*lane, 2*lane + 1 of
+                                // the chunk, summed over the valid rows of the 32 x 64 bf16 tile (conflict-free words)
+                                const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
+                                const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
+                                const int chunk = lane >> 2, word = lane & 3;
+                                float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                                // all 32 shared-memory loads are issued before the first add (a per-row `continue` kept the
+                                // loop a chain of load -> use round trips: 35 cycles x 32 rows per chunk)
+                                uint32_t u[32];
 #pragma unroll
-                            for (int row = 0; row < 32; ++row) u[row] = tw[(row * 8 + (chunk ^ (row & 7))) * 4 + word];
-                            if (okmask == 0xffffffffu) {
+                                for (int row = 0; row < 32; ++row) u[row] = tw[(row * 8 + (chunk ^ (row & 7))) * 4 + word];
+                                if (okmask == 0xffffffffu) {
 #pragma unroll
-                                for (int row = 0; row < 32; ++row) {
-                                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[row]));
-                                    s0 += f.x;
-                                    s1 += f.y;
-                                    q0 = fmaf(f.x, f.x, q0);
-                                    q1 = fmaf(f.y, f.y, q1);
+                                    for (int row = 0; row < 32; ++row) {
+                                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[row]));
+                                        s0 += f.x;
+                                        s1 += f.y;
+                                        q0 = fmaf(f.x, f.x, q0);
+                                        q1 = fmaf(f.y, f.y, q1);
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int row = 0; row < 32; ++row) {
+                                        if (!((okmask >> row) & 1u)) continue;
+                                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[row]));
+                                        s0 += f.x;
+                                        s1 += f.y;
+                                        q0 = fmaf(f.x, f.x, q0);
+                                        q1 = fmaf(f.y, f.y, q1);
+                                    }
+                                }
+                                float* bp = p.bn_part + (size_t)blockIdx.x * (2 * p.cout) + col0 + oc + 2 * lane;
+                                atomicAdd(bp, s0);
+                                atomicAdd(bp + 1, s1);
+                                atomicAdd(bp + p.cout, q0);
+                                atomicAdd(bp + p.cout + 1, q1);
+                            }
+    
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int row = i * 4 + (lane >> 3), ch = lane & 7;
+                                const uint4 val = tile[row * 8 + (ch ^ (row & 7))];
+                                const long long roff = __shfl_sync(0xffffffffu, my_off, row);
+                                const int rok = __shfl_sync(0xffffffffu, (int)row_ok, row);
+                                if (rok) *reinterpret_cast<uint4*>(dst + roff + coff + oc + ch * 8) = val;
+                            }
+                        } else {
+                            const bool stats = p.bn_part != nullptr && which == 0;
+                            if (stats && st_persist && st_col != col0 + oc) {
+                                flush_stats();
+                                st_col = col0 + oc;
+                            }
+                            if (which == 0) {
+                                float cs[8], cq[8];            // this chunk's column sums (8 channels of this lane's rows)
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) cs[j] = cq[j] = 0.f;
+                                const long long tile_off = p.out_phase_off[phase_idx] + coff + col0 + oc + (lane & 7) * 8;
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) {
+                                    const int row = i * 4 + (lane >> 3), ch = lane & 7;
+                                    const int sw_ = tw * p.bw + (spack[i] & 255), sh_ = th * p.bh + ((spack[i] >> 8) & 255);
+                                    const int sn_ = tn * p.bn + (spack[i] >> 16);
+                                    if (sw_ < p.gw && sh_ < p.gh && sn_ < p.gn) {
+                                        const uint4 val = tile[row * 8 + (ch ^ (row & 7))];
+                                        if (stats) {       // exactly the stored bf16 values
+                                            const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&val);
+#pragma unroll
+                                            for (int j = 0; j < 4; ++j) {
+                                                const float2 f = __bfloat1622float2(hv[j]);
+                                                cs[2 * j] += f.x;
+                                                cs[2 * j + 1] += f.y;
+                                                cq[2 * j] = fmaf(f.x, f.x, cq[2 * j]);
+                                                cq[2 * j + 1] = fmaf(f.y, f.y, cq[2 * j + 1]);
+                                            }
+                                        }
+                                        *reinterpret_cast<uint4*>(dst + tile_off + (long long)sn_ * p.out_sn + (long long)sh_ * p.out_sh +
+                                                                  (long long)sw_ * p.out_sw) = val;
+                                    }
+                                }
+                                if (stats) {
+                                    if (st_persist) {
+#pragma unroll
+                                        for (int j = 0; j < 8; ++j) st_sum[j] += cs[j], st_sq[j] += cq[j];
+                                    } else {
+                                        reduce_add(cs, cq, col0 + oc);
+                                    }
                                 }
                             } else {
+                                // second output (its own strides): offsets of the stored rows by shuffle
 #pragma unroll
-                                for (int row = 0; row < 32; ++row) {
-                                    if (!((okmask >> row) & 1u)) continue;
-                                    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[row]));
-                                    s0 += f.x;
-                                    s1 += f.y;
-                                    q0 = fmaf(f.x, f.x, q0);
-                                    q1 = fmaf(f.y, f.y, q1);
+                                for (int i = 0; i < 8; ++i) {
+                                    const int row = i * 4 + (lane >> 3), ch = lane & 7;
+                                    const uint4 val = tile[row * 8 + (ch ^ (row & 7))];
+                                    const long long roff = __shfl_sync(0xffffffffu, my_off, row);
+                                    const int rok = __shfl_sync(0xffffffffu, (int)row_ok, row);
+                                    if (rok) *reinterpret_cast<uint4*>(dst + roff + coff + oc + ch * 8) = val;
                                 }
                             }
-                            float* bp = p.bn_part + (size_t)blockIdx.x * (2 * p.cout) + col0 + oc + 2 * lane;
-                            atomicAdd(bp, s0);
-                            atomicAdd(bp + 1, s1);
-                            atomicAdd(bp + p.cout, q0);
-                            atomicAdd(bp + p.cout + 1, q1);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int row = i * 4 + (lane >> 3), ch = lane & 7;
-                            const uint4 val = tile[row * 8 + (ch ^ (row & 7))];
-                            const long long roff = __shfl_sync(0xffffffffu, my_off, row);
-                            const int rok = __shfl_sync(0xffffffffu, (int)row_ok, row);
-                            if (rok) *reinterpret_cast<uint4*>(dst + roff + coff + oc + ch * 8) = val;
                         }
                         __syncwarp();
                     }
@@ -570,6 +674,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             prof_total += clock64() - twork;
 #endif
         }
+        if (p.bn_part != nullptr) flush_stats();
 #ifdef PAI_PROFILE_ROLES
         if (blockIdx.x == 0 && threadIdx.x == 128)
             printf("[roles] epilogue warp 4: waiting for a full accumulator %lld cyc, working %lld cyc over %d tiles\n", prof_wait, prof_total, it);
@@ -806,8 +911,10 @@ int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFp
     const int dev = current_device(), num_sms = persistent_ctas(dev);
     if (num_sms < 0) return -1;
     if (once.need(dev)) {
-        PAI_CUDA_OK(cudaFuncSetAttribute(igemm_fprop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 194 * 1024));
-        PAI_CUDA_OK(cudaFuncSetAttribute(igemm_fprop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 194 * 1024));
+        PAI_CUDA_OK(cudaFuncSetAttribute(igemm_fprop_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 194 * 1024));
+        PAI_CUDA_OK(cudaFuncSetAttribute(igemm_fprop_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 194 * 1024));
+        PAI_CUDA_OK(cudaFuncSetAttribute(igemm_fprop_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 194 * 1024));
+        PAI_CUDA_OK(cudaFuncSetAttribute(igemm_fprop_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 194 * 1024));
         once.mark(dev);
     }
     if (p.splitk < 1) p.splitk = 1;
@@ -842,9 +949,15 @@ int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFp
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr, cfg.numAttrs = 1;
-        PAI_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_fprop_kernel<true>, tm_a, tm_b, p));
+        if (p.mask_src != nullptr)
+            PAI_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_fprop_kernel<true, true>, tm_a, tm_b, p));
+        else
+            PAI_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_fprop_kernel<true, false>, tm_a, tm_b, p));
     } else {
-        igemm_fprop_kernel<false><<<grid, kFpropThreads, smem, stream>>>(tm_a, tm_b, p);
+        if (p.mask_src != nullptr)
+            igemm_fprop_kernel<false, true><<<grid, kFpropThreads, smem, stream>>>(tm_a, tm_b, p);
+        else
+            igemm_fprop_kernel<false, false><<<grid, kFpropThreads, smem, stream>>>(tm_a, tm_b, p);
     }
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
