@@ -894,7 +894,9 @@ int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFp
     const size_t stage_bytes = sub_bytes * p.ksub;
     p.stages = pick_stages(stage_bytes, 192 * 1024);
     p.prefetch_taps = 0;
-    if (getenv("PAI_NO_L2_PREFETCH") == nullptr && p.splitk == 1) {
+    // opt-in (PAI_L2_PREFETCH=1): measured on every layer of the batch-64 step, it changes nothing -- the loop is not
+    // waiting on DRAM latency
+    if (getenv("PAI_L2_PREFETCH") != nullptr && p.splitk == 1) {
         if (p.fused_phases) {
             p.prefetch_taps = 1u;                       // the centre box
         } else {

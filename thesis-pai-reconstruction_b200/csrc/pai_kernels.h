@@ -39,10 +39,9 @@ struct IgemmFpropParams {
     int kc_per_tap, ntaps;     // 64-channel K blocks per tap, taps per phase
     int stages;
     int ksub;                  // 64-channel K blocks per pipeline stage (1 or 2), chosen by launch_igemm_fprop
-    // L2 prefetch of the NEXT tile's activation boxes while this tile is loaded (bit t: tap / box t is prefetched; one tap
-    // per parity class is enough, the others are shifted copies of the same lines).  The TMA-load -> MMA -> commit ->
-    // reload loop of a stage is latency-bound (8 stages x 24 KB in flight against a DRAM round trip): a box that already
-    // sits in L2 comes back in about half the time.  Filled by launch_igemm_fprop.
+    // Optional (PAI_L2_PREFETCH=1) L2 prefetch of the NEXT tile's activation boxes while this tile is loaded (bit t: tap /
+    // box t is prefetched; one tap per parity class is enough, the others are shifted copies of the same lines).  An
+    // experiment that ruled DRAM latency out as the limit of the narrow layers: no layer moved.  Filled by launch_igemm_fprop.
     unsigned prefetch_taps;
     int m_tiles, n_tiles, phases;  // tile grid walked by the persistent CTAs
     int tap_c[16], tap_w[16], tap_p[16], tap_h[16];  // per (phase * ntaps + tap): A-box coordinate offsets
