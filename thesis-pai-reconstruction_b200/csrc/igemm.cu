@@ -380,9 +380,9 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         // BatchNorm / bias-gradient column sums: this lane's 8 channels (chunk lane % 8) of the rows it stores, carried
         // in registers ACROSS tiles and reduced over the 4 row groups + added to the CTA's partial row only when the
         // warp moves to other columns or runs out of tiles (before: 32 shared-memory loads and 4 reductions per chunk)
-        // (only where the warp stays on ONE 64-channel block -- N <= 128 or the phase-fused tiles -- and outside the
-        // register-bound masked instantiation; elsewhere the chunk's sums are reduced and added right after its stores)
-        const bool st_persist = !MASKED && (fused || acc_n <= 128);
+        // (only where the warp stays on ONE 64-channel block -- N <= 128 or the phase-fused tiles; elsewhere the chunk's
+        // sums are reduced and added right after its stores)
+        const bool st_persist = fused || acc_n <= 128;
         float st_sum[8], st_sq[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) st_sum[j] = st_sq[j] = 0.f;
@@ -439,7 +439,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
             const bool masked = MASKED && p.mask_src != nullptr && fast;   // (MASKED: the instantiation of pai_conv4x4_dgrad_act)
             // two chunk buffers: both of this warp's chunks of a 256-column (phase-fused) tile are in flight before the
             // accumulator is waited for -- a DRAM round trip is longer than packing and storing one chunk
-            uint4 mreg[MASKED ? 2 : 1][8];
+            uint4 mreg[1][8];   // ONE chunk of masks in flight (two cost 32 more registers: every variant of the lean store / statistics path spilled)
             auto mask_fetch = [&](int c, uint4 (&dst)[8]) {
                 const long long coff = fused ? p.out_phase_off[c >> 6] : 0;
                 const __nv_bfloat16* mrow = reinterpret_cast<const __nv_bfloat16*>(p.mask_src) + off + coff + (fused ? 0 : c);
@@ -448,7 +448,6 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                     dst[ch] = row_ok ? __ldg(reinterpret_cast<const uint4*>(mrow) + ch) : make_uint4(0, 0, 0, 0);
             };
             if (masked && 64 * half < acc_n) mask_fetch(64 * half, mreg[0]);
-            if (masked && 64 * half + 128 < acc_n) mask_fetch(64 * half + 128, mreg[MASKED ? 1 : 0]);
             {
                 ROLE_T0();
                 mbar_wait(&ps.acc_full[a], acc_phase);
@@ -500,13 +499,8 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         if (masked && which == 0) {
                             // this warp's chunks are c = 64 * half + 128 * k (n_out == 1): buffer k & 1
                             // this warp's chunks are c = 64 * half + 128 * k (n_out == 1): buffer k & 1
-                            if (((c >> 7) & 1) == 0) {
-                                mask_pack(v, mreg[0], p.mask_slope, tile, lane);
-                                if (c + 256 < acc_n) mask_fetch(c + 256, mreg[0]);
-                            } else {
-                                mask_pack(v, mreg[MASKED ? 1 : 0], p.mask_slope, tile, lane);
-                                if (c + 256 < acc_n) mask_fetch(c + 256, mreg[MASKED ? 1 : 0]);
-                            }
+                            mask_pack(v, mreg[0], p.mask_slope, tile, lane);
+                            if (c + 128 < acc_n) mask_fetch(c + 128, mreg[0]);    // next chunk of this warp, behind this one's stores
                         } else if (act == PAI_ACT_LEAKY)
                             bias_act_pack<PAI_ACT_LEAKY>(v, bias_c, p.slope, tile, lane);
                         else if (act == PAI_ACT_RELU)
@@ -516,48 +510,48 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                         else
                             bias_act_pack<PAI_ACT_NONE>(v, bias_c, p.slope, tile, lane);
                         __syncwarp();
-                        if constexpr (MASKED) {
-                            // register-bound instantiation (64 registers of prefetched activation masks): statistics from
-                            // the staged tile, offsets of the stored rows by shuffle (the 8 packed row positions of the other path spill here)
-                            if (p.bn_part != nullptr && which == 0) {
-                                // BatchNorm statistics of exactly what is stored: lane <-> channels 2*lane, 2*lane + 1 of
-                                // the chunk, summed over the valid rows of the 32 x 64 bf16 tile (conflict-free words)
-                                const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
-                                const uint32_t* tw = reinterpret_cast<const uint32_t*>(tile);
-                                const int chunk = lane >> 2, word = lane & 3;
-                                float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-                                // all 32 shared-memory loads are issued before the first add (a per-row `continue` kept the
-                                // loop a chain of load -> use round trips: 35 cycles x 32 rows per chunk)
-                                uint32_t u[32];
+                        const bool stats = p.bn_part != nullptr && which == 0;
+                        if (stats && st_persist && st_col != col0 + oc) {
+                            flush_stats();
+                            st_col = col0 + oc;
+                        }
+                        if (which == 0) {
+                            float cs[8], cq[8];            // this chunk's column sums (8 channels of this lane's rows)
 #pragma unroll
-                                for (int row = 0; row < 32; ++row) u[row] = tw[(row * 8 + (chunk ^ (row & 7))) * 4 + word];
-                                if (okmask == 0xffffffffu) {
+                            for (int j = 0; j < 8; ++j) cs[j] = cq[j] = 0.f;
+                            const long long tile_off = p.out_phase_off[phase_idx] + coff + col0 + oc + (lane & 7) * 8;
 #pragma unroll
-                                    for (int row = 0; row < 32; ++row) {
-                                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[row]));
-                                        s0 += f.x;
-                                        s1 += f.y;
-                                        q0 = fmaf(f.x, f.x, q0);
-                                        q1 = fmaf(f.y, f.y, q1);
+                            for (int i = 0; i < 8; ++i) {
+                                const int row = i * 4 + (lane >> 3), ch = lane & 7;
+                                const int sw_ = tw * p.bw + (spack[i] & 255), sh_ = th * p.bh + ((spack[i] >> 8) & 255);
+                                const int sn_ = tn * p.bn + (spack[i] >> 16);
+                                if (sw_ < p.gw && sh_ < p.gh && sn_ < p.gn) {
+                                    const uint4 val = tile[row * 8 + (ch ^ (row & 7))];
+                                    if (stats) {       // exactly the stored bf16 values
+                                        const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&val);
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) {
+                                            const float2 f = __bfloat1622float2(hv[j]);
+                                            cs[2 * j] += f.x;
+                                            cs[2 * j + 1] += f.y;
+                                            cq[2 * j] = fmaf(f.x, f.x, cq[2 * j]);
+                                            cq[2 * j + 1] = fmaf(f.y, f.y, cq[2 * j + 1]);
+                                        }
                                     }
-                                } else {
-#pragma unroll
-                                    for (int row = 0; row < 32; ++row) {
-                                        if (!((okmask >> row) & 1u)) continue;
-                                        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u[row]));
-                                        s0 += f.x;
-                                        s1 += f.y;
-                                        q0 = fmaf(f.x, f.x, q0);
-                                        q1 = fmaf(f.y, f.y, q1);
-                                    }
+                                    *reinterpret_cast<uint4*>(dst + tile_off + (long long)sn_ * p.out_sn + (long long)sh_ * p.out_sh +
+                                                              (long long)sw_ * p.out_sw) = val;
                                 }
-                                float* bp = p.bn_part + (size_t)blockIdx.x * (2 * p.cout) + col0 + oc + 2 * lane;
-                                atomicAdd(bp, s0);
-                                atomicAdd(bp + 1, s1);
-                                atomicAdd(bp + p.cout, q0);
-                                atomicAdd(bp + p.cout + 1, q1);
                             }
-    
+                            if (stats) {
+                                if (st_persist) {
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) st_sum[j] += cs[j], st_sq[j] += cq[j];
+                                } else {
+                                    reduce_add(cs, cq, col0 + oc);
+                                }
+                            }
+                        } else {
+                            // second output (its own strides): offsets of the stored rows by shuffle
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
                                 const int row = i * 4 + (lane >> 3), ch = lane & 7;
@@ -566,60 +560,8 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
                                 const int rok = __shfl_sync(0xffffffffu, (int)row_ok, row);
                                 if (rok) *reinterpret_cast<uint4*>(dst + roff + coff + oc + ch * 8) = val;
                             }
-                        } else {
-                            const bool stats = p.bn_part != nullptr && which == 0;
-                            if (stats && st_persist && st_col != col0 + oc) {
-                                flush_stats();
-                                st_col = col0 + oc;
-                            }
-                            if (which == 0) {
-                                float cs[8], cq[8];            // this chunk's column sums (8 channels of this lane's rows)
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) cs[j] = cq[j] = 0.f;
-                                const long long tile_off = p.out_phase_off[phase_idx] + coff + col0 + oc + (lane & 7) * 8;
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const int row = i * 4 + (lane >> 3), ch = lane & 7;
-                                    const int sw_ = tw * p.bw + (spack[i] & 255), sh_ = th * p.bh + ((spack[i] >> 8) & 255);
-                                    const int sn_ = tn * p.bn + (spack[i] >> 16);
-                                    if (sw_ < p.gw && sh_ < p.gh && sn_ < p.gn) {
-                                        const uint4 val = tile[row * 8 + (ch ^ (row & 7))];
-                                        if (stats) {       // exactly the stored bf16 values
-                                            const __nv_bfloat162* hv = reinterpret_cast<const __nv_bfloat162*>(&val);
-#pragma unroll
-                                            for (int j = 0; j < 4; ++j) {
-                                                const float2 f = __bfloat1622float2(hv[j]);
-                                                cs[2 * j] += f.x;
-                                                cs[2 * j + 1] += f.y;
-                                                cq[2 * j] = fmaf(f.x, f.x, cq[2 * j]);
-                                                cq[2 * j + 1] = fmaf(f.y, f.y, cq[2 * j + 1]);
-                                            }
-                                        }
-                                        *reinterpret_cast<uint4*>(dst + tile_off + (long long)sn_ * p.out_sn + (long long)sh_ * p.out_sh +
-                                                                  (long long)sw_ * p.out_sw) = val;
-                                    }
-                                }
-                                if (stats) {
-                                    if (st_persist) {
-#pragma unroll
-                                        for (int j = 0; j < 8; ++j) st_sum[j] += cs[j], st_sq[j] += cq[j];
-                                    } else {
-                                        reduce_add(cs, cq, col0 + oc);
-                                    }
-                                }
-                            } else {
-                                // second output (its own strides): offsets of the stored rows by shuffle
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const int row = i * 4 + (lane >> 3), ch = lane & 7;
-                                    const uint4 val = tile[row * 8 + (ch ^ (row & 7))];
-                                    const long long roff = __shfl_sync(0xffffffffu, my_off, row);
-                                    const int rok = __shfl_sync(0xffffffffu, (int)row_ok, row);
-                                    if (rok) *reinterpret_cast<uint4*>(dst + roff + coff + oc + ch * 8) = val;
-                                }
-                            }
                         }
-                        __syncwarp();
+                                            __syncwarp();
                     }
                 }
             } else {
