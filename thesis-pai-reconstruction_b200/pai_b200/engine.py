@@ -153,6 +153,51 @@ def _thin_in_dgrad_pack(w, j):  # Conv2d weight [C, cin, 4, 4] -> bf16 [16, C]: 
     return _packs.get(f"thin_in_d{j}", w, lambda t: t[:, j].reshape(t.shape[0], 16).t().contiguous().bfloat16())
 
 
+# ---- models with in / out channels != 1 (the reference's own defaults are 3 / 3, models/pix2pix.py:25-27): the few image
+# channels travel in a zero-padded 64-channel NHWC carrier and the first / last convolution run on the ordinary
+# implicit-GEMM kernels with zero-padded weights.  Functionally complete, not tuned: the BASELINE configurations are
+# grayscale and take the thin-layer kernels (csrc/thin.cu).
+CARRIER = 64
+
+
+def _carrier(*images: torch.Tensor) -> torch.Tensor:
+    """``[N, C_k, H, W]`` tensors -> bf16 ``[N, H, W, 64]`` with the channels of all tensors side by side, rest zero."""
+    n, _, h, w = images[0].shape
+    total = sum(t.shape[1] for t in images)
+    if total > CARRIER:
+        raise RuntimeError(f"pai_b200: at most {CARRIER} image channels per convolution input (got {total})")
+    out = torch.zeros(n, h, w, CARRIER, dtype=torch.bfloat16, device=images[0].device)
+    c0 = 0
+    for t in images:
+        out[..., c0:c0 + t.shape[1]] = t.permute(0, 2, 3, 1)
+        c0 += t.shape[1]
+    return out
+
+
+def _pad_dim1(t: torch.Tensor) -> torch.Tensor:      # [A, B < 64, 4, 4] -> fp32 [A, 64, 4, 4]
+    return torch.nn.functional.pad(t.float(), (0, 0, 0, 0, 0, CARRIER - t.shape[1]))
+
+
+def _carrier_in_pack(w):         # Conv2d [C, cin, 4, 4] reading a carrier: fprop operand
+    return _aux_pack("car_in_f", w, lambda t: ops.pack_conv_weight(_pad_dim1(t)))
+
+
+def _carrier_in_dgrad_pack(w):   # ... its data gradient (ConvT fprop with the weight read as [in=C, out=64])
+    return _aux_pack("car_in_d", w, lambda t: ops.pack_convT_weight(_pad_dim1(t)))
+
+
+def _carrier_out_pack(w):        # ConvTranspose2d [Cin, cout, 4, 4] writing a carrier: fprop operand
+    return _aux_pack("car_out_f", w, lambda t: ops.pack_convT_weight(_pad_dim1(t)))
+
+
+def _carrier_out_dgrad_pack(w):  # ... its data gradient (Conv fprop with the weight read as [out=Cin, in=64])
+    return _aux_pack("car_out_d", w, lambda t: ops.pack_conv_weight(_pad_dim1(t)))
+
+
+def _carrier_bias(b):            # [cout] -> fp32 [64]
+    return _aux_pack("car_b", b, lambda t: torch.nn.functional.pad(t.float(), (0, CARRIER - t.shape[0])))
+
+
 FOLD_EVAL_BN = os.environ.get("PAI_NO_BN_FOLD") is None      # eval mode: BatchNorm folded into the GEMM operands
 
 
@@ -379,9 +424,9 @@ class UnetSpec:
         self.in_ch = enc_convs[0].weight.shape[1]
         self.out_ch = dec_convs[-1].weight.shape[1]
         self.dec_out = [c.weight.shape[1] for c in dec_convs]
-        if self.in_ch != 1 or self.out_ch != 1:
-            raise RuntimeError("pai_b200: the B200 path supports in_channels == out_channels == 1 (grayscale PAI "
-                               f"images, main.py:26-27); got {self.in_ch}/{self.out_ch}. No fallback exists.")
+        if not (1 <= self.in_ch <= CARRIER and 1 <= self.out_ch <= CARRIER):
+            raise RuntimeError(f"pai_b200: in / out channels must be in 1..{CARRIER}; got {self.in_ch}/{self.out_ch}. "
+                               "No fallback exists.")
         for c in self.enc_ch + self.dec_out[:-1]:
             if c % 64:
                 raise RuntimeError(f"pai_b200: channel counts must be multiples of 64 (got {c})")
@@ -407,7 +452,10 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
         raise RuntimeError(f"pai_b200: input {h}x{w} must be divisible by 2^{L}")
     dev = x.device
     x = x.contiguous().float()
-    plane = x.view(n, h, w)
+    if x.shape[1] != spec.in_ch:
+        raise RuntimeError(f"pai_b200: the generator takes {spec.in_ch}-channel images, got {x.shape[1]}")
+    plane = x.view(n, h, w) if spec.in_ch == 1 else None
+    xc = None if spec.in_ch == 1 else _carrier(x)        # multi-channel input: zero-padded 64-channel carrier
     ch = spec.enc_ch
     hs = [h >> (i + 1) for i in range(L)]
     ws = [w >> (i + 1) for i in range(L)]
@@ -425,7 +473,10 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
     # its concat buffer cat[L-1] holds UN-activated values; every other decoder starts with a ReLU.
     # enc0 (1 input channel) = im2col of the plane + one tensor-core GEMM with two fused outputs
     xcol = None
-    if THIN_DIRECT and c0 <= 256:
+    if xc is not None:
+        ops.conv4x4_fprop_dual(xc, _carrier_in_pack(conv0.weight), c0, conv0.bias.detach(), a_in[1], ACT_LEAKY,
+                               cat[L - 1][..., c0:], ACT_NONE, slope=SLOPE)
+    elif THIN_DIRECT and c0 <= 256:
         # one pass: the 16-tap rows are built in shared memory, both consumers are written by the same epilogue
         ops.thin_conv_fprop([plane], _thin_in_pack(conv0.weight), c0, conv0.bias.detach(), a_in[1], ACT_LEAKY,
                             cat[L - 1][..., c0:], ACT_NONE, slope=SLOPE)
@@ -493,7 +544,12 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
     last = spec.dec_convs[L - 1]
     # last decoder (1 output channel): 16 per-tap partial products per input pixel (GEMM, the wide input is
     # read once) + col2im with bias and Tanh
-    if THIN_DIRECT and ops.thin_plane_ok(d_in):
+    if spec.out_ch != 1:
+        # multi-channel output: ConvT into a 64-channel fp32 carrier (+bias, Tanh; the padding channels give tanh(0) = 0)
+        yc = ops.convT4x4s2_fprop(d_in, _carrier_out_pack(last.weight), CARRIER, bias=_carrier_bias(last.bias), act=ACT_TANH,
+                                  out_f32=True)
+        y = yc[..., :spec.out_ch].permute(0, 3, 1, 2).contiguous()
+    elif THIN_DIRECT and ops.thin_plane_ok(d_in):
         y = ops.thin_convT_plane(d_in, _thin_out_fprop_pack(last.weight), last.bias.detach(), ACT_TANH).view(n, 1, h, w)
     else:
         part = ops.pointwise_gemm(d_in, _thin_out_fprop_pack(last.weight), 16, out_f32=True)
@@ -505,6 +561,7 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
     s.xcol = xcol
     s.drop_masks = drop_masks
     s.plane, s.cat, s.a_in, s.raw_e, s.ss_e, s.raw_d, s.ss_d, s.dec_in0, s.y = plane, cat, a_in, raw_e, ss_e, raw_d, ss_d, dec_in0, y
+    s.xc = xc
     return y, s
 
 
@@ -515,25 +572,32 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
     y = s.y
     n, _, h, w = y.shape
     dev = y.device
-    g_pre = (grad_y.float() * (1.0 - y * y)).contiguous().view(n, h, w)        # through Tanh
+    g_pre = (grad_y.float() * (1.0 - y * y)).contiguous()                       # through Tanh
     grads = {}
-    # ---- last decoder: ConvT(2*c0 -> 1)
+    # ---- last decoder: ConvT(2*c0 -> out_ch)
     last = spec.dec_convs[L - 1]
     cin_last = last.weight.shape[0]
-    gcol = None
-    if THIN_DIRECT and ops.thin_wgrad_ok(s.cat[L - 1], [g_pre]):
-        dw = ops.thin_conv_wgrad(s.cat[L - 1], [g_pre])                          # [cin, 16]
+    if spec.out_ch != 1:
+        gc = _carrier(g_pre)
+        dwl = ops.wgrad_finish(ops.convT4x4s2_wgrad(s.cat[L - 1], gc))             # [cin, 64, 4, 4]
+        grads[(1, L - 1)] = (dwl[:, :spec.out_ch].contiguous(), g_pre.sum((0, 2, 3)))
+        dcat = ops.conv4x4_fprop(gc, _carrier_out_dgrad_pack(last.weight), cin_last, stride=2)
     else:
-        gcol = ops.im2col4x4([g_pre], h // 2, w // 2, stride=2)                  # [N, h/2, w/2, 64], 16 taps of g
-        dw = ops.pointwise_wgrad(s.cat[L - 1], gcol)                             # [cin, 64]
-    grads[(1, L - 1)] = (dw[:, :16].reshape(cin_last, 1, 4, 4), g_pre.sum().reshape(1))
-    if THIN_DIRECT and cin_last <= 256:
-        dcat = _bf16(n, h // 2, w // 2, cin_last, device=dev)
-        ops.thin_conv_fprop([g_pre], _thin_out_dgrad_pack(last.weight), cin_last, None, dcat, ACT_NONE)
-    else:
-        if gcol is None:
-            gcol = ops.im2col4x4([g_pre], h // 2, w // 2, stride=2)
-        dcat = ops.pointwise_gemm(gcol, _thin_out_dgrad_pack(last.weight), cin_last, k_valid=16)
+        g_pre = g_pre.view(n, h, w)
+        gcol = None
+        if THIN_DIRECT and ops.thin_wgrad_ok(s.cat[L - 1], [g_pre]):
+            dw = ops.thin_conv_wgrad(s.cat[L - 1], [g_pre])                      # [cin, 16]
+        else:
+            gcol = ops.im2col4x4([g_pre], h // 2, w // 2, stride=2)              # [N, h/2, w/2, 64], 16 taps of g
+            dw = ops.pointwise_wgrad(s.cat[L - 1], gcol)                         # [cin, 64]
+        grads[(1, L - 1)] = (dw[:, :16].reshape(cin_last, 1, 4, 4), g_pre.sum().reshape(1))
+        if THIN_DIRECT and cin_last <= 256:
+            dcat = _bf16(n, h // 2, w // 2, cin_last, device=dev)
+            ops.thin_conv_fprop([g_pre], _thin_out_dgrad_pack(last.weight), cin_last, None, dcat, ACT_NONE)
+        else:
+            if gcol is None:
+                gcol = ops.im2col4x4([g_pre], h // 2, w // 2, stride=2)
+            dcat = ops.pointwise_gemm(gcol, _thin_out_dgrad_pack(last.weight), cin_last, k_valid=16)
     # ---- decoders L-2 .. 0
     dskip = [None] * L                          # dskip[i]: grad w.r.t. relu(skip_i) (second half of dcat)
     for j in range(L - 2, -1, -1):
@@ -591,12 +655,16 @@ def unet_backward(spec: UnetSpec, s: _Saved, grad_y: torch.Tensor):
     c0 = ch[0]
     d_raw = _bf16(*s.a_in[1].shape, device=dev)
     sums = ops.act_bwd(s.a_in[1], d_a, ACT_LEAKY, dskip[0], ACT_NONE, d_raw, slope=SLOPE)
-    if THIN_DIRECT and ops.thin_wgrad_ok(d_raw, [s.plane]):
-        dw0 = ops.thin_conv_wgrad(d_raw, [s.plane])                              # [c0, 16]
+    if s.xc is not None:
+        dw0 = ops.wgrad_finish(ops.conv4x4_wgrad(s.xc, d_raw, stride=2))         # [c0, 64, 4, 4]
+        grads[(0, 0)] = (dw0[:, :spec.in_ch].contiguous(), sums[:c0].clone())
     else:
-        xcol = s.xcol if s.xcol is not None else ops.im2col4x4([s.plane], h // 2, w // 2, stride=2)
-        dw0 = ops.pointwise_wgrad(d_raw, xcol)                                   # [c0, 64]
-    grads[(0, 0)] = (dw0[:, :16].reshape(c0, 1, 4, 4), sums[:c0].clone())
+        if THIN_DIRECT and ops.thin_wgrad_ok(d_raw, [s.plane]):
+            dw0 = ops.thin_conv_wgrad(d_raw, [s.plane])                          # [c0, 16]
+        else:
+            xcol = s.xcol if s.xcol is not None else ops.im2col4x4([s.plane], h // 2, w // 2, stride=2)
+            dw0 = ops.pointwise_wgrad(d_raw, xcol)                               # [c0, 64]
+        grads[(0, 0)] = (dw0[:, :16].reshape(c0, 1, 4, 4), sums[:c0].clone())
     out = []
     for i in range(L):
         out += list(grads[(0, i)])
@@ -638,9 +706,10 @@ class DiscSpec:
         self.convs = convs                       # 4 stride-2 convs (bias) + final stride-1 conv (no bias)
         self.ch = [c.weight.shape[0] for c in convs]
         cin0 = convs[0].weight.shape[1]
-        if cin0 != 2:
-            raise RuntimeError("pai_b200: the B200 PatchGAN path takes cat([x, y]) of two 1-channel images "
-                               f"(Discriminator(in_channels=1), SURVEY.md Q1); the first conv has {cin0} inputs")
+        if cin0 % 2 or not (2 <= cin0 <= CARRIER):
+            raise RuntimeError("pai_b200: the PatchGAN's first conv reads cat([x, y]) of two images with the same number "
+                               f"of channels (at most {CARRIER} together); it has {cin0} inputs")
+        self.img_ch = cin0 // 2                  # 1: thin-layer kernels; more: 64-channel carrier (reference default 3)
         if self.ch[-1] != 1 or convs[-1].bias is not None:
             raise RuntimeError("pai_b200: unexpected PatchGAN head")
 
@@ -655,11 +724,18 @@ class DiscSpec:
 def disc_forward(spec: DiscSpec, x: torch.Tensor, y: torch.Tensor, save: bool):
     n, _, h, w = x.shape
     dev = x.device
-    px = x.contiguous().float().view(n, h, w)
-    py = y.contiguous().float().view(n, h, w)
+    if x.shape[1] != spec.img_ch or y.shape[1] != spec.img_ch:
+        raise RuntimeError(f"pai_b200: this PatchGAN takes two {spec.img_ch}-channel images, got {x.shape[1]} and {y.shape[1]}")
     c0 = spec.convs[0]
-    xycol = None                                                                 # cat([x, y]) is never materialised
-    if THIN_DIRECT and spec.ch[0] <= 256:
+    xycol = xyc = px = py = None
+    if spec.img_ch == 1:
+        px = x.contiguous().float().view(n, h, w)
+        py = y.contiguous().float().view(n, h, w)                                # cat([x, y]) is never materialised
+    if spec.img_ch != 1:
+        xyc = _carrier(x.float(), y.float())
+        hcur = ops.conv4x4_fprop(xyc, _carrier_in_pack(c0.weight), spec.ch[0], stride=2, bias=c0.bias.detach(), act=ACT_LEAKY,
+                                 slope=SLOPE)
+    elif THIN_DIRECT and spec.ch[0] <= 256:
         hcur = _bf16(n, h // 2, w // 2, spec.ch[0], device=dev)
         ops.thin_conv_fprop([px, py], _thin_in_pack(c0.weight), spec.ch[0], c0.bias.detach(), hcur, ACT_LEAKY, slope=SLOPE)
     else:
@@ -686,7 +762,7 @@ def disc_forward(spec: DiscSpec, x: torch.Tensor, y: torch.Tensor, save: bool):
     if not save:
         return logits, None
     s = _Saved()
-    s.px, s.py, s.hs, s.xycol = px, py, hs, xycol
+    s.px, s.py, s.hs, s.xycol, s.xyc, s.hw = px, py, hs, xycol, xyc, (h, w)
     return logits, s
 
 
@@ -730,8 +806,18 @@ def disc_backward(spec: DiscSpec, s: _Saved, g_logits: torch.Tensor, need_params
                 fused = (d_next, part.sum(0) if part is not None else None)
             else:
                 dh = ops.convT4x4s2_fprop(d_pre, _dgrad_pack(conv.weight), cprev)
+        elif s.xyc is not None:
+            h, w = s.hw
+            if need_params:
+                dw0 = ops.wgrad_finish(ops.conv4x4_wgrad(s.xyc, d_pre, stride=2))   # [c, 64, 4, 4]
+                grads[0] = dw0[:, :2 * spec.img_ch].contiguous()
+                grads[1] = sums[:ck].clone()
+            gy = None
+            if need_y:
+                gyc = ops.convT4x4s2_fprop(d_pre, _carrier_in_dgrad_pack(conv.weight), CARRIER, out_f32=True)
+                gy = gyc[..., spec.img_ch:2 * spec.img_ch].permute(0, 3, 1, 2).contiguous()
         else:
-            h, w = s.px.shape[1], s.px.shape[2]
+            h, w = s.hw
             if need_params:
                 if THIN_DIRECT and ops.thin_wgrad_ok(d_pre, [s.px, s.py]):
                     dw0 = ops.thin_conv_wgrad(d_pre, [s.px, s.py])               # [c, 32], column = tap*2 + j

@@ -27,9 +27,9 @@ def _to_int(x: torch.Tensor) -> torch.Tensor:
     """models/utils.py:12 (torchvision ConvertImageDtype(torch.uint8): ``x * 255.999`` truncated) on the device.  The
     reference converts the RAW SSIM map (report.py:134-135), whose values may be negative: like the host conversion
     it runs, out-of-range values wrap modulo 256 instead of being clamped."""
-    if x.is_cuda:
-        return ops.to_uint8(x)
-    return x.float().mul(255.0 + 1.0 - 1e-3).to(torch.int32).to(torch.uint8)
+    if not x.is_cuda:
+        raise RuntimeError("pai_b200.report: the uint8 conversion runs on the GPU (pai_to_uint8); there is no CPU fallback")
+    return ops.to_uint8(x)
 
 
 def hot_images(preds: torch.Tensor) -> torch.Tensor:
