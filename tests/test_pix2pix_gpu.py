@@ -163,10 +163,16 @@ def test_frozen_generator_builds_no_graph_and_discriminator_dgrad_only():
 
 
 def test_unsupported_configurations_fail_loudly():
+    """No CPU / PyTorch fallback: what the kernels cannot run raises (3-channel models run: tests/test_rgb_gpu.py)."""
     from models.pix2pix import Pix2Pix
     m3 = Pix2Pix(in_channels=3, out_channels=3, dropout=0.0, loss_type="mse").cuda()
     with pytest.raises(RuntimeError):
-        m3(torch.zeros(1, 3, 256, 256, device="cuda"))
+        m3(torch.zeros(1, 1, 256, 256, device="cuda"))          # wrong number of image channels
+    with pytest.raises(RuntimeError):
+        m3(torch.zeros(1, 3, 250, 256, device="cuda"))          # not divisible by 2^8
+    m1 = Pix2Pix(in_channels=1, out_channels=1, dropout=0.0, loss_type="mse")
+    with pytest.raises(RuntimeError):
+        m1(torch.zeros(1, 1, 256, 256))                         # CPU tensors: there is no host path
 
 
 def test_train_mode_dropout2d_matches_reference_arithmetic(monkeypatch):

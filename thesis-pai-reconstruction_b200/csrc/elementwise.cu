@@ -154,6 +154,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, long long m, 
                                    const float* __restrict__ beta, float eps, float momentum, int training,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ ss, int nparts) {
+    pdl_launch_dependents();
+    pdl_wait();
     // block = 32 channels x 32 row groups: the partial rows are summed by 32 threads per channel (coalesced 128-byte
     // loads, 5 rows each for the 160 per-CTA rows of the fused statistics), then thread row 0 finishes the channel
     constexpr int RG = 32;
@@ -209,6 +211,8 @@ template <int ACT1, int ACT2 /* -1: no second output */>
 __global__ void __launch_bounds__(kEwThreads)
 bn_apply_act_kernel(const __nv_bfloat16* __restrict__ x, long long m, int c, int ld, const float* __restrict__ ss,
                     __nv_bfloat16* __restrict__ o1, int ld1, __nv_bfloat16* __restrict__ o2, int ld2, float slope) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int cv = c >> 3;
     const int vec = threadIdx.x % cv;
     const long long ppb = kEwThreads / cv;
@@ -250,6 +254,8 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long m, int c, int ld, c
               const __nv_bfloat16* __restrict__ g1, int ldg1, const __nv_bfloat16* __restrict__ g2, int ldg2,
               float slope, float* __restrict__ sums, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
               int lddx) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int cv = c >> 3;
     const int vec = threadIdx.x % cv;
     const long long ppb = kEwThreads / cv;
@@ -368,6 +374,8 @@ bn_small_fwd_kernel(const __nv_bfloat16* __restrict__ x, int m, int c, int ld, c
                     float* __restrict__ running_var, float* __restrict__ ss, __nv_bfloat16* __restrict__ o1, int ld1,
                     int act1, __nv_bfloat16* __restrict__ o2, int ld2, int act2, float slope,
                     const float* __restrict__ mask, int ppi) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ uint4 small_vals[];
     __shared__ float red[kSmallThreads / 32][16];
     __shared__ float total[16], coef[16];
@@ -440,6 +448,8 @@ bn_small_bwd_kernel(const __nv_bfloat16* __restrict__ x, int m, int c, int ld, c
                     const __nv_bfloat16* __restrict__ g1, int ldg1, int act1, const __nv_bfloat16* __restrict__ g2,
                     int ldg2, int act2, float slope, const float* __restrict__ mask, int ppi,
                     const float* __restrict__ gamma, float* __restrict__ sums, __nv_bfloat16* __restrict__ dx, int lddx) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ uint4 small_vals[];
     __shared__ float red[kSmallBwdThreads / 32][16];
     __shared__ float total[16], coef[24];
@@ -514,8 +524,15 @@ static int bn_bwd_dispatch(cudaStream_t st, const __nv_bfloat16* x, long long m,
                            const __nv_bfloat16* g1, int ldg1, int act1, const __nv_bfloat16* g2, int ldg2, int act2,
                            float slope, float* sums, const float* gamma, __nv_bfloat16* dx, int lddx) {
 #define PAI_BWD(A1, A2, BNF)                                                                                        \
-    bn_bwd_kernel<A1, A2, BNF, MODE><<<wave_grid<bn_bwd_kernel<A1, A2, BNF, MODE>>(m, c), kEwThreads, 0, st>>>(x, m, c, ld, ss, g1, ldg1, g2, ldg2, slope, sums, \
-                                                                   gamma, dx, lddx)
+    do {                                                                                                             \
+        const dim3 g_((unsigned)wave_grid<bn_bwd_kernel<A1, A2, BNF, MODE>>(m, c));                                   \
+        if (MODE == 1) /* the reduce modes follow a memset node: ordinary launch */                                  \
+            PAI_CUDA_OK(launch_pdl(bn_bwd_kernel<A1, A2, BNF, MODE>, g_, dim3(kEwThreads), 0, st, 1, x, m, c, ld, ss, g1, ldg1, g2, \
+                                   ldg2, slope, sums, gamma, dx, lddx));                                               \
+        else                                                                                                         \
+            bn_bwd_kernel<A1, A2, BNF, MODE><<<g_, kEwThreads, 0, st>>>(x, m, c, ld, ss, g1, ldg1, g2, ldg2, slope, sums, gamma, \
+                                                                         dx, lddx);                                   \
+    } while (0)
 #define PAI_BWD_A2(A1, BNF)                                            \
     do {                                                               \
         if (g2 == nullptr) PAI_BWD(A1, -1, BNF);                       \
@@ -623,8 +640,8 @@ int pai_bn_finalize_partials(const float* sums, int nparts, long long m, int c, 
                              float* scale_shift, void* stream) {
     PAI_REQUIRE(scale_shift && (training ? (sums != nullptr && nparts >= 1) : (running_mean && running_var)),
                 "pai_bn_finalize: null pointer");
-    bn_finalize_kernel<<<(c + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(sums, m, c, gamma, beta, eps, momentum, training,
-                                                                         running_mean, running_var, scale_shift, nparts);
+    PAI_CUDA_OK(launch_pdl(bn_finalize_kernel, dim3((unsigned)((c + 31) / 32)), dim3(1024), 0, (cudaStream_t)stream, 1, sums, m, c, gamma, beta,
+                           eps, momentum, training, running_mean, running_var, scale_shift, nparts));
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -641,8 +658,10 @@ int pai_bn_apply_act(const void* x, long long m, int c, int ld, const float* sca
     PAI_REQUIRE(ew_ok(c, x, ld) && ew_ok(c, out1, ld1) && (out2 == nullptr || ew_ok(c, out2, ld2)),
                 "pai_bn_apply_act: bad channel count / stride / alignment (c=%d)", c);
     cudaStream_t st = (cudaStream_t)stream;
-#define PAI_APPLY(A1, A2) \
-    bn_apply_act_kernel<A1, A2><<<wave_grid<bn_apply_act_kernel<A1, A2>>(m, c), kEwThreads, 0, st>>>((const bf16*)x, m, c, ld, scale_shift, (bf16*)out1, ld1, (bf16*)out2, ld2, slope)
+#define PAI_APPLY(A1, A2)                                                                                              \
+    PAI_CUDA_OK(launch_pdl(bn_apply_act_kernel<A1, A2>, dim3((unsigned)wave_grid<bn_apply_act_kernel<A1, A2>>(m, c)),     \
+                           dim3(kEwThreads), 0, st, 1, (const bf16*)x, m, c, ld, scale_shift, (bf16*)out1, ld1, (bf16*)out2, \
+                           ld2, slope))
 #define PAI_APPLY_A2(A1)                                               \
     do {                                                               \
         if (out2 == nullptr) PAI_APPLY(A1, -1);                        \
@@ -717,10 +736,9 @@ int pai_bn_small_fwd(const void* x, long long m, int c, int ld, const float* gam
         PAI_CUDA_OK(cudaFuncSetAttribute(bn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmemMax));
         once.mark(dev);
     }
-    bn_small_fwd_kernel<<<c / 8, kSmallThreads, (size_t)m * 16, (cudaStream_t)stream>>>(
-        (const bf16*)x, (int)m, c, ld, gamma, beta, eps, momentum, running_mean, running_var, scale_shift, (bf16*)out1, ld1,
-        act1, (bf16*)out2, ld2, act2, slope, mask, pixels_per_image > 0 ? pixels_per_image : 1);
-    PAI_CUDA_OK(cudaGetLastError());
+    PAI_CUDA_OK(launch_pdl(bn_small_fwd_kernel, dim3((unsigned)(c / 8)), dim3(kSmallThreads), (size_t)m * 16, (cudaStream_t)stream, 1,
+                           (const bf16*)x, (int)m, c, ld, gamma, beta, eps, momentum, running_mean, running_var, scale_shift,
+                           (bf16*)out1, ld1, act1, (bf16*)out2, ld2, act2, slope, mask, pixels_per_image > 0 ? pixels_per_image : 1));
     return 0;
 }
 
@@ -740,10 +758,10 @@ int pai_bn_small_bwd(const void* x, long long m, int c, int ld, const float* sca
         PAI_CUDA_OK(cudaFuncSetAttribute(bn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallSmemMax));
         once.mark(dev);
     }
-    bn_small_bwd_kernel<<<c / 8, kSmallBwdThreads, (size_t)m * 16 * operands, (cudaStream_t)stream>>>(
-        (const bf16*)x, (int)m, c, ld, scale_shift, (const bf16*)g1, ldg1, act1, (const bf16*)g2, ldg2, act2, slope, mask,
-        pixels_per_image > 0 ? pixels_per_image : 1, gamma, sums, (bf16*)dx, lddx);
-    PAI_CUDA_OK(cudaGetLastError());
+    PAI_CUDA_OK(launch_pdl(bn_small_bwd_kernel, dim3((unsigned)(c / 8)), dim3(kSmallBwdThreads), (size_t)m * 16 * operands,
+                           (cudaStream_t)stream, 1, (const bf16*)x, (int)m, c, ld, scale_shift, (const bf16*)g1, ldg1, act1,
+                           (const bf16*)g2, ldg2, act2, slope, mask, pixels_per_image > 0 ? pixels_per_image : 1, gamma, sums,
+                           (bf16*)dx, lddx));
     return 0;
 }
 

@@ -62,6 +62,7 @@ template <bool PAIR, bool MASKED>
 __global__ void __launch_bounds__(kFpropThreads, 1)
 igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                    const IgemmFpropParams p) {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     __shared__ PipeSmem ps;
     __shared__ uint4 stage_buf[8][32 * 8];   // per epilogue warp: 32 rows x 128 B, XOR-swizzled 16-byte chunks
@@ -116,6 +117,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = ps.tmem_base;
+    pdl_wait();      // everything above overlapped the previous kernel's tail; its outputs are visible from here on
 
     long long prof_wait = 0, prof_wait2 = 0, prof_total = 0, prof_fence = 0, prof_issue = 0, prof_commit = 0;
     (void)prof_wait, (void)prof_wait2, (void)prof_total, (void)prof_fence, (void)prof_issue, (void)prof_commit;
@@ -649,6 +651,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_constant__ CUtensorMap tm_s,
                    const IgemmWgradParams p) {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     __shared__ PipeSmem ps;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -683,6 +686,7 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = ps.tmem_base;
+    pdl_wait();
 
     // three TMA producer warps deal the work units round-robin (see igemm_fprop_kernel: one thread cannot issue the up
     // to 8 boxes of a stage as fast as the tensor core consumes them)
@@ -886,23 +890,16 @@ int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFp
                     "igemm fprop: fused BatchNorm statistics need a bf16 output with cout %% 64 == 0, no split-K and "
                     "%d partial rows (cout=%d n_tile=%d splitk=%d rows=%d)", grid, p.cout, p.n_tile, p.splitk, p.bn_rows);
     }
-    if (pair) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid), cfg.blockDim = dim3(kFpropThreads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr, cfg.numAttrs = 1;
-        if (p.mask_src != nullptr)
-            PAI_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_fprop_kernel<true, true>, tm_a, tm_b, p));
-        else
-            PAI_CUDA_OK(cudaLaunchKernelEx(&cfg, igemm_fprop_kernel<true, false>, tm_a, tm_b, p));
-    } else {
-        if (p.mask_src != nullptr)
-            igemm_fprop_kernel<false, true><<<grid, kFpropThreads, smem, stream>>>(tm_a, tm_b, p);
-        else
-            igemm_fprop_kernel<false, false><<<grid, kFpropThreads, smem, stream>>>(tm_a, tm_b, p);
-    }
+    const int cl = pair ? 2 : 1;
+    const dim3 g((unsigned)grid), b(kFpropThreads);
+    if (pair && p.mask_src != nullptr)
+        PAI_CUDA_OK(launch_pdl(igemm_fprop_kernel<true, true>, g, b, smem, stream, cl, tm_a, tm_b, p));
+    else if (pair)
+        PAI_CUDA_OK(launch_pdl(igemm_fprop_kernel<true, false>, g, b, smem, stream, cl, tm_a, tm_b, p));
+    else if (p.mask_src != nullptr)
+        PAI_CUDA_OK(launch_pdl(igemm_fprop_kernel<false, true>, g, b, smem, stream, cl, tm_a, tm_b, p));
+    else
+        PAI_CUDA_OK(launch_pdl(igemm_fprop_kernel<false, false>, g, b, smem, stream, cl, tm_a, tm_b, p));
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -911,6 +908,8 @@ int launch_igemm_fprop(const CUtensorMap& tm_a, const CUtensorMap& tm_b, IgemmFp
 __global__ void __launch_bounds__(256)
 splitk_finish_kernel(const float* __restrict__ ws, long long total, int cout, const float* __restrict__ bias, int act,
                      float slope, void* __restrict__ y, int y_ld, int y_f32) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long pix = i / cout;
         const int c = (int)(i - pix * cout);
@@ -931,7 +930,7 @@ int launch_splitk_finish(const float* ws, long long pixels, int cout, const floa
     const int sms = sm_count(current_device());
     if (sms < 0) return -1;
     if (blocks > sms * 8) blocks = sms * 8;
-    splitk_finish_kernel<<<(int)blocks, 256, 0, stream>>>(ws, total, cout, bias, act, slope, y, y_ld, y_f32);
+    PAI_CUDA_OK(launch_pdl(splitk_finish_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, 1, ws, total, cout, bias, act, slope, y, y_ld, y_f32));
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -953,7 +952,7 @@ int launch_igemm_wgrad(const CUtensorMap& tm_u, const CUtensorMap& tm_s, IgemmWg
     if (grid > num_sms) grid = num_sms;
     if (grid < 1) grid = 1;
     if (p.max_ctas > 0 && grid > p.max_ctas) grid = p.max_ctas;
-    igemm_wgrad_kernel<<<(int)grid, kThreads, smem, stream>>>(tm_u, tm_s, p);
+    PAI_CUDA_OK(launch_pdl(igemm_wgrad_kernel, dim3((unsigned)grid), dim3(kThreads), smem, stream, 1, tm_u, tm_s, p));
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }

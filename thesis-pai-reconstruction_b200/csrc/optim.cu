@@ -24,6 +24,8 @@ struct AdamHyper {
 // Bias-correction scalars kept on the device so that a captured CUDA graph of the training step stays valid from one
 // replay to the next: ++*step; dyn = {lr / (1 - b1^t), 1 / sqrt(1 - b2^t)} in double like torch's host code.
 __global__ void adam_prepare_kernel(int* step, float lr, float beta1, float beta2, float* dyn) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const int t = *step + 1;
         *step = t;
@@ -152,6 +154,8 @@ struct AdamPackTable {
 
 __global__ void __launch_bounds__(kPackThreads)
 adam_pack_multi_kernel(const __grid_constant__ AdamPackTable t, AdamHyper hy0, const float* __restrict__ dyn) {
+    pdl_launch_dependents();
+    pdl_wait();
     int k = 0;
     while (k + 1 < t.count && (int)blockIdx.x >= t.first_tile[k + 1]) ++k;
     const int tile = blockIdx.x - t.first_tile[k];
@@ -167,6 +171,8 @@ adam_pack_multi_kernel(const __grid_constant__ AdamPackTable t, AdamHyper hy0, c
 // than a fresh fill right before the wgrad kernel, because the fill leaves the lines in L2 for the red.adds.
 __global__ void __launch_bounds__(256)
 wgrad_finish_kernel(float* __restrict__ dw, long long ab, float* __restrict__ grad, int zero_src) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ab; i += (long long)gridDim.x * blockDim.x) {
         float v[16];
 #pragma unroll
@@ -193,6 +199,8 @@ struct AdamTable {
 
 __global__ void __launch_bounds__(256)
 adam_multi_kernel(const __grid_constant__ AdamTable t, AdamHyper hy0, const float* __restrict__ dyn) {
+    pdl_launch_dependents();
+    pdl_wait();
     const AdamHyper hy = adam_dyn(hy0, dyn);
     for (int k = blockIdx.y; k < t.count; k += gridDim.y) {
         float* p = t.p[k];
@@ -319,8 +327,7 @@ int pai_adam_pack_conv4x4_multi(int count, float* const* ws, const float* const*
             tiles += ((as[k] + kTA - 1) / kTA) * ((bs[k] + kTB - 1) / kTB);
         }
         t.first_tile[t.count] = tiles;
-        adam_pack_multi_kernel<<<tiles, kPackThreads, smem, (cudaStream_t)stream>>>(t, hy, dyn);
-        PAI_CUDA_OK(cudaGetLastError());
+        PAI_CUDA_OK(launch_pdl(adam_pack_multi_kernel, dim3((unsigned)tiles), dim3(kPackThreads), (size_t)smem, (cudaStream_t)stream, 1, t, hy, dyn));
     }
     return 0;
 }
@@ -330,15 +337,13 @@ int pai_wgrad_finish(float* dw_tap_major, long long ab, float* grad, int zero_sr
     PAI_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0, "pai_wgrad_finish: grad must be 16 B aligned");
     long long blocks = (ab + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    wgrad_finish_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(dw_tap_major, ab, grad, zero_src);
-    PAI_CUDA_OK(cudaGetLastError());
+    PAI_CUDA_OK(launch_pdl(wgrad_finish_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, 1, dw_tap_major, ab, grad, zero_src));
     return 0;
 }
 
 int pai_adam_prepare(int* step, float lr, float beta1, float beta2, float* dyn, void* stream) {
     PAI_REQUIRE(step != nullptr && dyn != nullptr, "pai_adam_prepare: null pointer");
-    adam_prepare_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(step, lr, beta1, beta2, dyn);
-    PAI_CUDA_OK(cudaGetLastError());
+    PAI_CUDA_OK(launch_pdl(adam_prepare_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, 1, step, lr, beta1, beta2, dyn));
     return 0;
 }
 
@@ -360,8 +365,7 @@ int pai_adam_multi(int count, float* const* params, const float* const* grads, f
         }
         int bx = (max_n + 255) / 256;
         if (bx > 148 * 8) bx = 148 * 8;
-        adam_multi_kernel<<<dim3(bx, t.count), 256, 0, (cudaStream_t)stream>>>(t, hy, dyn);
-        PAI_CUDA_OK(cudaGetLastError());
+        PAI_CUDA_OK(launch_pdl(adam_multi_kernel, dim3(bx, t.count), dim3(256), 0, (cudaStream_t)stream, 1, t, hy, dyn));
     }
     return 0;
 }

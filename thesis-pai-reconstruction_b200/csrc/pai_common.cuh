@@ -39,6 +39,39 @@ int sm_count(int dev);
 // SMs the persistent (one CTA per SM) kernels may occupy: sm_count minus the reservation of pai_reserve_sms()
 int persistent_ctas(int dev);
 
+// ---- programmatic dependent launch (PDL).  The training step is ~200 dependent launches replayed as one CUDA graph; a
+// kernel launched with `programmaticStreamSerializationAllowed` may be SCHEDULED as soon as every CTA of the previous
+// kernel has executed griddepcontrol.launch_dependents (done at kernel entry), so its launch latency, CTA scheduling and
+// prologue (barrier init, TMEM allocation, tensor-map prefetch) overlap the previous kernel's tail; its own
+// griddepcontrol.wait then blocks until the previous grid has COMPLETED and its memory is visible.  Rule kept by every
+// launch site: a kernel is launched through launch_pdl only if it executes pdl_wait() before its first dependent memory
+// access (kernels with the two instructions launched the ordinary way see them as no-ops).  OPT-IN (PAI_PDL=1): on the
+// graph-replayed training step it measured 0.5-1 % slower than plain serialisation (7.74 against 7.69 ms, A/B on one box) --
+// the graph's kernel-to-kernel gaps are already ~1 us and early-resident CTAs compete with the running kernel's tail.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     int cluster_x, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (cluster_x > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = (unsigned)cluster_x, attr[na].val.clusterDim.y = 1, attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr, cfg.numAttrs = (unsigned)na;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Encodes a bf16 tiled tensor map (rank <= 5, SWIZZLE_128B, zero OOB fill) through the driver
 // entry point fetched at run time, so the library loads on a box without libcuda.
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,

@@ -105,6 +105,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 template <int CIN, bool STREAM>
 __global__ void __launch_bounds__(kThinFpropThreads, 1) thin_conv_fprop_kernel(const ThinFpropParams p) {
+    pdl_launch_dependents();
+    pdl_wait();              // (the set-up below already reads the weight pack written by the optimizer kernels)
     extern __shared__ uint8_t smem_raw[];
     __shared__ ThinPipe ps;
     __shared__ uint64_t ring_full[kThinRing], ring_empty[kThinRing];
@@ -472,6 +474,7 @@ struct __align__(8) ThinWgradPipe {
 template <int CIN>
 __global__ void __launch_bounds__(kThinWgradThreads, 1)
 thin_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const ThinWgradParams p) {
+    pdl_launch_dependents();
     constexpr int N = 16 * CIN;
     constexpr uint32_t kABytes = 2 * 8192, kBBytes = 4096, kStage = kABytes + kBBytes;
     extern __shared__ uint8_t smem_raw[];
@@ -494,6 +497,7 @@ thin_wgrad_kernel(const __grid_constant__ CUtensorMap tm_u, const ThinWgradParam
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = ps.tmem_base;
+    pdl_wait();
 
     if (warp == 0) {
         if (elect_one()) {
@@ -644,6 +648,7 @@ struct __align__(8) ThinPlanePipe {
 __global__ void __launch_bounds__(kThinPlaneThreads, 1)
 thin_convT_plane_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                         const ThinPlaneParams p) {
+    pdl_launch_dependents();
     extern __shared__ uint8_t smem_raw[];
     __shared__ ThinPlanePipe ps;
     __shared__ float ring[3][16][kPlaneW];
@@ -675,6 +680,7 @@ thin_convT_plane_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = ps.tmem_base;
+    pdl_wait();
 
     // Every role walks the same list of P rows: for each image segment [a_lo, a_hi) of the CTA's range, the rows
     // a_lo-1 .. a_hi clipped to the image.
@@ -815,6 +821,8 @@ thin_convT_plane_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_c
 // models/wrapper.py:233):  out[n, oy, ox] = sum_{ky,kx} P[n, oy-1+ky, ox-1+kx, ky*4+kx],  oy < h-1, ox < w-1
 __global__ void __launch_bounds__(256)
 col2im4x4s1_kernel(const float* __restrict__ P, int ldp, int n, int h, int w, float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int oh = h - 1, ow = w - 1;
     const int total = n * oh * ow;
     for (int idx = blockIdx.x * 256 + threadIdx.x; idx < total; idx += gridDim.x * 256) {
@@ -881,13 +889,13 @@ int pai_thin_conv4x4s2_fprop(const float* plane0, const float* plane1, int cin, 
     const int grid = p.tiles < sms ? p.tiles : sms;
     cudaStream_t st = (cudaStream_t)stream_;
     if (cin == 1 && stream)
-        thin_conv_fprop_kernel<1, true><<<grid, kThinFpropThreads, smem, st>>>(p);
+        PAI_CUDA_OK(launch_pdl(thin_conv_fprop_kernel<1, true>, dim3((unsigned)grid), dim3(kThinFpropThreads), smem, st, 1, p));
     else if (cin == 1)
-        thin_conv_fprop_kernel<1, false><<<grid, kThinFpropThreads, smem, st>>>(p);
+        PAI_CUDA_OK(launch_pdl(thin_conv_fprop_kernel<1, false>, dim3((unsigned)grid), dim3(kThinFpropThreads), smem, st, 1, p));
     else if (stream)
-        thin_conv_fprop_kernel<2, true><<<grid, kThinFpropThreads, smem, st>>>(p);
+        PAI_CUDA_OK(launch_pdl(thin_conv_fprop_kernel<2, true>, dim3((unsigned)grid), dim3(kThinFpropThreads), smem, st, 1, p));
     else
-        thin_conv_fprop_kernel<2, false><<<grid, kThinFpropThreads, smem, st>>>(p);
+        PAI_CUDA_OK(launch_pdl(thin_conv_fprop_kernel<2, false>, dim3((unsigned)grid), dim3(kThinFpropThreads), smem, st, 1, p));
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -925,9 +933,9 @@ int pai_thin_conv4x4s2_wgrad(const void* u, int u_ld, int c, const float* plane0
     long long grid = p.blocks / 4 > 0 ? p.blocks / 4 : 1;
     if (grid > sms) grid = sms;
     if (cin == 1)
-        thin_wgrad_kernel<1><<<(int)grid, kThinWgradThreads, smem, (cudaStream_t)stream>>>(tm_u, p);
+        PAI_CUDA_OK(launch_pdl(thin_wgrad_kernel<1>, dim3((unsigned)grid), dim3(kThinWgradThreads), smem, (cudaStream_t)stream, 1, tm_u, p));
     else
-        thin_wgrad_kernel<2><<<(int)grid, kThinWgradThreads, smem, (cudaStream_t)stream>>>(tm_u, p);
+        PAI_CUDA_OK(launch_pdl(thin_wgrad_kernel<2>, dim3((unsigned)grid), dim3(kThinWgradThreads), smem, (cudaStream_t)stream, 1, tm_u, p));
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -965,7 +973,7 @@ int pai_thin_convT4x4s2_plane(const void* x, int n, int h, int w, int c, int x_l
     const long long rows = (long long)n * h;
     long long grid = rows / 4 > 0 ? rows / 4 : 1;          // >= 4 rows per CTA keeps the halo recompute <= 50 %
     if (grid > sms) grid = sms;
-    thin_convT_plane_kernel<<<(int)grid, kThinPlaneThreads, smem, (cudaStream_t)stream>>>(tm_x, tm_w, p);
+    PAI_CUDA_OK(launch_pdl(thin_convT_plane_kernel, dim3((unsigned)grid), dim3(kThinPlaneThreads), smem, (cudaStream_t)stream, 1, tm_x, tm_w, p));
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -978,7 +986,7 @@ int pai_col2im4x4s1(const float* p, int ldp, int n, int h, int w, float* out, vo
     if (sms < 0) return -1;
     long long blocks = (total + 255) / 256;
     if (blocks > sms * 8) blocks = sms * 8;
-    col2im4x4s1_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, ldp, n, h, w, out);
+    PAI_CUDA_OK(launch_pdl(col2im4x4s1_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, 1, p, ldp, n, h, w, out));
     PAI_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -448,6 +448,9 @@ def unet_forward(spec: UnetSpec, x: torch.Tensor, training: bool, save: bool):
     """x: [N, 1, H, W] fp32 (cuda) -> (y [N, 1, H, W] fp32 in (-1, 1), saved-or-None)."""
     L = spec.levels
     n, _, h, w = x.shape
+    if not x.is_cuda or not spec.enc_convs[0].weight.is_cuda:
+        raise RuntimeError("pai_b200: the generator runs on the B200 kernels only: input and parameters must be CUDA tensors "
+                           "(there is no CPU or PyTorch fallback)")
     if h % (1 << L) or w % (1 << L):
         raise RuntimeError(f"pai_b200: input {h}x{w} must be divisible by 2^{L}")
     dev = x.device
@@ -724,6 +727,9 @@ class DiscSpec:
 def disc_forward(spec: DiscSpec, x: torch.Tensor, y: torch.Tensor, save: bool):
     n, _, h, w = x.shape
     dev = x.device
+    if not (x.is_cuda and y.is_cuda and spec.convs[0].weight.is_cuda):
+        raise RuntimeError("pai_b200: the PatchGAN runs on the B200 kernels only: inputs and parameters must be CUDA tensors "
+                           "(there is no CPU or PyTorch fallback)")
     if x.shape[1] != spec.img_ch or y.shape[1] != spec.img_ch:
         raise RuntimeError(f"pai_b200: this PatchGAN takes two {spec.img_ch}-channel images, got {x.shape[1]} and {y.shape[1]}")
     c0 = spec.convs[0]
