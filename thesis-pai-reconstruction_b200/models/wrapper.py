@@ -8,6 +8,7 @@
   graph-free generator forward, then the G step) but evaluates the loss and the three logged metrics
   from ONE pass of the SSIM/PSNR/MSE kernel instead of four torchmetrics calls.
 """
+import os
 from typing import Literal
 
 import torch
@@ -19,6 +20,8 @@ from pai_b200.optim import FusedAdam
 
 from ._lightning import LightningModule
 from .utils import denormalize, init_weights, psnr, rmse, ssim  # noqa: F401  (re-exported like the reference)
+
+BATCH_DISCRIMINATOR_PASSES = os.environ.get("PAI_NO_D_BATCHING", "0") != "1"
 
 _ADAM = dict(lr=2e-4, betas=(0.5, 0.999), eps=1e-7)        # wrapper.py:98-111
 
@@ -122,8 +125,16 @@ class UnetWrapper(LightningModule):
             opt_d = self.optimizers()[1]
             self.toggle_optimizer(opt_d)            # generator frozen: its forward builds no graph
             pred = self.unet(x)
-            target_label = self.discriminator(x, target)
-            pred_label = self.discriminator(x, pred)
+            if BATCH_DISCRIMINATOR_PASSES and x.is_cuda:
+                # D(x, target) and D(x, pred) as ONE pass over 2N samples: the PatchGAN has no BatchNorm, so every sample's
+                # logits and every gradient are what the two separate calls of models/wrapper.py:121-122 give, with half
+                # the kernel launches and no gradient-accumulation adds  [PAI_NO_D_BATCHING=1: two calls]
+                n = x.shape[0]
+                both = self.discriminator(torch.cat([x, x]), torch.cat([target, pred.detach()]))
+                target_label, pred_label = both[:n], both[n:]
+            else:
+                target_label = self.discriminator(x, target)
+                pred_label = self.discriminator(x, pred)
             d_loss = self.discriminator_loss(pred_label, target_label)
             self._pai_log("d_loss", d_loss)
             self.discriminator.zero_grad(set_to_none=True)
