@@ -338,9 +338,6 @@ __device__ __forceinline__ void umma_kblock_lo(uint32_t tmem_d, uint32_t a_lo, u
                                                uint32_t accumulate) {
 #pragma unroll
     for (int k = 0; k < KSTEPS; ++k) {
-#ifdef PAI_EXP_FEWER_MMA   // timing experiment only (wrong results): 1 of 4 k-steps, to tell issue-bound from tensor-bound
-        if (k > 0) break;
-#endif
         if (PAIR)
             asm volatile(
                 "{\n"
