@@ -324,3 +324,27 @@ def test_step_graph_recaptures_and_optimizer_state_round_trips():
     assert steps2 == {5.0}, steps2
     moved = (m2.unet.encoders[3].encode[1].weight.detach() - model_sd["unet.encoders.3.encode.1.weight"]).abs().max().item()
     assert 0 < moved < 1e-3        # one Adam step of lr 2e-4 with the restored moments
+
+
+def test_batched_discriminator_passes_equal_the_two_reference_calls(monkeypatch):
+    """training_step evaluates D(x, target) and D(x, pred) as ONE pass over 2N samples (models/wrapper.py of this repo);
+    the PatchGAN has no BatchNorm, so the logged d_loss and every discriminator weight after the update must equal those
+    of the reference's two separate calls (models/wrapper.py:121-122 of the reference) up to bf16 summation order."""
+    import models.wrapper as W
+    x, target = port.synthetic_pairs(4, seed=77)
+    batch = (x.cuda(), target.cuda())
+    out = {}
+    for batched in (True, False):
+        monkeypatch.setattr(W, "BATCH_DISCRIMINATOR_PASSES", batched)
+        m = _build("gan", seed=5).train()
+        m.training_step(batch, 0)
+        torch.cuda.synchronize()
+        out[batched] = (float(m.logged["d_loss"][-1]), float(m.logged["loss"][-1]),
+                        {k: v.detach().float().clone() for k, v in m.discriminator.named_parameters()})
+    (da, la, pa), (db, lb, pb) = out[True], out[False]
+    assert da == pytest.approx(db, rel=2e-3) and la == pytest.approx(lb, rel=1e-2)
+    for k in pa:
+        # The first Adam step moves every weight by lr * sign-like(g) = +-2e-4: an element whose gradient is rounding
+        # noise may flip (difference 2 lr), everything else must agree to a small fraction of the step
+        d = (pa[k] - pb[k]).abs()
+        assert d.max().item() <= 4.1e-4 and d.mean().item() < 2e-5, (k, d.max().item(), d.mean().item())
