@@ -310,20 +310,39 @@ bn_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long m, int c, int ld, c
         }
         if (MODE != 0) store8(dx + pix * lddx + vec * 8, o);
     };
-    // U pixels (2-3 independent 16-byte loads each) in flight per thread
-    constexpr int U = 4;
+    // Software pipeline: two register sets of U pixels (2-3 independent 16-byte loads each); the loads of the NEXT U pixels
+    // are issued before the arithmetic of the current ones, so a warp's memory latency overlaps its own ~400 instructions
+    // instead of alternating with them (the single-set loop reached 3.0-3.9 TB/s on the read-only reduce modes)
+    constexpr int U = (ACT2 >= 0 || MODE == 1) ? 2 : 4;       // (measured per variant: registers decide the occupancy)
     long long pix = (long long)blockIdx.x * ppb + threadIdx.x / cv;
-    for (; pix + (U - 1) * stride < m; pix += U * stride) {
-        uint4 rv[U], ra[U], rb[U];
+    uint4 rvA[U], raA[U], rbA[U], rvB[U], raB[U], rbB[U];
+    auto load_set = [&](uint4 (&rv)[U], uint4 (&ra)[U], uint4 (&rb)[U], long long p0) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const long long pp = pix + u * stride;
+            const long long pp = p0 + u * stride;
             rv[u] = load_raw(x + pp * ld + vec * 8);
             ra[u] = load_raw(g1 + pp * ldg1 + vec * 8);
             rb[u] = ACT2 >= 0 ? load_raw(g2 + pp * ldg2 + vec * 8) : make_uint4(0, 0, 0, 0);
         }
+    };
+    auto run_set = [&](const uint4 (&rv)[U], const uint4 (&ra)[U], const uint4 (&rb)[U], long long p0) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) body(rv[u], ra[u], rb[u], pix + u * stride);
+        for (int u = 0; u < U; ++u) body(rv[u], ra[u], rb[u], p0 + u * stride);
+    };
+    const long long step = (long long)U * stride;
+    bool have = pix + (U - 1) * stride < m;
+    if (have) load_set(rvA, raA, rbA, pix);
+    while (have) {
+        bool next = pix + step + (U - 1) * stride < m;
+        if (next) load_set(rvB, raB, rbB, pix + step);
+        run_set(rvA, raA, rbA, pix);
+        pix += step;
+        if (!next) break;
+        next = pix + step + (U - 1) * stride < m;
+        if (next) load_set(rvA, raA, rbA, pix + step);
+        run_set(rvB, raB, rbB, pix);
+        pix += step;
+        have = next;
     }
     for (; pix < m; pix += stride) {
         const uint4 v0 = load_raw(x + pix * ld + vec * 8), a0 = load_raw(g1 + pix * ldg1 + vec * 8);
