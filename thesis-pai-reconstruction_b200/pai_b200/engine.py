@@ -20,6 +20,13 @@ The 1- and 2-channel layers (enc0, D0, dec7 and their gradients, the PatchGAN he
 the thin GEMM operand in shared memory (csrc/thin.cu) instead of an im2col / col2im carrier in HBM  [PAI_NO_THIN_DIRECT].
 Train-mode Dropout2d (decoders 0-2 of the default constructor) is a per-(sample, channel) mask applied to the concat
 slot; ``check_path()`` switches the forward to the exact fp32 kernels of csrc/check_f32.cu.
+The <= 8x8 levels run their whole training-mode BatchNorm (+ activation, + Dropout2d mask) and its whole backward as ONE
+launch each (``ops.bn_small_fwd`` / ``bn_small_bwd``)  [PAI_NO_BN_SMALL]; small zeroed temporaries of a step come from one
+pooled fill (``ops.zero_pool``)  [PAI_NO_ZERO_POOL]; eval-mode BatchNorm is folded into the GEMM operands  [PAI_NO_BN_FOLD].
+Models with more than one image channel (the reference's default is 3) send the image through a zero-padded 64-channel
+carrier and the ordinary implicit-GEMM kernels (``_carrier``).
+Library-side switches (read by csrc/): PAI_NO_CTA_PAIR, PAI_NO_PHASE_FUSION, PAI_NO_PHASE_MERGE, PAI_IGEMM_KSUB=1,
+PAI_L2_PREFETCH=1, PAI_PDL=1 (the last two are opt-in experiments that measured no gain).
 """
 from __future__ import annotations
 
